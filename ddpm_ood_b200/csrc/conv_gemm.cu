@@ -1,0 +1,447 @@
+// tcgen05 / TMA implicit-GEMM convolution kernel. See conv_gemm.cuh for the contract.
+#include "conv_gemm.cuh"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "ptx.cuh"
+
+namespace ddpm {
+
+// ------------------------------------------------------------------------------------------------ error string
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <int BN>
+struct Cfg {
+    static constexpr int kStages = (BN == 256) ? 4 : 6;
+    static constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
+    static constexpr int kBBytes = BN * kBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment.
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + C::kStages * C::kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+    uint64_t* full_bar = bars;                     // [kStages]  TMA -> MMA
+    uint64_t* empty_bar = bars + C::kStages;       // [kStages]  MMA -> TMA
+    uint64_t* tfull_bar = bars + 2 * C::kStages;   // [2]        MMA -> epilogue
+    uint64_t* tempty_bar = tfull_bar + 2;          // [2]        epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.n_seg; ++s) ptx::prefetch_tmap(&p.tmA[s]);
+        ptx::prefetch_tmap(&p.tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < C::kStages; ++i) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tfull_bar[i], 1);
+            ptx::mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+
+    if (warp == 0) {
+        // ================================================================= TMA producer (one thread)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_tile = tile / p.num_n_tiles;
+                const int n_tile = tile - m_tile * p.num_n_tiles;
+                int t = m_tile;
+                const int tw = t % p.tiles_w; t /= p.tiles_w;
+                const int th = t % p.tiles_h; t /= p.tiles_h;
+                const int td = t % p.tiles_d; t /= p.tiles_d;
+                const int tn = t;
+                const int w0 = tw * p.bw * p.stride, h0 = th * p.bh * p.stride;
+                const int d0 = td * p.bd * (p.D > 1 ? p.stride : 1);
+                const int n0 = tn * p.bn;
+                const int brow = n_tile * BN + m_tile * p.b_rows_per_mtile;
+                int seg = 0, seg_begin = 0;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    while (kb >= p.seg_kb_end[seg]) { seg_begin = p.seg_kb_end[seg]; ++seg; }
+                    const int local = kb - seg_begin;
+                    const int chunks = p.seg_chunks[seg];
+                    const int tap = local / chunks;
+                    const int chunk = local - tap * chunks;
+                    const int kw = p.seg_kw[seg], kh = p.seg_kh[seg], kd = p.seg_kd[seg];
+                    const int iw = tap % kw;
+                    const int ih = (tap / kw) % kh;
+                    const int id = tap / (kw * kh);
+                    const CUtensorMap* ma = seg == 0 ? &p.tmA[0] : (seg == 1 ? &p.tmA[1] : &p.tmA[2]);
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+                    ptx::tma_load_5d(smem_a + stage * C::kABytes, ma, &full_bar[stage], chunk * kBlockK,
+                                     w0 + iw - (kw >> 1), h0 + ih - (kh >> 1), d0 + id - (kd >> 1), n0);
+                    ptx::tma_load_2d(smem_b + stage * C::kBBytes, &p.tmB, &full_bar[stage], kb * kBlockK, brow);
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_f16(kBlockM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint64_t da = ptx::make_desc_k128(ptx::smem_u32(smem_a + stage * C::kABytes));
+                    const uint64_t db = ptx::make_desc_k128(ptx::smem_u32(smem_b + stage * C::kBBytes));
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        // +32 bytes (>>4 = 2) per 16-element K step inside the 128B swizzle row
+                        ptx::umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(&tfull_bar[as]);  // accumulator ready for the epilogue
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================================================= epilogue (4 warps, 1 row per thread)
+        const int q = warp - 4;  // TMEM lane quarter == warp % 4
+        const int row = q * 32 + lane;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_tile = tile / p.num_n_tiles;
+            const int n_tile = tile - m_tile * p.num_n_tiles;
+            int t = m_tile;
+            const int tw = t % p.tiles_w; t /= p.tiles_w;
+            const int th = t % p.tiles_h; t /= p.tiles_h;
+            const int td = t % p.tiles_d; t /= p.tiles_d;
+            const int tn = t;
+            int r = row;
+            const int w = tw * p.bw + r % p.bw; r /= p.bw;
+            const int h = th * p.bh + r % p.bh; r /= p.bh;
+            const int d = td * p.bd + r % p.bd; r /= p.bd;
+            const int n = tn * p.bn + r;
+            const bool valid = (w < p.W) && (h < p.H) && (d < p.D) && (n < p.N);
+            const size_t pix = ((static_cast<size_t>(n) * p.D + d) * p.H + h) * p.W + w;
+
+            ptx::mbar_wait(&tfull_bar[as], aphase);
+            ptx::tc_fence_after();
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+
+            if (p.mode == EPI_SOFTMAX_BD) {
+                // Attention probabilities. Row = query token; its keys are the `group` columns of its own image:
+                // columns [g0, g0+group) of this tile when group <= 128 (block diagonal), all BN columns otherwise.
+                const int G = p.group < BN ? p.group : BN;
+                const int g0 = p.group < BN ? (row / G) * G : 0;
+                float mx = -INFINITY;
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(t_addr + c * 32, v);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = c * 32 + j;
+                        if (col >= g0 && col < g0 + G) mx = fmaxf(mx, __uint_as_float(v[j]) * p.scale);
+                    }
+                }
+                float sum = 0.f;
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(t_addr + c * 32, v);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = c * 32 + j;
+                        if (col >= g0 && col < g0 + G) sum += __expf(__uint_as_float(v[j]) * p.scale - mx);
+                    }
+                }
+                const float inv = 1.0f / sum;
+                __half* dst = p.out + pix * static_cast<size_t>(p.Cout) + static_cast<size_t>(n_tile) * BN;
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(t_addr + c * 32, v);
+                    ptx::tmem_ld_wait();
+                    if (valid) {
+                        uint32_t packed[16];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const int col = c * 32 + j;
+                            float a = 0.f, b = 0.f;
+                            if (col >= g0 && col < g0 + G) {
+                                a = __expf(__uint_as_float(v[j]) * p.scale - mx) * inv;
+                                b = __expf(__uint_as_float(v[j + 1]) * p.scale - mx) * inv;
+                            }
+                            __half2 hh = __floats2half2_rn(a, b);
+                            packed[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+                        }
+                        uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                    }
+                }
+            } else {
+                const int col_base = n_tile * BN;
+                const float* cadd = p.chan_add ? p.chan_add + static_cast<size_t>(valid ? n : 0) * p.Cout : nullptr;
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(t_addr + c * 32, v);
+                    ptx::tmem_ld_wait();
+                    const int col0 = col_base + c * 32;
+                    if (valid) {
+                        float f[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                        if (p.bias) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                            }
+                        }
+                        if (cadd) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(cadd + col0 + j));
+                                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                            }
+                        }
+                        if (p.residual) {
+                            const uint4* r4 =
+                                reinterpret_cast<const uint4*>(p.residual + pix * static_cast<size_t>(p.Cout) + col0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint4 rv = __ldg(r4 + j);
+                                const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 ff = __half22float2(h2[e]);
+                                    f[8 * j + 2 * e] += ff.x;
+                                    f[8 * j + 2 * e + 1] += ff.y;
+                                }
+                            }
+                        }
+                        if (p.mode == EPI_STORE_VT && col0 >= p.vt_col0) {
+                            // transposed store for the attention V operand: out_vt[pair][c][token-in-pair], where a
+                            // "pair" is the 128 consecutive tokens of one M tile.
+                            const size_t tok = pix;  // token index == pixel index (N*T rows)
+                            const size_t pair = tok >> 7;
+                            const int tin = static_cast<int>(tok & 127);
+                            const int vc = col0 - p.vt_col0;
+                            const int vC = p.Cout - p.vt_col0;
+                            __half* dv = p.out_vt + (pair * vC + vc) * 128 + tin;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) dv[static_cast<size_t>(j) * 128] = __float2half_rn(f[j]);
+                        } else {
+                            uint32_t packed[16];
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                __half2 hh = __floats2half2_rn(f[j], f[j + 1]);
+                                packed[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+                            }
+                            uint4* d4 = reinterpret_cast<uint4*>(p.out + pix * static_cast<size_t>(p.Cout) + col0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) {
+            set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?): %s", cudaGetErrorString(e));
+            return nullptr;
+        }
+        fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    }
+    return fn;
+}
+
+static int pow2ceil(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+int conv_prepare(const ConvProblem& q, int num_sms, ConvLaunch* out) {
+    PFN_encodeTiled encode = get_encode();
+    if (!encode) return 1;
+    memset(out, 0, sizeof(*out));
+    ConvGemmParams& p = out->p;
+    if (q.n_seg < 1 || q.n_seg > kMaxSeg) { set_error("conv: n_seg=%d out of range", q.n_seg); return 2; }
+    if (q.stride != 1 && q.stride != 2) { set_error("conv: stride %d unsupported", q.stride); return 2; }
+    const int sd = q.spatial_dims;
+    if (sd != 2 && sd != 3) { set_error("conv: spatial_dims %d unsupported", sd); return 2; }
+    if (sd == 2 && q.D != 1) { set_error("conv: 2-D problem needs D == 1"); return 2; }
+    const int sW = q.stride, sH = q.stride, sD = (sd == 3) ? q.stride : 1;
+    p.N = q.N;
+    p.W = (q.W + sW - 1) / sW;
+    p.H = (q.H + sH - 1) / sH;
+    p.D = (q.D + sD - 1) / sD;
+    p.stride = q.stride;
+    // tile box: fill W first, then H, D, N; product is always 128 output pixels.
+    p.bw = pow2ceil(p.W) < kBlockM ? pow2ceil(p.W) : kBlockM;
+    int rem = kBlockM / p.bw;
+    p.bh = pow2ceil(p.H) < rem ? pow2ceil(p.H) : rem;
+    rem /= p.bh;
+    p.bd = pow2ceil(p.D) < rem ? pow2ceil(p.D) : rem;
+    rem /= p.bd;
+    p.bn = rem;
+    p.tiles_w = (p.W + p.bw - 1) / p.bw;
+    p.tiles_h = (p.H + p.bh - 1) / p.bh;
+    p.tiles_d = (p.D + p.bd - 1) / p.bd;
+    p.tiles_n = (p.N + p.bn - 1) / p.bn;
+    p.num_m_tiles = p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
+    const int BN = (q.Cout % 256 == 0) ? 256 : 128;
+    if (q.Cout % BN != 0) { set_error("conv: Cout=%d must be a multiple of 128", q.Cout); return 2; }
+    out->block_n = BN;
+    p.num_n_tiles = q.Cout / BN;
+    p.Cout = q.Cout;
+    p.b_rows_per_mtile = q.b_rows_per_mtile;
+    p.mode = q.mode;
+    p.bias = q.bias;
+    p.chan_add = q.chan_add;
+    p.residual = static_cast<const __half*>(q.residual);
+    p.out = static_cast<__half*>(q.out);
+    p.scale = q.scale;
+    p.group = q.group;
+    p.vt_col0 = q.vt_col0;
+    p.out_vt = static_cast<__half*>(q.out_vt);
+    if (q.mode == EPI_SOFTMAX_BD && p.num_n_tiles != 1) { set_error("conv: softmax epilogue needs one N tile"); return 2; }
+
+    p.n_seg = q.n_seg;
+    int kb = 0;
+    size_t ktot = 0;
+    for (int s = 0; s < q.n_seg; ++s) {
+        const ConvSegment& g = q.seg[s];
+        if (g.channels % kBlockK != 0) { set_error("conv: segment channels %d not a multiple of 64", g.channels); return 2; }
+        if (g.ksize != 1 && g.ksize != 3) { set_error("conv: ksize %d unsupported", g.ksize); return 2; }
+        p.seg_chunks[s] = g.channels / kBlockK;
+        p.seg_kw[s] = g.ksize;
+        p.seg_kh[s] = g.ksize;
+        p.seg_kd[s] = (sd == 3) ? g.ksize : 1;
+        const int taps = p.seg_kw[s] * p.seg_kh[s] * p.seg_kd[s];
+        kb += taps * p.seg_chunks[s];
+        p.seg_kb_end[s] = kb;
+        ktot += static_cast<size_t>(taps) * g.channels;
+        // A tensor map over the INPUT tensor (C, W, H, D, N)
+        cuuint64_t gdim[5] = {static_cast<cuuint64_t>(g.channels), static_cast<cuuint64_t>(q.W),
+                              static_cast<cuuint64_t>(q.H), static_cast<cuuint64_t>(q.D),
+                              static_cast<cuuint64_t>(q.N)};
+        cuuint64_t gstr[4];
+        gstr[0] = static_cast<cuuint64_t>(g.channels) * 2;
+        gstr[1] = gstr[0] * q.W;
+        gstr[2] = gstr[1] * q.H;
+        gstr[3] = gstr[2] * q.D;
+        cuuint32_t box[5] = {kBlockK, static_cast<cuuint32_t>(p.bw * sW), static_cast<cuuint32_t>(p.bh * sH),
+                             static_cast<cuuint32_t>(p.bd * sD), static_cast<cuuint32_t>(p.bn)};
+        cuuint32_t estr[5] = {1, static_cast<cuuint32_t>(sW), static_cast<cuuint32_t>(sH),
+                              static_cast<cuuint32_t>(sD), 1};
+        CUresult r = encode(&p.tmA[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(g.ptr), gdim, gstr, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv: cuTensorMapEncodeTiled(A seg %d) failed: %d", s, (int)r); return 3; }
+    }
+    for (int s = q.n_seg; s < kMaxSeg; ++s) p.seg_kb_end[s] = kb;
+    p.num_kb = kb;
+    {
+        cuuint64_t gdim[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(q.w_rows)};
+        cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ktot) * 2};
+        cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(BN)};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(q.weights), gdim, gstr, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv: cuTensorMapEncodeTiled(B) failed: %d", (int)r); return 3; }
+    }
+    const int total = p.num_m_tiles * p.num_n_tiles;
+    out->grid = total < num_sms ? total : num_sms;
+    return 0;
+}
+
+static bool g_attr_set = false;
+int conv_launch(const ConvLaunch& l, cudaStream_t stream) {
+    if (!g_attr_set) {
+        cudaError_t e1 = cudaFuncSetAttribute(conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              Cfg<128>::kSmemBytes);
+        cudaError_t e2 = cudaFuncSetAttribute(conv_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              Cfg<256>::kSmemBytes);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) {
+            set_error("conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+            return 4;
+        }
+        g_attr_set = true;
+    }
+    if (l.block_n == 256)
+        conv_gemm_kernel<256><<<l.grid, 256, Cfg<256>::kSmemBytes, stream>>>(l.p);
+    else
+        conv_gemm_kernel<128><<<l.grid, 256, Cfg<128>::kSmemBytes, stream>>>(l.p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("conv: launch failed: %s", cudaGetErrorString(e)); return 5; }
+    return 0;
+}
+
+}  // namespace ddpm

@@ -1,0 +1,101 @@
+// Implicit-GEMM convolution / linear layer on tcgen05 tensor cores (sm_100a).
+//
+//   D[pixel, cout] = sum_{segment s} sum_{tap t in s} sum_{c} A_s[pixel shifted by t, c] * W[cout, k(s,t,c)]
+//
+// * A operands are NDHWC fp16 tensors read by 5-D TMA boxes (C, W, H, D, N); the 3x3(x3) halo and the zero padding
+//   come from TMA out-of-bounds zero fill, a stride-2 conv from the tensor map's element strides.
+// * Up to three K-segments share one accumulator: the main 3x3 conv plus e.g. the ResnetBlock 1x1 skip conv over the
+//   raw block input (one or two concatenated tensors), so skip + conv2 is ONE launch.
+// * B operand: fp16 weights [Cout][Ktot], K-major, K ordered segment -> tap -> channel.
+// * 128-pixel x BN-channel tiles, fp32 accumulators double-buffered in TMEM, persistent CTAs, warp-specialised:
+//   warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue.
+// * Epilogue: + bias[c] (+ per-(image,channel) add, the timestep embedding) (+ residual tensor) -> fp16 NDHWC.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ddpm {
+
+constexpr int kMaxSeg = 3;
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 fp16 = 128 B = one swizzle row
+
+enum EpilogueMode : int {
+    EPI_STORE = 0,       // out[pixel, c] = acc + bias (+chan_add) (+residual)
+    EPI_SOFTMAX_BD = 1,  // block-diagonal softmax over groups of T columns (attention scores), writes P fp16
+    EPI_STORE_VT = 2,    // like STORE but columns >= vt_col0 are written transposed ([pair][c][128 tokens])
+};
+
+struct ConvGemmParams {
+    CUtensorMap tmA[kMaxSeg];
+    CUtensorMap tmB;
+    // K schedule
+    int n_seg;
+    int seg_kb_end[kMaxSeg];  // exclusive prefix end in k-blocks
+    int seg_chunks[kMaxSeg];  // channels/64
+    int seg_kw[kMaxSeg], seg_kh[kMaxSeg], seg_kd[kMaxSeg];  // tap extents (1 or 3)
+    int num_kb;
+    // output geometry (output pixels)
+    int N, D, H, W;
+    int bn, bd, bh, bw;                       // tile box, product == 128
+    int tiles_n, tiles_d, tiles_h, tiles_w;   // tile counts per dim
+    int num_m_tiles, num_n_tiles;
+    int stride;                               // input coord = out*stride + tap - (k/2)
+    int Cout;                                 // real output channels (row pitch of out)
+    int b_rows_per_mtile;                     // batched GEMM: extra B row offset per m tile (0 = shared weights)
+    // epilogue
+    int mode;
+    const float* bias;        // [Cout] or null
+    const float* chan_add;    // [N][Cout] or null
+    const __half* residual;   // same layout as out, or null
+    __half* out;
+    float scale;              // EPI_SOFTMAX_BD: logits scale
+    int group;                // EPI_SOFTMAX_BD: tokens per image (block size)
+    int vt_col0;              // EPI_STORE_VT: first transposed column
+    __half* out_vt;           // EPI_STORE_VT: destination of the transposed columns
+};
+
+// Host side: filled by conv_prepare(), launched by conv_launch().
+struct ConvLaunch {
+    ConvGemmParams p;
+    int block_n;  // 128 or 256
+    int grid;
+};
+
+struct ConvSegment {
+    const void* ptr;  // NDHWC fp16
+    int channels;     // multiple of 64
+    int ksize;        // 1 or 3 (per spatial dim)
+};
+
+struct ConvProblem {
+    int spatial_dims;  // 2 or 3 (2 => D == 1)
+    int N, D, H, W;    // INPUT spatial dims
+    int stride;        // 1 or 2
+    int n_seg;
+    ConvSegment seg[kMaxSeg];
+    const void* weights;  // fp16 [w_rows][Ktot]
+    int w_rows;           // rows in the weight matrix (Cout, or batched)
+    int Cout;
+    int b_rows_per_mtile;
+    int mode;
+    const float* bias;
+    const float* chan_add;
+    const void* residual;
+    void* out;
+    float scale;
+    int group;
+    int vt_col0;
+    void* out_vt;
+};
+
+// returns 0 on success; on failure sets the thread-local error string (see ddpm_last_error()).
+int conv_prepare(const ConvProblem& prob, int num_sms, ConvLaunch* out);
+int conv_launch(const ConvLaunch& l, cudaStream_t stream);
+
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+}  // namespace ddpm

@@ -1,0 +1,88 @@
+"""Thin Python wrappers over the C ABI building blocks (torch tensors in, torch tensors out).
+
+torch is used only to own device memory and name the stream; all arithmetic happens in libddpm_ood_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from ._lib import ConvArgs, check, current_stream_ptr, lib
+
+EPI_STORE, EPI_SOFTMAX_BD, EPI_STORE_VT = 0, 1, 2
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def pack_conv_weight(w: torch.Tensor, dst: torch.Tensor, koff: int = 0) -> None:
+    """w: fp32 [Cout, Cin, *k] on device; dst: fp16 [rows, Ktot] packed matrix (written at column offset koff)."""
+    assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
+    assert dst.dtype == torch.float16 and dst.is_contiguous()
+    cout, cin = w.shape[0], w.shape[1]
+    taps = 1
+    for k in w.shape[2:]:
+        taps *= k
+    check(lib().ddpm_pack_conv_weight(w.data_ptr(), cout, cin, taps, dst.data_ptr(), dst.shape[1], koff,
+                                      current_stream_ptr()), "ddpm_pack_conv_weight")
+
+
+def conv_forward(
+    segs: Sequence[torch.Tensor],
+    ksizes: Sequence[int],
+    weights: torch.Tensor,
+    cout: int,
+    *,
+    stride: int = 1,
+    bias: Optional[torch.Tensor] = None,
+    chan_add: Optional[torch.Tensor] = None,
+    residual: Optional[torch.Tensor] = None,
+    out: Optional[torch.Tensor] = None,
+    mode: int = EPI_STORE,
+    b_rows_per_mtile: int = 0,
+    scale: float = 1.0,
+    group: int = 0,
+    vt_col0: int = 0,
+    out_vt: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """segs: fp16 channels-last tensors [N, (D,) H, W, C]; weights: packed fp16 [rows, Ktot]."""
+    x0 = segs[0]
+    sd = x0.dim() - 2
+    assert sd in (2, 3)
+    if sd == 2:
+        n, h, w = x0.shape[0], x0.shape[1], x0.shape[2]
+        d = 1
+    else:
+        n, d, h, w = x0.shape[0], x0.shape[1], x0.shape[2], x0.shape[3]
+    a = ConvArgs()
+    a.spatial_dims = sd
+    a.N, a.D, a.H, a.W = n, d, h, w
+    a.stride = stride
+    a.n_seg = len(segs)
+    for i, s in enumerate(segs):
+        assert s.dtype == torch.float16 and s.is_contiguous() and s.is_cuda
+        a.seg_ptr[i] = s.data_ptr()
+        a.seg_channels[i] = s.shape[-1]
+        a.seg_ksize[i] = ksizes[i]
+    a.weights = weights.data_ptr()
+    a.w_rows = weights.shape[0]
+    a.Cout = cout
+    a.b_rows_per_mtile = b_rows_per_mtile
+    a.mode = mode
+    a.bias = _ptr(bias)
+    a.chan_add = _ptr(chan_add)
+    a.residual = _ptr(residual)
+    so = lambda v: (v + stride - 1) // stride  # noqa: E731
+    if out is None:
+        shape = (n, so(h), so(w), cout) if sd == 2 else (n, so(d), so(h), so(w), cout)
+        out = torch.empty(shape, dtype=torch.float16, device=x0.device)
+    a.out = out.data_ptr()
+    a.scale = scale
+    a.group = group
+    a.vt_col0 = vt_col0
+    a.out_vt = _ptr(out_vt)
+    check(lib().ddpm_conv_forward(C.byref(a), current_stream_ptr()), "ddpm_conv_forward")
+    return out

@@ -1,0 +1,99 @@
+"""GPU parity of the tcgen05 implicit-GEMM conv kernel against plain PyTorch fp32 convs of the same fp16-rounded
+operands (kernel-level numerics; the end-to-end parity against oracle/ lives in test_unet_gpu.py)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _nhwc(x):  # [N,C,*sp] fp32 -> channels-last fp16 contiguous [N,*sp,C]
+    perm = (0,) + tuple(range(2, x.dim())) + (1,)
+    return x.permute(*perm).contiguous().half()
+
+
+def _to_ncx(y):  # channels-last -> [N,C,*sp] fp32
+    perm = (0, y.dim() - 1) + tuple(range(1, y.dim() - 1))
+    return y.permute(*perm).float()
+
+
+def _run_case(sd, n, sp, segs, cout, stride=1, use_bias=True, use_cadd=False, use_res=False, seed=0):
+    """segs: list of (channels, ksize). Returns (rel_l2, max_abs_err/max_ref)."""
+    from ddpm_ood_b200 import ops
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    dev = "cuda"
+    conv = F.conv2d if sd == 2 else F.conv3d
+    xs, ws = [], []
+    ktot = sum(c * (k ** sd) for c, k in segs)
+    wp = torch.zeros(cout, ktot, dtype=torch.float16, device=dev)
+    koff = 0
+    ref = None
+    for c, k in segs:
+        x = torch.randn((n, c) + tuple(sp), generator=g, device=dev)
+        w = torch.randn((cout, c) + (k,) * sd, generator=g, device=dev) * (1.0 / (c * k ** sd) ** 0.5)
+        x16 = _nhwc(x)
+        ops.pack_conv_weight(w.contiguous(), wp, koff)
+        koff += c * k ** sd
+        xs.append(x16)
+        r = conv(_to_ncx(x16), w.half().float(), stride=stride, padding=k // 2)
+        ref = r if ref is None else ref + r
+    bias = torch.randn(cout, generator=g, device=dev) if use_bias else None
+    cadd = torch.randn(n, cout, generator=g, device=dev) if use_cadd else None
+    if bias is not None:
+        ref = ref + bias.view(1, -1, *([1] * sd))
+    if cadd is not None:
+        ref = ref + cadd.view(n, -1, *([1] * sd))
+    res16 = None
+    if use_res:
+        res = torch.randn(ref.shape, generator=g, device=dev)
+        res16 = _nhwc(res)
+        ref = ref + _to_ncx(res16)
+    out = ops.conv_forward(xs, [k for _, k in segs], wp, cout, stride=stride, bias=bias, chan_add=cadd,
+                           residual=res16)
+    torch.cuda.synchronize()
+    got = _to_ncx(out)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    err = (got - ref)
+    rel = (err.norm() / ref.norm()).item()
+    mx = (err.abs().max() / ref.abs().max()).item()
+    return rel, mx
+
+
+CASES = {
+    "3x3_32px_128to128": dict(sd=2, n=4, sp=(32, 32), segs=[(128, 3)], cout=128),
+    "3x3_16px_128to256_bias_temb_res": dict(sd=2, n=4, sp=(16, 16), segs=[(128, 3)], cout=256, use_cadd=True,
+                                            use_res=True),
+    "3x3_8px_256to256_oddN": dict(sd=2, n=3, sp=(8, 8), segs=[(256, 3)], cout=256),
+    "3x3_stride2_32to16": dict(sd=2, n=4, sp=(32, 32), segs=[(128, 3)], cout=128, stride=2),
+    "3x3_stride2_16to8_256": dict(sd=2, n=5, sp=(16, 16), segs=[(256, 3)], cout=256, stride=2),
+    "resnet_conv2_plus_1x1_skip_concat": dict(sd=2, n=4, sp=(16, 16), segs=[(256, 3), (256, 1), (128, 1)], cout=256),
+    "linear_qkv": dict(sd=2, n=1, sp=(1, 512), segs=[(256, 1)], cout=768),
+    "3x3_28px": dict(sd=2, n=3, sp=(28, 28), segs=[(128, 3)], cout=128),
+    "3x3_7px": dict(sd=2, n=5, sp=(7, 7), segs=[(256, 3)], cout=256),
+    "3x3_64px_384to128": dict(sd=2, n=2, sp=(64, 64), segs=[(384, 3)], cout=128),
+    "3x3x3_8vox_128to128": dict(sd=3, n=2, sp=(8, 8, 8), segs=[(128, 3)], cout=128),
+    "3x3x3_stride2_8to4": dict(sd=3, n=3, sp=(8, 8, 8), segs=[(128, 3)], cout=256, stride=2),
+    "3x3x3_2vox_256": dict(sd=3, n=20, sp=(2, 2, 2), segs=[(256, 3)], cout=256),
+    "many_tiles_persistent": dict(sd=2, n=64, sp=(32, 32), segs=[(128, 3)], cout=128, use_res=True),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_conv_case(name):
+    rel, mx = _run_case(**CASES[name])
+    # fp16 operands are shared with the reference; what remains is fp32 accumulation order + the fp16 output rounding
+    # (2^-11 relative).
+    assert rel < 6e-4, (name, rel, mx)
+    assert mx < 3e-3, (name, rel, mx)
+
+
+if __name__ == "__main__":
+    for name, kw in CASES.items():
+        try:
+            rel, mx = _run_case(**kw)
+            print(f"{name:40s} rel_l2={rel:.3e} max={mx:.3e}", flush=True)
+        except Exception as e:  # noqa: BLE001
+            print(f"{name:40s} EXC {type(e).__name__}: {e}", flush=True)
