@@ -9,6 +9,7 @@ from pathlib import Path
 
 _CSRC = Path(__file__).resolve().parent / "csrc"
 LIB_PATH = _CSRC / "libddpm_ood_b200.so"
+MAX_LEVELS = 8
 
 _lib = None
 
@@ -38,12 +39,74 @@ class ConvArgs(C.Structure):
     ]
 
 
+class UNetConfig(C.Structure):
+    _fields_ = [
+        ("spatial_dims", C.c_int),
+        ("in_channels", C.c_int), ("out_channels", C.c_int),
+        ("num_levels", C.c_int),
+        ("num_channels", C.c_int * MAX_LEVELS),
+        ("attention_levels", C.c_int * MAX_LEVELS),
+        ("num_res_blocks", C.c_int * MAX_LEVELS),
+        ("num_head_channels", C.c_int * MAX_LEVELS),
+        ("norm_num_groups", C.c_int),
+        ("norm_eps", C.c_float),
+    ]
+
+
+class PlmsStep(C.Structure):
+    _fields_ = [
+        ("c", C.c_float * 4),
+        ("vA", C.c_float), ("vB", C.c_float),
+        ("A", C.c_float), ("Bc", C.c_float),
+        ("use_stash", C.c_int),
+        ("write_stash", C.c_int),
+        ("push", C.c_int),
+        ("slot_new", C.c_int),
+        ("slot", C.c_int * 3),
+    ]
+
+
 class DdpmError(RuntimeError):
     pass
 
 
+# name -> (restype, argtypes); every symbol include/ddpm_ood_b200.h declares.
+SIGNATURES = {
+    "ddpm_last_error": (C.c_char_p, []),
+    "ddpm_abi_version": (C.c_int, []),
+    "ddpm_conv_forward": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    "ddpm_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong,
+                                        C.c_longlong, C.c_void_p]),
+    "ddpm_unet_create": (C.c_int, [C.POINTER(UNetConfig), C.POINTER(C.c_void_p)]),
+    "ddpm_unet_destroy": (None, [C.c_void_p]),
+    "ddpm_unet_set_param": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "ddpm_unet_finalize": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ddpm_unet_workspace_bytes": (C.c_longlong, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ddpm_unet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "ddpm_unet_launch_count": (C.c_longlong, [C.c_void_p]),
+    "ddpm_add_noise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p,
+                                 C.c_int, C.c_longlong, C.c_void_p]),
+    "ddpm_plms_update": (C.c_int, [C.c_void_p, C.POINTER(PlmsStep), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_longlong, C.c_void_p]),
+    "ddpm_unet_run_chain": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(PlmsStep), C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_longlong, C.c_void_p]),
+    "ddpm_clamp_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong,
+                                 C.c_void_p]),
+    "ddpm_lpips_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "ddpm_lpips_destroy": (None, [C.c_void_p]),
+    "ddpm_lpips_set_param": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "ddpm_lpips_finalize": (C.c_int, [C.c_void_p]),
+    "ddpm_lpips_workspace_bytes": (C.c_longlong, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "ddpm_lpips_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "ddpm_lpips_launch_count": (C.c_longlong, [C.c_void_p]),
+}
+
+
 def lib() -> C.CDLL:
-    """Load the shared library (building it first if the sources are newer and nvcc is present)."""
+    """Load the shared library (building it first if it is missing and nvcc is present)."""
     global _lib
     if _lib is not None:
         return _lib
@@ -54,13 +117,10 @@ def lib() -> C.CDLL:
     if not LIB_PATH.exists():
         raise DdpmError(f"{LIB_PATH} is missing: build it with `python -m ddpm_ood_b200.csrc.build`")
     L = C.CDLL(str(LIB_PATH))
-    L.ddpm_last_error.restype = C.c_char_p
-    L.ddpm_abi_version.restype = C.c_int
-    L.ddpm_conv_forward.argtypes = [C.POINTER(ConvArgs), C.c_void_p]
-    L.ddpm_conv_forward.restype = C.c_int
-    L.ddpm_pack_conv_weight.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong,
-                                        C.c_longlong, C.c_void_p]
-    L.ddpm_pack_conv_weight.restype = C.c_int
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)  # AttributeError here means header and library disagree
+        fn.restype = res
+        fn.argtypes = args
     _lib = L
     return L
 

@@ -3,6 +3,7 @@
 
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <string.h>
 
 #include "conv_gemm.cuh"
 
@@ -62,6 +63,7 @@ int ddpm_conv_forward(const ddpm_conv_args* a, void* stream) {
     q.mode = a->mode;
     q.bias = a->bias;
     q.chan_add = a->chan_add;
+    q.chan_add_stride = a->Cout;
     q.residual = a->residual;
     q.out = a->out;
     q.scale = a->scale;
@@ -86,5 +88,145 @@ int ddpm_pack_conv_weight(const float* w, int Cout, int Cin, int taps, void* dst
     if (e != cudaSuccess) { ddpm::set_error("pack_conv_weight: %s", cudaGetErrorString(e)); return 5; }
     return 0;
 }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ UNet / scheduler
+#include "engine.cuh"
+
+static_assert(sizeof(ddpm_plms_step) == sizeof(ddpm::PlmsStep), "ddpm_plms_step must mirror ddpm::PlmsStep");
+static_assert(DDPM_MAX_LEVELS == ddpm::kMaxLevels, "level capacity mismatch");
+
+static ddpm::PlmsStep to_step(const ddpm_plms_step& s) {
+    ddpm::PlmsStep o;
+    memcpy(&o, &s, sizeof(o));
+    return o;
+}
+
+extern "C" {
+
+int ddpm_unet_create(const ddpm_unet_config* cfg, void** handle) {
+    if (!cfg || !handle) { ddpm::set_error("ddpm_unet_create: null argument"); return 2; }
+    ddpm::UNetConfig c{};
+    c.spatial_dims = cfg->spatial_dims;
+    c.in_channels = cfg->in_channels;
+    c.out_channels = cfg->out_channels;
+    c.num_levels = cfg->num_levels;
+    for (int i = 0; i < DDPM_MAX_LEVELS; ++i) {
+        c.num_channels[i] = cfg->num_channels[i];
+        c.attention_levels[i] = cfg->attention_levels[i];
+        c.num_res_blocks[i] = cfg->num_res_blocks[i];
+        c.num_head_channels[i] = cfg->num_head_channels[i];
+    }
+    c.norm_num_groups = cfg->norm_num_groups;
+    c.norm_eps = cfg->norm_eps;
+    ddpm::UNet* u = new ddpm::UNet(c);
+    int rc = u->init();
+    if (rc) { delete u; *handle = nullptr; return rc; }
+    *handle = u;
+    return 0;
+}
+
+void ddpm_unet_destroy(void* handle) { delete static_cast<ddpm::UNet*>(handle); }
+
+int ddpm_unet_set_param(void* handle, const char* name, const float* data, long long numel, void* stream) {
+    if (!handle || !name || !data) { ddpm::set_error("ddpm_unet_set_param: null argument"); return 2; }
+    return static_cast<ddpm::UNet*>(handle)->set_param(name, data, numel, static_cast<cudaStream_t>(stream));
+}
+
+int ddpm_unet_finalize(void* handle, void* stream) {
+    if (!handle) { ddpm::set_error("ddpm_unet_finalize: null handle"); return 2; }
+    return static_cast<ddpm::UNet*>(handle)->finalize(static_cast<cudaStream_t>(stream));
+}
+
+long long ddpm_unet_workspace_bytes(void* handle, int N, int D, int H, int W) {
+    if (!handle) { ddpm::set_error("ddpm_unet_workspace_bytes: null handle"); return 0; }
+    return static_cast<long long>(static_cast<ddpm::UNet*>(handle)->workspace_bytes(N, D, H, W));
+}
+
+int ddpm_unet_forward(void* handle, const float* x, const long long* timesteps, float* out, int N, int D, int H, int W,
+                      void* workspace, long long workspace_bytes, void* stream) {
+    if (!handle || !x || !timesteps || !out || !workspace) { ddpm::set_error("ddpm_unet_forward: null argument"); return 2; }
+    return static_cast<ddpm::UNet*>(handle)->forward(x, timesteps, 0, out, N, D, H, W, workspace,
+                                                     static_cast<size_t>(workspace_bytes),
+                                                     static_cast<cudaStream_t>(stream));
+}
+
+long long ddpm_unet_launch_count(void* handle) {
+    return handle ? static_cast<ddpm::UNet*>(handle)->launches() : 0;
+}
+
+int ddpm_add_noise(const float* x0, const float* noise, const float* alphas_cumprod, const long long* timesteps,
+                   int t_uniform, float b_scale, float* out, int N, long long per_image, void* stream) {
+    return ddpm::add_noise(x0, noise, alphas_cumprod, timesteps, t_uniform, b_scale, out, N, per_image,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int ddpm_plms_update(const float* model_output, const ddpm_plms_step* step, float* ring, float* stash,
+                     const float* sample_in, float* sample_out, long long numel, void* stream) {
+    if (!step) { ddpm::set_error("ddpm_plms_update: null step"); return 2; }
+    return ddpm::plms_update(model_output, to_step(*step), ring, stash, sample_in, sample_out, numel,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int ddpm_unet_run_chain(void* handle, int n_steps, const int* timesteps, const ddpm_plms_step* steps, float* sample,
+                        float* ring, float* stash, int N, int D, int H, int W, void* workspace,
+                        long long workspace_bytes, void* stream) {
+    if (!handle || !timesteps || !steps || !sample || !ring || !stash || !workspace) {
+        ddpm::set_error("ddpm_unet_run_chain: null argument");
+        return 2;
+    }
+    ddpm::UNet* u = static_cast<ddpm::UNet*>(handle);
+    for (int i = 0; i < n_steps; ++i) {
+        const ddpm::PlmsStep st = to_step(steps[i]);
+        int rc = u->forward(sample, nullptr, timesteps[i], nullptr, N, D, H, W, workspace,
+                            static_cast<size_t>(workspace_bytes), static_cast<cudaStream_t>(stream), &st, ring, stash,
+                            sample);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int ddpm_clamp_mse(const float* x, const float* x0, float b_scale, float* recon, float* mse, int N,
+                   long long per_image, void* stream) {
+    return ddpm::clamp_mse(x, x0, b_scale, recon, mse, N, per_image, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ LPIPS
+#include "lpips.cuh"
+
+extern "C" {
+
+int ddpm_lpips_create(void** handle) {
+    if (!handle) { ddpm::set_error("ddpm_lpips_create: null argument"); return 2; }
+    ddpm::Lpips* l = new ddpm::Lpips();
+    int rc = l->init();
+    if (rc) { delete l; *handle = nullptr; return rc; }
+    *handle = l;
+    return 0;
+}
+void ddpm_lpips_destroy(void* handle) { delete static_cast<ddpm::Lpips*>(handle); }
+int ddpm_lpips_set_param(void* handle, const char* name, const float* data, long long numel, void* stream) {
+    if (!handle || !name || !data) { ddpm::set_error("ddpm_lpips_set_param: null argument"); return 2; }
+    return static_cast<ddpm::Lpips*>(handle)->set_param(name, data, numel, static_cast<cudaStream_t>(stream));
+}
+int ddpm_lpips_finalize(void* handle) {
+    if (!handle) { ddpm::set_error("ddpm_lpips_finalize: null handle"); return 2; }
+    return static_cast<ddpm::Lpips*>(handle)->finalize();
+}
+long long ddpm_lpips_workspace_bytes(void* handle, int B, int H, int W) {
+    if (!handle) return 0;
+    return static_cast<long long>(static_cast<ddpm::Lpips*>(handle)->workspace_bytes(B, H, W));
+}
+int ddpm_lpips_forward(void* handle, const float* in0, const float* in1, float* out, int B, int C, int H, int W,
+                       int normalize, void* workspace, long long workspace_bytes, void* stream) {
+    if (!handle || !in0 || !in1 || !out || !workspace) { ddpm::set_error("ddpm_lpips_forward: null argument"); return 2; }
+    return static_cast<ddpm::Lpips*>(handle)->forward(in0, in1, out, B, C, H, W, normalize != 0, workspace,
+                                                      static_cast<size_t>(workspace_bytes),
+                                                      static_cast<cudaStream_t>(stream));
+}
+long long ddpm_lpips_launch_count(void* handle) { return handle ? static_cast<ddpm::Lpips*>(handle)->launches() : 0; }
 
 }  // extern "C"

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
                 }
             } else {
                 const int col_base = n_tile * BN;
-                const float* cadd = p.chan_add ? p.chan_add + static_cast<size_t>(valid ? n : 0) * p.Cout : nullptr;
+                const float* cadd = p.chan_add ? p.chan_add + static_cast<size_t>(valid ? n : 0) * p.chan_add_stride : nullptr;
                 for (int c = 0; c < BN / 32; ++c) {
                     uint32_t v[32];
                     ptx::tmem_ld_32x32(t_addr + c * 32, v);
@@ -364,6 +364,7 @@ int conv_prepare(const ConvProblem& q, int num_sms, ConvLaunch* out) {
     p.mode = q.mode;
     p.bias = q.bias;
     p.chan_add = q.chan_add;
+    p.chan_add_stride = q.chan_add_stride;
     p.residual = static_cast<const __half*>(q.residual);
     p.out = static_cast<__half*>(q.out);
     p.scale = q.scale;

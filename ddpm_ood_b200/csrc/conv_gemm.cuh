@@ -48,7 +48,8 @@ struct ConvGemmParams {
     // epilogue
     int mode;
     const float* bias;        // [Cout] or null
-    const float* chan_add;    // [N][Cout] or null
+    const float* chan_add;    // per-image channel offsets (timestep embedding) or null: chan_add[n*chan_add_stride + c]
+    long long chan_add_stride;  // row pitch in floats (0 = one shared row)
     const __half* residual;   // same layout as out, or null
     __half* out;
     float scale;              // EPI_SOFTMAX_BD: logits scale
@@ -83,6 +84,7 @@ struct ConvProblem {
     int mode;
     const float* bias;
     const float* chan_add;
+    long long chan_add_stride;
     const void* residual;
     void* out;
     float scale;

@@ -1,0 +1,641 @@
+// DiffusionModelUNet forward engine. See engine.cuh.
+#include "engine.cuh"
+
+#include <math.h>
+#include <string.h>
+
+namespace ddpm {
+
+int num_sms();  // api.cu
+
+__global__ void add_vec_kernel(const float* a, const float* b, float* out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);
+}
+
+__global__ void pack_conv_weight_kernel2(const float* __restrict__ w, int Cout, int Cin, int taps,
+                                         __half* __restrict__ dst, long long ktot, long long koff) {
+    const long long total = static_cast<long long>(Cout) * Cin * taps;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ci = static_cast<int>(i % Cin);
+        const long long r = i / Cin;
+        const int tap = static_cast<int>(r % taps);
+        const int co = static_cast<int>(r / taps);
+        dst[co * ktot + koff + static_cast<long long>(tap) * Cin + ci] =
+            __float2half_rn(w[(static_cast<long long>(co) * Cin + ci) * taps + tap]);
+    }
+}
+
+__global__ void nhwc_half_to_nchw_kernel(const __half* __restrict__ y, float* __restrict__ out, int C, long long S) {
+    __shared__ float tile[32][33];
+    const long long n = blockIdx.z;
+    const long long s0 = static_cast<long long>(blockIdx.x) * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const long long s = s0 + i;
+        const int c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && s < S) ? __half2float(y[(n * S + s) * C + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i;
+        const long long s = s0 + threadIdx.x;
+        if (c < C && s < S) out[(n * C + c) * S + s] = tile[threadIdx.x][i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ construction
+UNet::UNet(const UNetConfig& cfg) : cfg_(cfg), E_(cfg.num_channels[0]) {}
+
+UNet::~UNet() {
+    if (f32_arena_) cudaFree(f32_arena_);
+    if (f16_arena_) cudaFree(f16_arena_);
+}
+
+template <typename T>
+T* UNet::arena_alloc(size_t count, bool half_arena) {
+    const size_t aligned = (count + 127) & ~size_t(127);  // 256 B (fp16) / 512 B (fp32) granules keep TMA bases aligned
+    if (half_arena) {
+        T* p = sizing_ ? nullptr : reinterpret_cast<T*>(f16_arena_ + f16_used_);
+        f16_used_ += aligned;
+        return p;
+    }
+    T* p = sizing_ ? nullptr : reinterpret_cast<T*>(f32_arena_ + f32_used_);
+    f32_used_ += aligned;
+    return p;
+}
+
+void UNet::add_copy(const std::string& name, float* dst, long long numel) {
+    if (sizing_) return;
+    ParamSlot s{};
+    s.kind = ParamSlot::COPY_F32;
+    s.dst = dst;
+    s.numel = numel;
+    slots_[name] = s;
+}
+void UNet::add_pack(const std::string& name, __half* dst, int Cout, int Cin, int taps, long long ktot,
+                    long long koff) {
+    if (sizing_) return;
+    ParamSlot s{};
+    s.kind = ParamSlot::PACK_CONV;
+    s.dst = dst;
+    s.numel = static_cast<long long>(Cout) * Cin * taps;
+    s.Cout = Cout; s.Cin = Cin; s.taps = taps; s.ktot = ktot; s.koff = koff;
+    slots_[name] = s;
+}
+
+ResW UNet::make_res(const std::string& prefix, int c0, int c1, int cout) {
+    const int taps = cfg_.spatial_dims == 3 ? 27 : 9;
+    ResW r{};
+    r.prefix = prefix;
+    r.c0 = c0; r.c1 = c1; r.cout = cout;
+    const int cin = c0 + c1;
+    r.skip_conv = (cin != cout);
+    r.g1 = arena_alloc<float>(cin, false);
+    r.b1 = arena_alloc<float>(cin, false);
+    r.g2 = arena_alloc<float>(cout, false);
+    r.b2 = arena_alloc<float>(cout, false);
+    r.bias1 = arena_alloc<float>(cout, false);
+    r.bias2 = arena_alloc<float>(cout, false);
+    r.bias_skip = r.skip_conv ? arena_alloc<float>(cout, false) : nullptr;
+    r.bias2_total = arena_alloc<float>(cout, false);
+    const long long k1 = static_cast<long long>(taps) * cin;
+    const long long k2 = static_cast<long long>(taps) * cout + (r.skip_conv ? cin : 0);
+    r.w1 = arena_alloc<__half>(static_cast<size_t>(cout) * k1, true);
+    r.w2 = arena_alloc<__half>(static_cast<size_t>(cout) * k2, true);
+    r.temb_off = P_;
+    add_copy(prefix + ".norm1.weight", r.g1, cin);
+    add_copy(prefix + ".norm1.bias", r.b1, cin);
+    add_copy(prefix + ".norm2.weight", r.g2, cout);
+    add_copy(prefix + ".norm2.bias", r.b2, cout);
+    add_pack(prefix + ".conv1.conv.weight", r.w1, cout, cin, taps, k1, 0);
+    add_copy(prefix + ".conv1.conv.bias", r.bias1, cout);
+    add_pack(prefix + ".conv2.conv.weight", r.w2, cout, cout, taps, k2, 0);
+    add_copy(prefix + ".conv2.conv.bias", r.bias2, cout);
+    if (r.skip_conv) {
+        add_pack(prefix + ".skip_connection.conv.weight", r.w2, cout, cin, 1, k2, static_cast<long long>(taps) * cout);
+        add_copy(prefix + ".skip_connection.conv.bias", r.bias_skip, cout);
+    }
+    if (!sizing_) {
+        add_copy(prefix + ".time_emb_proj.weight", tp_w_ + static_cast<size_t>(P_) * 4 * E_,
+                 static_cast<long long>(cout) * 4 * E_);
+        add_copy(prefix + ".time_emb_proj.bias", tp_b_ + P_, cout);
+    }
+    P_ += cout;
+    return r;
+}
+
+AttnW UNet::make_attn(const std::string& prefix, int C, int head_channels) {
+    AttnW a{};
+    a.prefix = prefix;
+    a.C = C;
+    a.heads = head_channels > 0 ? C / head_channels : 1;
+    a.g = arena_alloc<float>(C, false);
+    a.b = arena_alloc<float>(C, false);
+    a.bqkv = arena_alloc<float>(3 * C, false);
+    a.bproj = arena_alloc<float>(C, false);
+    a.wqkv = arena_alloc<__half>(static_cast<size_t>(3) * C * C, true);
+    a.wproj = arena_alloc<__half>(static_cast<size_t>(C) * C, true);
+    add_copy(prefix + ".norm.weight", a.g, C);
+    add_copy(prefix + ".norm.bias", a.b, C);
+    const char* names[3] = {"to_q", "to_k", "to_v"};
+    for (int i = 0; i < 3; ++i) {
+        add_pack(prefix + "." + names[i] + ".weight", sizing_ ? nullptr : a.wqkv + static_cast<size_t>(i) * C * C, C, C,
+                 1, C, 0);
+        add_copy(prefix + "." + names[i] + ".bias", sizing_ ? nullptr : a.bqkv + i * C, C);
+    }
+    add_pack(prefix + ".proj_attn.weight", a.wproj, C, C, 1, C, 0);
+    add_copy(prefix + ".proj_attn.bias", a.bproj, C);
+    return a;
+}
+
+int UNet::init() {
+    const UNetConfig& c = cfg_;
+    if (c.num_levels < 1 || c.num_levels > kMaxLevels) { set_error("unet: num_levels=%d unsupported", c.num_levels); return 2; }
+    if (c.spatial_dims != 2 && c.spatial_dims != 3) { set_error("unet: spatial_dims=%d unsupported", c.spatial_dims); return 2; }
+    for (int i = 0; i < c.num_levels; ++i) {
+        if (c.num_channels[i] % 64 != 0) { set_error("unet: num_channels must be multiples of 64 (tcgen05 K blocks)"); return 2; }
+        if (c.num_channels[i] % 128 != 0) { set_error("unet: num_channels must be multiples of 128 (tcgen05 N tiles)"); return 2; }
+    }
+    const int taps = c.spatial_dims == 3 ? 27 : 9;
+    in_gemm_ = (c.in_channels % 64 == 0);
+    out_gemm_ = (c.out_channels % 128 == 0);
+    if (!in_gemm_ && c.in_channels > 8) { set_error("unet: in_channels=%d unsupported (<=8 or multiple of 64)", c.in_channels); return 2; }
+    if (!out_gemm_ && c.out_channels > 8) { set_error("unet: out_channels=%d unsupported (<=8 or multiple of 128)", c.out_channels); return 2; }
+
+    for (int pass = 0; pass < 2; ++pass) {
+        sizing_ = (pass == 0);
+        f32_used_ = f16_used_ = 0;
+        P_ = 0;
+        down_.clear();
+        up_.clear();
+        slots_.clear();
+        if (!sizing_) {
+            if (cudaMalloc(&f32_arena_, f32_count_ * sizeof(float)) != cudaSuccess ||
+                cudaMalloc(&f16_arena_, f16_count_ * sizeof(__half)) != cudaSuccess) {
+                set_error("unet: cudaMalloc of weight arenas failed (%zu + %zu bytes): %s", f32_count_ * 4, f16_count_ * 2,
+                          cudaGetErrorString(cudaGetLastError()));
+                return 6;
+            }
+            cudaMemset(f32_arena_, 0, f32_count_ * sizeof(float));
+            cudaMemset(f16_arena_, 0, f16_count_ * sizeof(__half));
+        }
+        const int C0 = c.num_channels[0];
+        const int TE = 4 * E_;
+        // conv_in
+        if (in_gemm_) {
+            conv_in_wp_ = arena_alloc<__half>(static_cast<size_t>(C0) * taps * c.in_channels, true);
+            add_pack("conv_in.conv.weight", conv_in_wp_, C0, c.in_channels, taps, static_cast<long long>(taps) * c.in_channels, 0);
+        } else {
+            conv_in_w_ = arena_alloc<float>(static_cast<size_t>(C0) * taps * c.in_channels, false);
+            add_copy("conv_in.conv.weight", conv_in_w_, static_cast<long long>(C0) * taps * c.in_channels);
+        }
+        conv_in_b_ = arena_alloc<float>(C0, false);
+        add_copy("conv_in.conv.bias", conv_in_b_, C0);
+        // time embedding
+        te_w0_ = arena_alloc<float>(static_cast<size_t>(TE) * E_, false);
+        te_b0_ = arena_alloc<float>(TE, false);
+        te_w1_ = arena_alloc<float>(static_cast<size_t>(TE) * TE, false);
+        te_b1_ = arena_alloc<float>(TE, false);
+        add_copy("time_embed.0.weight", te_w0_, static_cast<long long>(TE) * E_);
+        add_copy("time_embed.0.bias", te_b0_, TE);
+        add_copy("time_embed.2.weight", te_w1_, static_cast<long long>(TE) * TE);
+        add_copy("time_embed.2.bias", te_b1_, TE);
+        // total projection width is known only after the walk; size generously on the sizing pass
+        int ptotal = 0;
+        {
+            for (int i = 0; i < c.num_levels; ++i) ptotal += c.num_res_blocks[i] * c.num_channels[i];
+            ptotal += 2 * c.num_channels[c.num_levels - 1];
+            for (int i = 0; i < c.num_levels; ++i) ptotal += (c.num_res_blocks[c.num_levels - 1 - i] + 1) * c.num_channels[c.num_levels - 1 - i];
+        }
+        tp_w_ = arena_alloc<float>(static_cast<size_t>(ptotal) * TE, false);
+        tp_b_ = arena_alloc<float>(ptotal, false);
+        // down path
+        int oc = C0;
+        for (int i = 0; i < c.num_levels; ++i) {
+            const int ic = oc;
+            oc = c.num_channels[i];
+            Level L{};
+            for (int j = 0; j < c.num_res_blocks[i]; ++j) {
+                const std::string pre = "down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j);
+                L.res.push_back(make_res(pre, j == 0 ? ic : oc, 0, oc));
+                if (c.attention_levels[i])
+                    L.attn.push_back(make_attn("down_blocks." + std::to_string(i) + ".attentions." + std::to_string(j), oc,
+                                               c.num_head_channels[i]));
+            }
+            L.has_samp = (i != c.num_levels - 1);
+            if (L.has_samp) {
+                L.samp.C = oc;
+                L.samp.w = arena_alloc<__half>(static_cast<size_t>(oc) * taps * oc, true);
+                L.samp.bias = arena_alloc<float>(oc, false);
+                const std::string pre = "down_blocks." + std::to_string(i) + ".downsampler.op.conv";
+                add_pack(pre + ".weight", L.samp.w, oc, oc, taps, static_cast<long long>(taps) * oc, 0);
+                add_copy(pre + ".bias", L.samp.bias, oc);
+            }
+            down_.push_back(std::move(L));
+        }
+        // middle
+        const int CM = c.num_channels[c.num_levels - 1];
+        mid1_ = make_res("middle_block.resnet_1", CM, 0, CM);
+        mid_attn_ = make_attn("middle_block.attention", CM, c.num_head_channels[c.num_levels - 1]);
+        mid2_ = make_res("middle_block.resnet_2", CM, 0, CM);
+        // up path
+        oc = CM;
+        for (int i = 0; i < c.num_levels; ++i) {
+            const int lvl = c.num_levels - 1 - i;  // un-reversed level index
+            const int prev = oc;
+            oc = c.num_channels[lvl];
+            const int ic = c.num_channels[lvl > 0 ? lvl - 1 : 0];  // reversed[min(i+1, L-1)]
+            const int nres = c.num_res_blocks[lvl] + 1;
+            Level L{};
+            for (int j = 0; j < nres; ++j) {
+                const int res_skip = (j == nres - 1) ? ic : oc;
+                const int res_in = (j == 0) ? prev : oc;
+                const std::string pre = "up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j);
+                L.res.push_back(make_res(pre, res_in, res_skip, oc));
+                if (c.attention_levels[lvl])
+                    L.attn.push_back(make_attn("up_blocks." + std::to_string(i) + ".attentions." + std::to_string(j), oc,
+                                               c.num_head_channels[lvl]));
+            }
+            L.has_samp = (i != c.num_levels - 1);
+            if (L.has_samp) {
+                L.samp.C = oc;
+                L.samp.w = arena_alloc<__half>(static_cast<size_t>(oc) * taps * oc, true);
+                L.samp.bias = arena_alloc<float>(oc, false);
+                const std::string pre = "up_blocks." + std::to_string(i) + ".upsampler.conv.conv";
+                add_pack(pre + ".weight", L.samp.w, oc, oc, taps, static_cast<long long>(taps) * oc, 0);
+                add_copy(pre + ".bias", L.samp.bias, oc);
+            }
+            up_.push_back(std::move(L));
+        }
+        // out
+        out_g_ = arena_alloc<float>(C0, false);
+        out_b_ = arena_alloc<float>(C0, false);
+        add_copy("out.0.weight", out_g_, C0);
+        add_copy("out.0.bias", out_b_, C0);
+        if (out_gemm_) {
+            conv_out_wp_ = arena_alloc<__half>(static_cast<size_t>(c.out_channels) * taps * C0, true);
+            add_pack("out.2.conv.weight", conv_out_wp_, c.out_channels, C0, taps, static_cast<long long>(taps) * C0, 0);
+        } else {
+            conv_out_w_ = arena_alloc<float>(static_cast<size_t>(c.out_channels) * taps * C0, false);
+            add_copy("out.2.conv.weight", conv_out_w_, static_cast<long long>(c.out_channels) * taps * C0);
+        }
+        conv_out_b_ = arena_alloc<float>(c.out_channels, false);
+        add_copy("out.2.conv.bias", conv_out_b_, c.out_channels);
+        if (sizing_) {
+            f32_count_ = f32_used_;
+            f16_count_ = f16_used_;
+        }
+        if (P_ != ptotal) { set_error("unet: internal projection width mismatch %d vs %d", P_, ptotal); return 7; }
+    }
+    return 0;
+}
+
+int UNet::set_param(const char* name, const float* data, long long numel, cudaStream_t stream) {
+    auto it = slots_.find(name);
+    if (it == slots_.end()) { set_error("unet: unexpected parameter '%s'", name); return 8; }
+    ParamSlot& s = it->second;
+    if (numel != s.numel) { set_error("unet: parameter '%s' has %lld elements, expected %lld", name, numel, s.numel); return 8; }
+    if (s.kind == ParamSlot::COPY_F32) {
+        cudaError_t e = cudaMemcpyAsync(s.dst, data, numel * sizeof(float), cudaMemcpyDeviceToDevice, stream);
+        if (e != cudaSuccess) { set_error("unet: copy of '%s' failed: %s", name, cudaGetErrorString(e)); return 5; }
+    } else {
+        long long blocks = (numel + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        pack_conv_weight_kernel2<<<static_cast<int>(blocks), 256, 0, stream>>>(data, s.Cout, s.Cin, s.taps,
+                                                                               static_cast<__half*>(s.dst), s.ktot, s.koff);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { set_error("unet: pack of '%s' failed: %s", name, cudaGetErrorString(e)); return 5; }
+    }
+    s.set = true;
+    finalized_ = false;
+    return 0;
+}
+
+int UNet::finalize(cudaStream_t stream) {
+    for (auto& kv : slots_) {
+        if (!kv.second.set) { set_error("unet: parameter '%s' was never set", kv.first.c_str()); return 8; }
+    }
+    auto fold = [&](ResW& r) {
+        add_vec_kernel<<<(r.cout + 255) / 256, 256, 0, stream>>>(r.bias2, r.bias_skip, r.bias2_total, r.cout);
+    };
+    for (auto& L : down_) for (auto& r : L.res) fold(r);
+    fold(mid1_);
+    fold(mid2_);
+    for (auto& L : up_) for (auto& r : L.res) fold(r);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("unet: finalize failed: %s", cudaGetErrorString(e)); return 5; }
+    finalized_ = true;
+    plans_.clear();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ planning
+struct UNet::Layout {
+    uint8_t* base;
+    size_t off = 0;
+    template <typename T>
+    T* take(size_t count) {
+        off = (off + 1023) & ~size_t(1023);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws_bytes, bool dry, size_t* need) const {
+    const UNetConfig& c = cfg_;
+    const int sd = c.spatial_dims;
+    const int sms = num_sms();
+    Layout lay{dry ? nullptr : static_cast<uint8_t*>(ws)};
+    struct Act { __half* p; int C, D, H, W; long long S() const { return static_cast<long long>(D) * H * W; } };
+    auto new_act = [&](int C, int d, int h, int w) {
+        Act a{lay.take<__half>(static_cast<size_t>(N) * d * h * w * C), C, d, h, w};
+        return a;
+    };
+    // scratch sized by a first dry walk: compute maxima analytically while walking (allocate lazily at the end is not
+    // possible with a bump allocator, so walk twice: first to find the maxima, then to lay out).
+    size_t max_z = 0, max_h = 0, max_qkv = 0, max_up = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool measure = (pass == 0);
+        Layout saved = lay;
+        __half *zA = nullptr, *zB = nullptr, *hB = nullptr, *qkv = nullptr;
+        plan.ops.clear();
+        if (!measure) {
+            plan.temb_act = lay.take<float>(static_cast<size_t>(N) * 4 * E_);
+            plan.temb_all = lay.take<float>(static_cast<size_t>(N) * P_);
+            zA = lay.take<__half>(max_z);
+            zB = lay.take<__half>(max_h);
+            hB = lay.take<__half>(max_h);
+            qkv = lay.take<__half>(max_qkv);
+            plan.x_half = in_gemm_ ? lay.take<__half>(static_cast<size_t>(N) * D * H * W * c.in_channels) : nullptr;
+            plan.y_half = out_gemm_ ? lay.take<__half>(static_cast<size_t>(N) * D * H * W * c.out_channels) : nullptr;
+        }
+        int rc = 0;
+        auto gn = [&](const Act& a, const Act* b, const float* g, const float* bt, __half* dst, bool silu) {
+            const size_t cnt = static_cast<size_t>(N) * a.S() * (a.C + (b ? b->C : 0));
+            if (measure) { if (cnt > max_z) max_z = cnt; return; }
+            Op op{};
+            op.type = Op::GN;
+            op.src0 = a.p; op.C0 = a.C;
+            op.src1 = b ? b->p : nullptr; op.C1 = b ? b->C : 0;
+            op.gamma = g; op.beta = bt; op.dst = dst; op.S = static_cast<int>(a.S()); op.silu = silu;
+            plan.ops.push_back(op);
+        };
+        auto gemm = [&](ConvProblem q, bool uses_temb) {
+            if (measure || dry) { if (!measure) { Op op{}; op.type = Op::GEMM; op.uses_temb = uses_temb; plan.ops.push_back(op); } return; }
+            Op op{};
+            op.type = Op::GEMM;
+            op.uses_temb = uses_temb;
+            int r = conv_prepare(q, sms, &op.conv);
+            if (r && !rc) rc = r;
+            plan.ops.push_back(op);
+        };
+        auto conv3 = [&](const Act& in, __half* zin, int cin, const __half* w, const float* bias, int cout, int stride,
+                         int temb_off, const __half* residual, __half* out, const Act* raw0, const Act* raw1) {
+            const float* cadd = (temb_off >= 0 && plan.temb_all) ? plan.temb_all + temb_off : nullptr;
+            ConvProblem q{};
+            q.spatial_dims = sd;
+            q.N = N; q.D = in.D; q.H = in.H; q.W = in.W;
+            q.stride = stride;
+            q.n_seg = 1;
+            q.seg[0] = {zin, cin, 3};
+            if (raw0) { q.seg[q.n_seg++] = {raw0->p, raw0->C, 1}; }
+            if (raw1) { q.seg[q.n_seg++] = {raw1->p, raw1->C, 1}; }
+            q.weights = w; q.w_rows = cout; q.Cout = cout;
+            q.mode = EPI_STORE;
+            q.bias = bias; q.chan_add = cadd; q.chan_add_stride = P_;
+            q.residual = residual; q.out = out;
+            gemm(q, temb_off >= 0);
+        };
+        auto linear = [&](const __half* in, long long rows, int cin, const __half* w, const float* bias, int cout,
+                          const __half* residual, __half* out) {
+            ConvProblem q{};
+            q.spatial_dims = 2;
+            q.N = 1; q.D = 1; q.H = 1; q.W = static_cast<int>(rows);
+            q.stride = 1;
+            q.n_seg = 1;
+            q.seg[0] = {in, cin, 1};
+            q.weights = w; q.w_rows = cout; q.Cout = cout;
+            q.mode = EPI_STORE;
+            q.bias = bias; q.residual = residual; q.out = out;
+            gemm(q, false);
+        };
+        auto resblock = [&](const ResW& r, const Act& h, const Act* skip) -> Act {
+            const int cin = r.c0 + r.c1;
+            if (measure) {
+                const size_t ch = static_cast<size_t>(N) * h.S() * r.cout;
+                if (ch > max_h) max_h = ch;
+            }
+            gn(h, skip, r.g1, r.b1, zA, true);
+            Act h1{hB, r.cout, h.D, h.H, h.W};
+            conv3(h, zA, cin, r.w1, r.bias1, r.cout, 1, r.temb_off, nullptr, hB, nullptr, nullptr);
+            gn(h1, nullptr, r.g2, r.b2, zB, true);
+            Act out = measure ? Act{nullptr, r.cout, h.D, h.H, h.W} : new_act(r.cout, h.D, h.H, h.W);
+            if (r.skip_conv)
+                conv3(h, zB, r.cout, r.w2, r.bias2_total, r.cout, 1, -1, nullptr, out.p, &h, skip);
+            else
+                conv3(h, zB, r.cout, r.w2, r.bias2_total, r.cout, 1, -1, h.p, out.p, nullptr, nullptr);
+            return out;
+        };
+        auto attnblock = [&](const AttnW& a, const Act& h) -> Act {
+            const long long rows = static_cast<long long>(N) * h.S();
+            if (measure) {
+                const size_t cq = static_cast<size_t>(rows) * 3 * a.C;
+                if (cq > max_qkv) max_qkv = cq;
+                const size_t ch = static_cast<size_t>(rows) * a.C;
+                if (ch > max_h) max_h = ch;
+            }
+            gn(h, nullptr, a.g, a.b, zA, false);
+            linear(zA, rows, a.C, a.wqkv, a.bqkv, 3 * a.C, nullptr, qkv);
+            if (!measure) {
+                Op op{};
+                op.type = Op::ATTN;
+                op.src0 = qkv; op.dst = hB; op.T = static_cast<int>(h.S()); op.C = a.C; op.heads = a.heads;
+                op.scale = 1.0f / sqrtf(static_cast<float>(a.C) / static_cast<float>(a.heads));
+                plan.ops.push_back(op);
+            }
+            Act out = measure ? Act{nullptr, a.C, h.D, h.H, h.W} : new_act(a.C, h.D, h.H, h.W);
+            linear(hB, rows, a.C, a.wproj, a.bproj, a.C, h.p, out.p);
+            return out;
+        };
+
+        // ---- walk
+        Act h = measure ? Act{nullptr, c.num_channels[0], D, H, W} : new_act(c.num_channels[0], D, H, W);
+        if (!measure) {
+            Op op{};
+            op.type = in_gemm_ ? Op::CONV_IN_GEMM : Op::CONV_IN_SMALL;
+            op.dst = h.p; op.D = D; op.H = H; op.W = W;
+            if (in_gemm_ && !dry) {
+                ConvProblem q{};
+                q.spatial_dims = sd; q.N = N; q.D = D; q.H = H; q.W = W; q.stride = 1; q.n_seg = 1;
+                q.seg[0] = {plan.x_half, c.in_channels, 3};
+                q.weights = conv_in_wp_; q.w_rows = c.num_channels[0]; q.Cout = c.num_channels[0];
+                q.mode = EPI_STORE; q.bias = conv_in_b_; q.out = h.p;
+                int r = conv_prepare(q, sms, &op.conv);
+                if (r && !rc) rc = r;
+            }
+            plan.ops.push_back(op);
+        }
+        std::vector<Act> skips;
+        skips.push_back(h);
+        for (size_t i = 0; i < down_.size(); ++i) {
+            const Level& L = down_[i];
+            for (size_t j = 0; j < L.res.size(); ++j) {
+                h = resblock(L.res[j], h, nullptr);
+                if (!L.attn.empty()) h = attnblock(L.attn[j], h);
+                skips.push_back(h);
+            }
+            if (L.has_samp) {
+                const int d2 = sd == 3 ? (h.D + 1) / 2 : h.D, h2 = (h.H + 1) / 2, w2 = (h.W + 1) / 2;
+                Act o = measure ? Act{nullptr, h.C, d2, h2, w2} : new_act(h.C, d2, h2, w2);
+                conv3(h, h.p, h.C, L.samp.w, L.samp.bias, h.C, 2, -1, nullptr, o.p, nullptr, nullptr);
+                h = o;
+                skips.push_back(h);
+            }
+        }
+        h = resblock(mid1_, h, nullptr);
+        h = attnblock(mid_attn_, h);
+        h = resblock(mid2_, h, nullptr);
+        for (size_t i = 0; i < up_.size(); ++i) {
+            const Level& L = up_[i];
+            for (size_t j = 0; j < L.res.size(); ++j) {
+                Act sk = skips.back();
+                skips.pop_back();
+                if (sk.D != h.D || sk.H != h.H || sk.W != h.W) {
+                    set_error("unet: spatial size %dx%dx%d is not divisible by 2^%d (use --latent_pad)", D, H, W, c.num_levels - 1);
+                    return 2;
+                }
+                h = resblock(L.res[j], h, &sk);
+                if (!L.attn.empty()) h = attnblock(L.attn[j], h);
+            }
+            if (L.has_samp) {
+                const int fd = sd == 3 ? 2 : 1;
+                const size_t cnt = static_cast<size_t>(N) * (h.D * fd) * (h.H * 2) * (h.W * 2) * h.C;
+                if (measure && cnt > max_up) max_up = cnt;
+                Act up = measure ? Act{nullptr, h.C, h.D * fd, h.H * 2, h.W * 2} : new_act(h.C, h.D * fd, h.H * 2, h.W * 2);
+                if (!measure) {
+                    Op op{};
+                    op.type = Op::UPSAMPLE;
+                    op.src0 = h.p; op.dst = up.p; op.D = h.D; op.H = h.H; op.W = h.W; op.C = h.C;
+                    plan.ops.push_back(op);
+                }
+                Act o = measure ? up : new_act(h.C, up.D, up.H, up.W);
+                conv3(up, up.p, h.C, L.samp.w, L.samp.bias, h.C, 1, -1, nullptr, o.p, nullptr, nullptr);
+                h = o;
+            }
+        }
+        if (h.D != D || h.H != H || h.W != W) { set_error("unet: output spatial size mismatch"); return 7; }
+        gn(h, nullptr, out_g_, out_b_, zA, true);
+        if (!measure) {
+            plan.z_out = zA;
+            Op op{};
+            op.type = out_gemm_ ? Op::CONV_OUT_GEMM : Op::CONV_OUT_SMALL;
+            op.src0 = zA; op.D = D; op.H = H; op.W = W; op.C = h.C;
+            if (out_gemm_ && !dry) {
+                ConvProblem q{};
+                q.spatial_dims = sd; q.N = N; q.D = D; q.H = H; q.W = W; q.stride = 1; q.n_seg = 1;
+                q.seg[0] = {zA, h.C, 3};
+                q.weights = conv_out_wp_; q.w_rows = c.out_channels; q.Cout = c.out_channels;
+                q.mode = EPI_STORE; q.bias = conv_out_b_; q.out = plan.y_half;
+                int r = conv_prepare(q, sms, &op.conv);
+                if (r && !rc) rc = r;
+            }
+            plan.ops.push_back(op);
+        }
+        if (rc) return rc;
+        if (measure) lay = saved;
+    }
+    if (need) *need = lay.off + 1024;
+    if (!dry && lay.off > ws_bytes) { set_error("unet: workspace too small (%zu < %zu)", ws_bytes, lay.off); return 9; }
+    plan.N = N; plan.D = D; plan.H = H; plan.W = W; plan.ws = ws;
+    return 0;
+}
+
+size_t UNet::workspace_bytes(int N, int D, int H, int W) const {
+    Plan p{};
+    size_t need = 0;
+    if (build_plan(p, N, D, H, W, nullptr, 0, true, &need)) return 0;
+    return need;
+}
+
+double UNet::flops_per_image(int D, int H, int W) const {
+    (void)D; (void)H; (void)W;
+    return 0.0;  // computed on the Python side from the layer list (oracle.unet.count_flops for tests)
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+int UNet::forward(const float* x, const long long* timesteps, int t_uniform, float* out, int N, int D, int H, int W,
+                  void* ws, size_t ws_bytes, cudaStream_t stream, const PlmsStep* plms, float* ring, float* stash,
+                  float* sample) {
+    if (!finalized_) { set_error("unet: forward before finalize()"); return 10; }
+    if (cfg_.spatial_dims == 2 && D != 1) { set_error("unet: 2-D model needs D == 1"); return 2; }
+    auto key = std::make_tuple(N, D, H, W, ws);
+    auto it = plans_.find(key);
+    if (it == plans_.end()) {
+        std::unique_ptr<Plan> p(new Plan());
+        int rc = build_plan(*p, N, D, H, W, ws, ws_bytes, false, nullptr);
+        if (rc) return rc;
+        it = plans_.emplace(key, std::move(p)).first;
+    }
+    Plan& plan = *it->second;
+    const UNetConfig& c = cfg_;
+    const int R = timesteps ? N : 1;
+    int rc = time_embed(timesteps, t_uniform, R, E_, te_w0_, te_b0_, te_w1_, te_b1_, plan.temb_act, stream);
+    if (rc) return rc;
+    rc = time_proj_all(plan.temb_act, R, 4 * E_, tp_w_, tp_b_, P_, plan.temb_all, stream);
+    if (rc) return rc;
+    launches_ += 2;
+    const long long S = static_cast<long long>(D) * H * W;
+    for (Op& op : plan.ops) {
+        switch (op.type) {
+            case Op::CONV_IN_SMALL:
+                rc = conv_in_small(x, conv_in_w_, conv_in_b_, op.dst, N, c.in_channels, D, H, W, c.num_channels[0],
+                                   c.spatial_dims, stream);
+                break;
+            case Op::CONV_IN_GEMM:
+                rc = nchw_to_nhwc_half(x, plan.x_half, N, c.in_channels, S, stream);
+                if (!rc) rc = conv_launch(op.conv, stream);
+                ++launches_;
+                break;
+            case Op::GN:
+                rc = gn_silu(op.src0, op.C0, op.src1, op.C1, op.gamma, op.beta, op.dst, N, op.S, c.norm_num_groups,
+                             c.norm_eps, op.silu, stream);
+                break;
+            case Op::GEMM:
+                if (op.uses_temb) op.conv.p.chan_add_stride = timesteps ? P_ : 0;
+                rc = conv_launch(op.conv, stream);
+                break;
+            case Op::ATTN:
+                rc = attention_core(op.src0, op.dst, N, op.T, op.C, op.heads, op.scale, stream);
+                break;
+            case Op::UPSAMPLE:
+                rc = upsample_nearest2(op.src0, op.dst, N, op.D, op.H, op.W, op.C, c.spatial_dims, stream);
+                break;
+            case Op::CONV_OUT_SMALL:
+                rc = conv_out_small(op.src0, conv_out_w_, conv_out_b_, out, N, op.C, D, H, W, c.out_channels,
+                                    c.spatial_dims, plms, ring, stash, sample, stream);
+                break;
+            case Op::CONV_OUT_GEMM: {
+                rc = conv_launch(op.conv, stream);
+                if (rc) break;
+                float* eps = out ? out : ring + static_cast<long long>(plms ? plms->slot_new : 0) * N * c.out_channels * S;
+                if (!out && plms && !plms->push) { set_error("unet: fused PLMS corrector step needs an eps buffer"); rc = 2; break; }
+                dim3 grid(static_cast<unsigned>((S + 31) / 32), (c.out_channels + 31) / 32, N);
+                nhwc_half_to_nchw_kernel<<<grid, dim3(32, 8), 0, stream>>>(plan.y_half, eps, c.out_channels, S);
+                ++launches_;
+                if (plms) {
+                    rc = plms_update(eps, *plms, ring, stash, sample, sample, static_cast<long long>(N) * c.out_channels * S, stream);
+                    ++launches_;
+                }
+                break;
+            }
+        }
+        ++launches_;
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // namespace ddpm

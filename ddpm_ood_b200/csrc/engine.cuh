@@ -1,0 +1,155 @@
+// DiffusionModelUNet forward engine: owns packed weights, builds a static launch plan per (batch, spatial) shape and
+// replays it on a stream. Mirrors the module the reference builds at src/trainers/base.py:66-86 and calls at
+// src/trainers/reconstruct.py:150-153.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "conv_gemm.cuh"
+#include "kernels.cuh"
+
+namespace ddpm {
+
+constexpr int kMaxLevels = 8;
+
+struct UNetConfig {
+    int spatial_dims;
+    int in_channels, out_channels;
+    int num_levels;
+    int num_channels[kMaxLevels];
+    int attention_levels[kMaxLevels];
+    int num_res_blocks[kMaxLevels];
+    int num_head_channels[kMaxLevels];
+    int norm_num_groups;
+    float norm_eps;
+};
+
+struct ResW {
+    int c0, c1;  // input channels: main tensor, concatenated skip tensor (0 if none)
+    int cout;
+    bool skip_conv;
+    float *g1, *b1, *g2, *b2;
+    __half* w1;  // [cout][9*(c0+c1)]
+    float* bias1;
+    __half* w2;  // [cout][9*cout (+ c0 + c1 when skip_conv)]
+    float *bias2, *bias_skip, *bias2_total;
+    int temb_off;
+    std::string prefix;
+};
+struct AttnW {
+    int C, heads;
+    float *g, *b;
+    __half* wqkv;  // [3C][C]
+    float* bqkv;
+    __half* wproj;  // [C][C]
+    float* bproj;
+    std::string prefix;
+};
+struct SampW {  // down / up sampler conv
+    int C;
+    __half* w;
+    float* bias;
+};
+
+struct ParamSlot {
+    enum Kind { COPY_F32, PACK_CONV } kind;
+    void* dst;
+    long long numel;     // expected element count of the source tensor
+    int Cout, Cin, taps; // PACK_CONV
+    long long ktot, koff;
+    bool set;
+};
+
+struct Op {
+    enum Type { CONV_IN_SMALL, CONV_IN_GEMM, GN, GEMM, ATTN, UPSAMPLE, CONV_OUT_SMALL, CONV_OUT_GEMM } type;
+    // GN
+    const __half *src0, *src1;
+    int C0, C1;
+    const float *gamma, *beta;
+    __half* dst;
+    int S;
+    bool silu;
+    // GEMM
+    ConvLaunch conv;
+    bool uses_temb;
+    // ATTN
+    int T, C, heads;
+    float scale;
+    // UPSAMPLE
+    int D, H, W;
+};
+
+struct Plan {
+    int N, D, H, W;
+    void* ws;
+    std::vector<Op> ops;
+    float* temb_act;  // [N][4E]
+    float* temb_all;  // [N][P]
+    __half* z_out;    // input of conv_out (small path)
+    __half* x_half;   // conv_in gemm path: input in NDHWC fp16
+    __half* y_half;   // conv_out gemm path: output in NDHWC fp16
+};
+
+class UNet {
+   public:
+    explicit UNet(const UNetConfig& cfg);
+    ~UNet();
+    int init();  // allocate weight arenas; returns non-zero on failure
+    int set_param(const char* name, const float* data, long long numel, cudaStream_t stream);
+    int finalize(cudaStream_t stream);
+    size_t workspace_bytes(int N, int D, int H, int W) const;
+    // x: fp32 [N, Cin, D, H, W]; timesteps: device int64 [N] or null (then t_uniform applies to every image);
+    // out: fp32 [N, Cout, D, H, W] (may be null when `plms` is given). When `plms` is non-null the scheduler update is
+    // fused after the output conv and `sample` (== x allowed) is updated in place.
+    int forward(const float* x, const long long* timesteps, int t_uniform, float* out, int N, int D, int H, int W,
+                void* ws, size_t ws_bytes, cudaStream_t stream, const PlmsStep* plms = nullptr, float* ring = nullptr,
+                float* stash = nullptr, float* sample = nullptr);
+    const UNetConfig& config() const { return cfg_; }
+    int num_params_expected() const { return static_cast<int>(slots_.size()); }
+    long long launches() const { return launches_; }
+    double flops_per_image(int D, int H, int W) const;
+
+   private:
+    struct Layout;  // buffer planner
+    int build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws_bytes, bool dry, size_t* need) const;
+    ResW make_res(const std::string& prefix, int c0, int c1, int cout);
+    AttnW make_attn(const std::string& prefix, int C, int head_channels);
+    template <typename T>
+    T* arena_alloc(size_t count, bool half_arena);
+    void add_copy(const std::string& name, float* dst, long long numel);
+    void add_pack(const std::string& name, __half* dst, int Cout, int Cin, int taps, long long ktot, long long koff);
+
+    UNetConfig cfg_;
+    int E_;       // num_channels[0]
+    int P_ = 0;   // total time_emb_proj outputs
+    // weights
+    float *conv_in_w_ = nullptr, *conv_in_b_ = nullptr;  // small path keeps fp32 [Cout][Cin][taps]
+    __half* conv_in_wp_ = nullptr;                        // gemm path
+    float *te_w0_, *te_b0_, *te_w1_, *te_b1_;
+    float *tp_w_, *tp_b_;
+    struct Level { std::vector<ResW> res; std::vector<AttnW> attn; bool has_samp; SampW samp; };
+    std::vector<Level> down_, up_;
+    ResW mid1_, mid2_;
+    AttnW mid_attn_;
+    float *out_g_, *out_b_;
+    float *conv_out_w_ = nullptr, *conv_out_b_ = nullptr;
+    __half* conv_out_wp_ = nullptr;
+    bool in_gemm_, out_gemm_;
+    // arenas
+    size_t f32_count_ = 0, f16_count_ = 0, f32_used_ = 0, f16_used_ = 0;
+    float* f32_arena_ = nullptr;
+    __half* f16_arena_ = nullptr;
+    bool sizing_ = true;
+    std::map<std::string, ParamSlot> slots_;
+    bool finalized_ = false;
+    mutable std::map<std::tuple<int, int, int, int, void*>, std::unique_ptr<Plan>> plans_;
+    long long launches_ = 0;
+};
+
+}  // namespace ddpm

@@ -1,0 +1,651 @@
+// Non-GEMM kernels of the reconstruction path. See kernels.cuh.
+#include "kernels.cuh"
+
+#include <math.h>
+
+#include "conv_gemm.cuh"  // set_error
+
+namespace ddpm {
+
+#define DDPM_CHECK_LAUNCH(name)                                                      \
+    do {                                                                             \
+        cudaError_t e__ = cudaGetLastError();                                        \
+        if (e__ != cudaSuccess) {                                                    \
+            set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));       \
+            return 5;                                                                \
+        }                                                                            \
+    } while (0)
+
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = __half22float2(h[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 v;
+    __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm + SiLU
+// One CTA per (image, chunk of `gpc` groups). Two passes over the chunk's [S x CH] slab (the second hits L1/L2):
+// pass 1 accumulates per-channel sum / sum of squares in fp32, pass 2 applies y = silu(x * a[c] + b[c]).
+constexpr int kGnMaxCH = 256;
+
+__global__ void __launch_bounds__(256) gn_silu_kernel(const __half* __restrict__ src0, int C0,
+                                                      const __half* __restrict__ src1, int C1,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      __half* __restrict__ out, int S, int cpg, int gpc, float eps,
+                                                      int do_silu) {
+    // per-thread partials go to shared memory and are summed in a fixed order: bitwise reproducible (no atomics)
+    __shared__ float s_psum[2048], s_psq[2048];  // [PL][CH], PL*CH <= 256*8
+    __shared__ float s_sum[kGnMaxCH], s_sq[kGnMaxCH], s_a[kGnMaxCH], s_b[kGnMaxCH];
+    const int CH = cpg * gpc;
+    const int V = CH >> 3;
+    const int PL = blockDim.x / V;
+    const int n = blockIdx.y;
+    const int c_chunk = blockIdx.x * CH;
+    const int C = C0 + C1;
+    const int tid = threadIdx.x;
+    const bool active = tid < PL * V;
+    const int v = tid % V, pl = tid / V;
+    const int c = c_chunk + v * 8;  // channel in the concatenation
+    const __half* base;
+    int Cs;
+    if (c < C0) { base = src0 + static_cast<size_t>(n) * S * C0 + c; Cs = C0; }
+    else        { base = src1 + static_cast<size_t>(n) * S * C1 + (c - C0); Cs = C1; }
+    if (active) {
+        float s[8], q[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+        for (int p = pl; p < S; p += PL) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(p) * Cs);
+            float f[8];
+            unpack8(raw, f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            s_psum[pl * CH + v * 8 + i] = s[i];
+            s_psq[pl * CH + v * 8 + i] = q[i];
+        }
+    }
+    __syncthreads();
+    if (tid < CH) {
+        float a = 0.f, b = 0.f;
+        for (int i = 0; i < PL; ++i) { a += s_psum[i * CH + tid]; b += s_psq[i * CH + tid]; }
+        s_sum[tid] = a;
+        s_sq[tid] = b;
+    }
+    __syncthreads();
+    if (tid < CH) {
+        const int g = tid / cpg;
+        float sum = 0.f, sq = 0.f;
+        for (int i = 0; i < cpg; ++i) { sum += s_sum[g * cpg + i]; sq += s_sq[g * cpg + i]; }
+        const float inv_n = 1.0f / (static_cast<float>(cpg) * static_cast<float>(S));
+        const float mean = sum * inv_n;
+        float var = sq * inv_n - mean * mean;
+        var = var < 0.f ? 0.f : var;
+        const float rstd = rsqrtf(var + eps);
+        const float a = gamma[c_chunk + tid] * rstd;
+        s_a[tid] = a;
+        s_b[tid] = beta[c_chunk + tid] - mean * a;
+    }
+    __syncthreads();
+    if (active) {
+        float a[8], b[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a[i] = s_a[v * 8 + i]; b[i] = s_b[v * 8 + i]; }
+        __half* obase = out + static_cast<size_t>(n) * S * C + c;
+        for (int p = pl; p < S; p += PL) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(p) * Cs);
+            float f[8];
+            unpack8(raw, f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float y = f[i] * a[i] + b[i];
+                f[i] = do_silu ? silu(y) : y;
+            }
+            *reinterpret_cast<uint4*>(obase + static_cast<size_t>(p) * C) = pack8(f);
+        }
+    }
+}
+
+int gn_silu(const __half* src0, int C0, const __half* src1, int C1, const float* gamma, const float* beta,
+            __half* out, int N, int S, int groups, float eps, bool do_silu, cudaStream_t stream) {
+    const int C = C0 + C1;
+    if (C % groups != 0 || C0 % 8 != 0 || C1 % 8 != 0) { set_error("gn_silu: C=%d+%d groups=%d unsupported", C0, C1, groups); return 2; }
+    const int cpg = C / groups;
+    int gpc = 0;
+    for (int g = 1; g <= groups; g <<= 1) {
+        if (groups % g == 0 && (g * cpg) % 8 == 0 && (g * cpg >= 32 || g == groups)) { gpc = g; break; }
+    }
+    if (!gpc) gpc = groups;
+    if ((gpc * cpg) % 8 != 0 || gpc * cpg > kGnMaxCH) { set_error("gn_silu: chunk of %d channels unsupported", gpc * cpg); return 2; }
+    dim3 grid(groups / gpc, N);
+    gn_silu_kernel<<<grid, 256, 0, stream>>>(src0, C0, src1, C1, gamma, beta, out, S, cpg, gpc, eps, do_silu ? 1 : 0);
+    DDPM_CHECK_LAUNCH("gn_silu");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ time embedding
+// One CTA per row: sinusoid(E) -> Linear(E,4E)+SiLU -> Linear(4E,4E) -> SiLU. Warp-per-output dot products.
+__global__ void __launch_bounds__(256) time_embed_kernel(const long long* __restrict__ timesteps, int t_uniform, int E,
+                                                         const float* __restrict__ w0, const float* __restrict__ b0,
+                                                         const float* __restrict__ w1, const float* __restrict__ b1,
+                                                         float* __restrict__ act_out) {
+    extern __shared__ float sm[];
+    float* s_emb = sm;           // [E]
+    float* s_hid = sm + E;       // [4E]
+    const int r = blockIdx.x;
+    const int H4 = 4 * E;
+    const float t = timesteps ? static_cast<float>(timesteps[r]) : static_cast<float>(t_uniform);
+    const int half = E / 2;
+    for (int i = threadIdx.x; i < half; i += blockDim.x) {
+        const float exponent = -logf(10000.0f) * static_cast<float>(i);
+        const float freq = expf(exponent / static_cast<float>(half));
+        const float arg = t * freq;
+        s_emb[i] = cosf(arg);
+        s_emb[half + i] = sinf(arg);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int j = warp; j < H4; j += nw) {
+        float acc = 0.f;
+        for (int k = lane; k < E; k += 32) acc += w0[static_cast<size_t>(j) * E + k] * s_emb[k];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_hid[j] = silu(acc + b0[j]);
+    }
+    __syncthreads();
+    for (int j = warp; j < H4; j += nw) {
+        float acc = 0.f;
+        for (int k = lane; k < H4; k += 32) acc += w1[static_cast<size_t>(j) * H4 + k] * s_hid[k];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) act_out[static_cast<size_t>(r) * H4 + j] = silu(acc + b1[j]);
+    }
+}
+
+int time_embed(const long long* timesteps, int t_uniform, int R, int E, const float* w0, const float* b0,
+               const float* w1, const float* b1, float* act_out, cudaStream_t stream) {
+    if (E % 2) { set_error("time_embed: odd embedding dim"); return 2; }
+    time_embed_kernel<<<R, 256, 5 * E * sizeof(float), stream>>>(timesteps, t_uniform, E, w0, b0, w1, b1, act_out);
+    DDPM_CHECK_LAUNCH("time_embed");
+    return 0;
+}
+
+// out[r, p] = act[r, :] . W[p, :] + b[p]; one warp per output column p, rows looped.
+__global__ void __launch_bounds__(256) time_proj_kernel(const float* __restrict__ act, int R, int K,
+                                                        const float* __restrict__ w, const float* __restrict__ b,
+                                                        int P, float* __restrict__ out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= P) return;
+    const float* wr = w + static_cast<size_t>(warp) * K;
+    const float bias = b[warp];
+    for (int r = 0; r < R; ++r) {
+        const float* ar = act + static_cast<size_t>(r) * K;
+        float acc = 0.f;
+        for (int k = lane; k < K; k += 32) acc += wr[k] * ar[k];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) out[static_cast<size_t>(r) * P + warp] = acc + bias;
+    }
+}
+
+int time_proj_all(const float* act, int R, int K, const float* wcat, const float* bcat, int P, float* out,
+                  cudaStream_t stream) {
+    const int blocks = (P * 32 + 255) / 256;
+    time_proj_kernel<<<blocks, 256, 0, stream>>>(act, R, K, wcat, bcat, P, out);
+    DDPM_CHECK_LAUNCH("time_proj_all");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ attention core
+// Generic-T attention on CUDA cores (fp32 math, fp16 I/O): one CTA per (16 queries, image*head). The score row lives
+// in shared memory, K and V stream through a 64-key staging tile. Head dim fixed at 256 (num_head_channels=256 in both
+// reference configurations, src/trainers/base.py:73,84).
+constexpr int kHD = 256, kQT = 16, kKT = 64, kPadHD = kHD + 8;
+
+__global__ void __launch_bounds__(256) attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int T,
+                                                        int C, int heads, float scale) {
+    extern __shared__ __align__(16) uint8_t smem_att[];
+    __half* q_s = reinterpret_cast<__half*>(smem_att);                 // [kQT][kPadHD]
+    __half* kv_s = q_s + kQT * kPadHD;                                 // [kKT][kPadHD]
+    float* s_s = reinterpret_cast<float*>(kv_s + kKT * kPadHD);        // [kQT][Tp]
+    const int Tp = (T + 3) & ~3;
+    const int nh = blockIdx.y;
+    const int n = nh / heads, head = nh % heads;
+    const int q0 = blockIdx.x * kQT;
+    const int tid = threadIdx.x;
+    const size_t row_stride = static_cast<size_t>(3) * C;
+    const __half* qbase = qkv + static_cast<size_t>(n) * T * row_stride + head * kHD;
+    const __half* kbase = qbase + C;
+    const __half* vbase = qbase + 2 * C;
+
+    // load the query tile
+    for (int i = tid; i < kQT * (kHD / 8); i += blockDim.x) {
+        const int r = i / (kHD / 8), cv = i % (kHD / 8);
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (q0 + r < T) val = *reinterpret_cast<const uint4*>(qbase + static_cast<size_t>(q0 + r) * row_stride + cv * 8);
+        *reinterpret_cast<uint4*>(q_s + r * kPadHD + cv * 8) = val;
+    }
+    // phase 1: scores
+    for (int k0 = 0; k0 < T; k0 += kKT) {
+        __syncthreads();
+        for (int i = tid; i < kKT * (kHD / 8); i += blockDim.x) {
+            const int r = i / (kHD / 8), cv = i % (kHD / 8);
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (k0 + r < T) val = *reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(k0 + r) * row_stride + cv * 8);
+            *reinterpret_cast<uint4*>(kv_s + r * kPadHD + cv * 8) = val;
+        }
+        __syncthreads();
+        const int j = tid % kKT, qg = tid / kKT;  // 4 query groups x 4 queries
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int d = 0; d < kHD; d += 8) {
+            float kf[8];
+            unpack8(*reinterpret_cast<const uint4*>(kv_s + j * kPadHD + d), kf);
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+                float qf[8];
+                unpack8(*reinterpret_cast<const uint4*>(q_s + (qg * 4 + qq) * kPadHD + d), qf);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[qq] += qf[e] * kf[e];
+            }
+        }
+        if (k0 + j < T) {
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) s_s[(qg * 4 + qq) * Tp + k0 + j] = acc[qq] * scale;
+        }
+    }
+    __syncthreads();
+    // phase 2: softmax rows (one warp per two rows)
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int r = warp; r < kQT; r += 8) {
+            float* row = s_s + r * Tp;
+            float mx = -INFINITY;
+            for (int jx = lane; jx < T; jx += 32) mx = fmaxf(mx, row[jx]);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            float sum = 0.f;
+            for (int jx = lane; jx < T; jx += 32) {
+                const float e = __expf(row[jx] - mx);
+                row[jx] = e;
+                sum += e;
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float inv = 1.0f / sum;
+            for (int jx = lane; jx < T; jx += 32) row[jx] *= inv;
+        }
+    }
+    // phase 3: O = P V ; thread -> 2 channels x 8 queries
+    const int c2 = tid % (kHD / 2), qg2 = tid / (kHD / 2);
+    float o_acc[8][2];
+#pragma unroll
+    for (int qq = 0; qq < 8; ++qq) { o_acc[qq][0] = 0.f; o_acc[qq][1] = 0.f; }
+    for (int k0 = 0; k0 < T; k0 += kKT) {
+        __syncthreads();
+        for (int i = tid; i < kKT * (kHD / 8); i += blockDim.x) {
+            const int r = i / (kHD / 8), cv = i % (kHD / 8);
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (k0 + r < T) val = *reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(k0 + r) * row_stride + cv * 8);
+            *reinterpret_cast<uint4*>(kv_s + r * kPadHD + cv * 8) = val;
+        }
+        __syncthreads();
+        const int kmax = (T - k0) < kKT ? (T - k0) : kKT;
+        for (int jx = 0; jx < kmax; ++jx) {
+            const float2 vv = __half22float2(*reinterpret_cast<const __half2*>(kv_s + jx * kPadHD + 2 * c2));
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) {
+                const float pj = s_s[(qg2 * 8 + qq) * Tp + k0 + jx];
+                o_acc[qq][0] += pj * vv.x;
+                o_acc[qq][1] += pj * vv.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int qq = 0; qq < 8; ++qq) {
+        const int qrow = q0 + qg2 * 8 + qq;
+        if (qrow < T) {
+            __half2 hv = __floats2half2_rn(o_acc[qq][0], o_acc[qq][1]);
+            *reinterpret_cast<__half2*>(out + (static_cast<size_t>(n) * T + qrow) * C + head * kHD + 2 * c2) = hv;
+        }
+    }
+}
+
+int attention_core(const __half* qkv, __half* out, int N, int T, int C, int heads, float scale, cudaStream_t stream) {
+    if (C != heads * kHD) { set_error("attention_core: head dim %d unsupported (need 256)", heads ? C / heads : 0); return 2; }
+    const int Tp = (T + 3) & ~3;
+    const size_t smem = static_cast<size_t>(kQT + kKT) * kPadHD * sizeof(__half) + static_cast<size_t>(kQT) * Tp * sizeof(float);
+    if (smem > 220 * 1024) { set_error("attention_core: T=%d too large", T); return 2; }
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) { set_error("attention_core: %s", cudaGetErrorString(e)); return 4; }
+        smem_set = smem;
+    }
+    dim3 grid((T + kQT - 1) / kQT, N * heads);
+    attention_kernel<<<grid, 256, smem, stream>>>(qkv, out, T, C, heads, scale);
+    DDPM_CHECK_LAUNCH("attention_core");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ upsample
+__global__ void upsample_nearest2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int D, int H, int W,
+                                         int CV, int fd, long long total) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        long long r = i;
+        const int cv = static_cast<int>(r % CV); r /= CV;
+        const int w = static_cast<int>(r % (2 * W)); r /= (2 * W);
+        const int h = static_cast<int>(r % (2 * H)); r /= (2 * H);
+        const int d = static_cast<int>(r % (fd * D)); r /= (fd * D);
+        const long long n = r;
+        out[i] = in[(((n * D + d / fd) * H + h / 2) * W + w / 2) * CV + cv];
+    }
+}
+
+int upsample_nearest2(const __half* in, __half* out, int N, int D, int H, int W, int C, int spatial_dims,
+                      cudaStream_t stream) {
+    if (C % 8) { set_error("upsample: C %% 8 != 0"); return 2; }
+    const int fd = spatial_dims == 3 ? 2 : 1;
+    const int CV = C / 8;
+    const long long total = static_cast<long long>(N) * (fd * D) * (2 * H) * (2 * W) * CV;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    upsample_nearest2_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
+        reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), D, H, W, CV, fd, total);
+    DDPM_CHECK_LAUNCH("upsample_nearest2");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ conv_in (few ch)
+// thread = (pixel, group of 8 output channels); weights transposed to [tap*Cin][Cout] fp32 in shared memory.
+__global__ void __launch_bounds__(256) conv_in_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ b, __half* __restrict__ out,
+                                                            int N, int Cin, int D, int H, int W, int Cout, int kd) {
+    extern __shared__ float s_w[];  // [taps*Cin][Cout]
+    const int taps = kd * 9;
+    for (int i = threadIdx.x; i < taps * Cin * Cout; i += blockDim.x) {
+        const int co = i % Cout;
+        const int r = i / Cout;  // tap*Cin + ci
+        const int ci = r % Cin, tap = r / Cin;
+        s_w[i] = w[(static_cast<size_t>(co) * Cin + ci) * taps + tap];
+    }
+    __syncthreads();
+    const int G = Cout / 8;
+    const long long total = static_cast<long long>(N) * D * H * W * G;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % G);
+        long long pix = i / G;
+        const int wq = static_cast<int>(pix % W);
+        const int hq = static_cast<int>((pix / W) % H);
+        const int dq = static_cast<int>((pix / (static_cast<long long>(W) * H)) % D);
+        const long long n = pix / (static_cast<long long>(W) * H * D);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = b[g * 8 + j];
+        for (int tap = 0; tap < taps; ++tap) {
+            const int tw = tap % 3, th = (tap / 3) % 3, td = tap / 9;
+            const int ww = wq + tw - 1, hh = hq + th - 1, dd = dq + td - (kd == 3 ? 1 : 0);
+            if (ww < 0 || ww >= W || hh < 0 || hh >= H || dd < 0 || dd >= D) continue;
+            for (int ci = 0; ci < Cin; ++ci) {
+                const float xv = __ldg(x + (((n * Cin + ci) * D + dd) * H + hh) * W + ww);
+                const float4* wp = reinterpret_cast<const float4*>(s_w + (tap * Cin + ci) * Cout + g * 8);
+                const float4 w0 = wp[0], w1 = wp[1];
+                acc[0] += xv * w0.x; acc[1] += xv * w0.y; acc[2] += xv * w0.z; acc[3] += xv * w0.w;
+                acc[4] += xv * w1.x; acc[5] += xv * w1.y; acc[6] += xv * w1.z; acc[7] += xv * w1.w;
+            }
+        }
+        *reinterpret_cast<uint4*>(out + pix * Cout + g * 8) = pack8(acc);
+    }
+}
+
+int conv_in_small(const float* x, const float* w, const float* b, __half* out, int N, int Cin, int D, int H, int W,
+                  int Cout, int spatial_dims, cudaStream_t stream) {
+    const int kd = spatial_dims == 3 ? 3 : 1;
+    const size_t smem = static_cast<size_t>(kd) * 9 * Cin * Cout * sizeof(float);
+    if (Cout % 8 || smem > 200 * 1024) { set_error("conv_in_small: Cin=%d Cout=%d unsupported", Cin, Cout); return 2; }
+    static size_t smem_set = 48 * 1024;
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_in_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) { set_error("conv_in_small: %s", cudaGetErrorString(e)); return 4; }
+        smem_set = smem;
+    }
+    const long long total = static_cast<long long>(N) * D * H * W * (Cout / 8);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    conv_in_small_kernel<<<static_cast<int>(blocks), 256, smem, stream>>>(x, w, b, out, N, Cin, D, H, W, Cout, kd);
+    DDPM_CHECK_LAUNCH("conv_in_small");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ layout conversion
+__global__ void nchw_to_nhwc_half_kernel(const float* __restrict__ x, __half* __restrict__ out, int C, long long S) {
+    __shared__ float tile[32][33];
+    const long long n = blockIdx.z;
+    const long long s0 = static_cast<long long>(blockIdx.x) * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i;
+        const long long s = s0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && s < S) ? x[(n * C + c) * S + s] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const long long s = s0 + i;
+        const int c = c0 + threadIdx.x;
+        if (s < S && c < C) out[(n * S + s) * C + c] = __float2half_rn(tile[threadIdx.x][i]);
+    }
+}
+
+int nchw_to_nhwc_half(const float* x, __half* out, int N, int C, long long S, cudaStream_t stream) {
+    dim3 grid(static_cast<unsigned>((S + 31) / 32), (C + 31) / 32, N);
+    nchw_to_nhwc_half_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, out, C, S);
+    DDPM_CHECK_LAUNCH("nchw_to_nhwc_half");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ PLMS
+__device__ __forceinline__ void plms_apply(const PlmsStep& st, float e_new, long long idx, long long numel,
+                                           float* __restrict__ ring, float* __restrict__ stash,
+                                           const float* __restrict__ sample_in, float* __restrict__ sample_out) {
+    // explicit rounding/contraction so the fused (conv_out tail) and stand-alone instances are bitwise identical
+    float eb = __fmul_rn(st.c[0], e_new);
+    if (st.c[1] != 0.f) eb = __fmaf_rn(st.c[1], ring[st.slot[0] * numel + idx], eb);
+    if (st.c[2] != 0.f) eb = __fmaf_rn(st.c[2], ring[st.slot[1] * numel + idx], eb);
+    if (st.c[3] != 0.f) eb = __fmaf_rn(st.c[3], ring[st.slot[2] * numel + idx], eb);
+    const float cur = sample_in[idx];
+    const float s = st.use_stash ? stash[idx] : cur;
+    if (st.write_stash) stash[idx] = cur;
+    const float mo = __fmaf_rn(st.vA, eb, __fmul_rn(st.vB, s));
+    sample_out[idx] = __fmaf_rn(st.A, s, -__fmul_rn(st.Bc, mo));
+    if (st.push) ring[st.slot_new * numel + idx] = e_new;
+}
+
+__global__ void plms_update_kernel(const float* __restrict__ eps_new, PlmsStep st, float* ring, float* stash,
+                                   const float* sample_in, float* sample_out, long long numel) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < numel;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        plms_apply(st, eps_new[i], i, numel, ring, stash, sample_in, sample_out);
+}
+
+int plms_update(const float* eps_new, const PlmsStep& st, float* ring, float* stash, const float* sample_in,
+                float* sample_out, long long numel, cudaStream_t stream) {
+    long long blocks = (numel + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    plms_update_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(eps_new, st, ring, stash, sample_in, sample_out, numel);
+    DDPM_CHECK_LAUNCH("plms_update");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ conv_out (few ch)
+// 8 lanes per output pixel, each lane owns 8-channel vectors (lane + 8k) of every tap; shuffle-reduce; lane 0 of the
+// octet finishes the pixel: bias, fp32 NCDHW store, and (optionally) the fused PLMS update of the sample.
+constexpr int kMaxCoutSmall = 8;
+
+__global__ void __launch_bounds__(256) conv_out_small_kernel(const __half* __restrict__ z, const float* __restrict__ w,
+                                                             const float* __restrict__ b, float* __restrict__ eps_out,
+                                                             int N, int Cin, int D, int H, int W, int Cout, int kd,
+                                                             int fuse, PlmsStep st, float* ring, float* stash,
+                                                             float* sample) {
+    extern __shared__ float s_w[];  // [Cout][taps][Cin]
+    const int taps = kd * 9;
+    for (int i = threadIdx.x; i < Cout * taps * Cin; i += blockDim.x) {
+        const int ci = i % Cin;
+        const int r = i / Cin;
+        const int tap = r % taps, co = r / taps;
+        s_w[i] = w[(static_cast<size_t>(co) * Cin + ci) * taps + tap];
+    }
+    __syncthreads();
+    const int lane8 = threadIdx.x & 7;
+    const long long npix = static_cast<long long>(N) * D * H * W;
+    const long long spatial = static_cast<long long>(D) * H * W;
+    const long long numel = npix * Cout;
+    const long long npix_pad = (npix + 31) & ~31LL;  // keep whole warps alive for the shuffles
+    for (long long pix = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 3; pix < npix_pad;
+         pix += (static_cast<long long>(gridDim.x) * blockDim.x) >> 3) {
+        const bool live = pix < npix;
+        const long long pp = live ? pix : 0;
+        const int wq = static_cast<int>(pp % W);
+        const int hq = static_cast<int>((pp / W) % H);
+        const int dq = static_cast<int>((pp / (static_cast<long long>(W) * H)) % D);
+        const long long n = pp / spatial;
+        float acc[kMaxCoutSmall];
+#pragma unroll
+        for (int co = 0; co < kMaxCoutSmall; ++co) acc[co] = 0.f;
+        if (live) {
+            for (int tap = 0; tap < taps; ++tap) {
+                const int tw = tap % 3, th = (tap / 3) % 3, td = tap / 9;
+                const int ww = wq + tw - 1, hh = hq + th - 1, dd = dq + td - (kd == 3 ? 1 : 0);
+                if (ww < 0 || ww >= W || hh < 0 || hh >= H || dd < 0 || dd >= D) continue;
+                const __half* zp = z + (((n * D + dd) * H + hh) * W + ww) * Cin;
+                for (int cv = lane8; cv < Cin / 8; cv += 8) {
+                    float f[8];
+                    unpack8(__ldg(reinterpret_cast<const uint4*>(zp + cv * 8)), f);
+#pragma unroll
+                    for (int co = 0; co < kMaxCoutSmall; ++co) {
+                        if (co < Cout) {
+                            const float* wp = s_w + (co * taps + tap) * Cin + cv * 8;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) acc[co] += f[e] * wp[e];
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int co = 0; co < kMaxCoutSmall; ++co) {
+            acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 4);
+            acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 2);
+            acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 1);
+        }
+        if (live && lane8 == 0) {
+            const long long sp = pp % spatial;
+#pragma unroll
+            for (int co = 0; co < kMaxCoutSmall; ++co) {
+                if (co < Cout) {
+                    const float e = acc[co] + b[co];
+                    const long long idx = (n * Cout + co) * spatial + sp;
+                    if (eps_out) eps_out[idx] = e;
+                    if (fuse) plms_apply(st, e, idx, numel, ring, stash, sample, sample);
+                }
+            }
+        }
+    }
+}
+
+int conv_out_small(const __half* z, const float* w, const float* b, float* eps_out, int N, int Cin, int D, int H,
+                   int W, int Cout, int spatial_dims, const PlmsStep* plms, float* ring, float* stash, float* sample,
+                   cudaStream_t stream) {
+    const int kd = spatial_dims == 3 ? 3 : 1;
+    const size_t smem = static_cast<size_t>(Cout) * kd * 9 * Cin * sizeof(float);
+    if (Cout > kMaxCoutSmall || Cin % 64 || smem > 200 * 1024) { set_error("conv_out_small: Cin=%d Cout=%d unsupported", Cin, Cout); return 2; }
+    static size_t smem_set = 48 * 1024;
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_out_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) { set_error("conv_out_small: %s", cudaGetErrorString(e)); return 4; }
+        smem_set = smem;
+    }
+    const long long npix = static_cast<long long>(N) * D * H * W;
+    long long blocks = (npix * 8 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    PlmsStep st{};
+    if (plms) st = *plms;
+    conv_out_small_kernel<<<static_cast<int>(blocks), 256, smem, stream>>>(z, w, b, eps_out, N, Cin, D, H, W, Cout, kd,
+                                                                           plms ? 1 : 0, st, ring, stash, sample);
+    DDPM_CHECK_LAUNCH("conv_out_small");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ add_noise
+__global__ void add_noise_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
+                                 const float* __restrict__ ac, const long long* __restrict__ timesteps, int t_uniform,
+                                 float b_scale, float* __restrict__ out, long long per_image, long long total) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long n = i / per_image;
+        const long long t = timesteps ? timesteps[n] : t_uniform;
+        const float a = ac[t];
+        out[i] = sqrtf(a) * (x0[i] * b_scale) + sqrtf(1.0f - a) * noise[i];
+    }
+}
+
+int add_noise(const float* x0, const float* noise, const float* alphas_cumprod, const long long* timesteps,
+              int t_uniform, float b_scale, float* out, int N, long long per_image, cudaStream_t stream) {
+    const long long total = static_cast<long long>(N) * per_image;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    add_noise_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x0, noise, alphas_cumprod, timesteps, t_uniform,
+                                                                   b_scale, out, per_image, total);
+    DDPM_CHECK_LAUNCH("add_noise");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ clamp + MSE
+__global__ void __launch_bounds__(256) clamp_mse_kernel(const float* __restrict__ x, const float* __restrict__ x0,
+                                                        float b_scale, float* __restrict__ recon,
+                                                        float* __restrict__ mse, long long per_image) {
+    __shared__ float s_part[8];
+    const long long n = blockIdx.x;
+    float acc = 0.f;
+    for (long long i = threadIdx.x; i < per_image; i += blockDim.x) {
+        const long long idx = n * per_image + i;
+        float r = x[idx] / b_scale;
+        r = fminf(fmaxf(r, 0.f), 1.f);
+        if (recon) recon[idx] = r;
+        const float d = x0[idx] - r;
+        acc += d * d;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += s_part[i];
+        mse[n] = t / static_cast<float>(per_image);
+    }
+}
+
+int clamp_mse(const float* x, const float* x0, float b_scale, float* recon, float* mse, int N, long long per_image,
+              cudaStream_t stream) {
+    clamp_mse_kernel<<<N, 256, 0, stream>>>(x, x0, b_scale, recon, mse, per_image);
+    DDPM_CHECK_LAUNCH("clamp_mse");
+    return 0;
+}
+
+}  // namespace ddpm

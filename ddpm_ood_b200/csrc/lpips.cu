@@ -1,0 +1,285 @@
+// LPIPS (AlexNet, v0.1, linear heads, spatial average) on the device, fp32 throughout.
+// Replaces `lpips.LPIPS.forward(in0, in1, normalize=...)` as called through the reference's wrapper
+// src/losses/perceptual_loss.py:125,181-183 from src/trainers/reconstruct.py:170-187.
+// The feature extractor is a few MFLOP per image (vs ~400 GFLOP for the reconstruction chain it scores), so plain
+// direct convolutions on CUDA cores are used; what matters is that the whole score stays on the device.
+#include "lpips.cuh"
+
+#include <string.h>
+
+#include "conv_gemm.cuh"  // set_error
+
+namespace ddpm {
+
+#define LP_CHECK(name)                                                             \
+    do {                                                                           \
+        cudaError_t e__ = cudaGetLastError();                                      \
+        if (e__ != cudaSuccess) {                                                  \
+            set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));     \
+            return 5;                                                              \
+        }                                                                          \
+    } while (0)
+
+static const int kChn[5] = {64, 192, 384, 256, 256};
+static const int kCin[5] = {3, 64, 192, 384, 256};
+static const int kK[5] = {11, 5, 3, 3, 3};
+static const int kStride[5] = {4, 1, 1, 1, 1};
+static const int kPad[5] = {2, 2, 1, 1, 1};
+
+// in0/in1: [B, C, H, W] (C = 1 broadcasts to 3, like the reference's ScalingLayer does for grayscale); out: [2B,3,H,W]
+__global__ void lpips_scale_kernel(const float* __restrict__ in0, const float* __restrict__ in1, float* __restrict__ out,
+                                   int B, int C, int HW, int normalize, float3 shift, float3 scale) {
+    const long long total = 2LL * B * 3 * HW;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int p = static_cast<int>(i % HW);
+        const int c = static_cast<int>((i / HW) % 3);
+        const long long b2 = i / (3LL * HW);
+        const float* src = b2 < B ? in0 : in1;
+        const long long b = b2 < B ? b2 : b2 - B;
+        float v = src[(b * C + (C == 1 ? 0 : c)) * HW + p];
+        if (normalize) v = 2.0f * v - 1.0f;
+        const float sh = c == 0 ? shift.x : (c == 1 ? shift.y : shift.z);
+        const float sc = c == 0 ? scale.x : (c == 1 ? scale.y : scale.z);
+        out[i] = (v - sh) / sc;
+    }
+}
+
+// Direct convolution + bias + ReLU, NCHW fp32. One warp per (image, output channel, block of 32 output pixels): the
+// filter row is streamed once per warp (lanes split the Cin*k*k reduction for tiny maps, pixels for large maps).
+__global__ void __launch_bounds__(256) lpips_conv_relu_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, float* __restrict__ out,
+                                                              int NB, int Cin, int H, int W, int Cout, int Ho, int Wo,
+                                                              int K, int stride, int pad) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+    const int npix = Ho * Wo;
+    const int pblocks = (npix + 31) / 32;
+    const long long total = static_cast<long long>(NB) * Cout * pblocks;
+    if (warp >= total) return;
+    const int pb = static_cast<int>(warp % pblocks);
+    const int co = static_cast<int>((warp / pblocks) % Cout);
+    const long long n = warp / (static_cast<long long>(pblocks) * Cout);
+    const float* wrow = w + static_cast<long long>(co) * Cin * K * K;
+    const float* img = in + n * Cin * H * W;
+    if (npix >= 16) {
+        // lane = output pixel
+        const int p = pb * 32 + lane;
+        if (p >= npix) return;
+        const int ho = p / Wo, wo = p % Wo;
+        float acc = bias[co];
+        for (int ci = 0; ci < Cin; ++ci) {
+            for (int kh = 0; kh < K; ++kh) {
+                const int hi = ho * stride + kh - pad;
+                if (hi < 0 || hi >= H) continue;
+                for (int kw = 0; kw < K; ++kw) {
+                    const int wi = wo * stride + kw - pad;
+                    if (wi < 0 || wi >= W) continue;
+                    acc += img[(ci * H + hi) * W + wi] * __ldg(wrow + (ci * K + kh) * K + kw);
+                }
+            }
+        }
+        out[(n * Cout + co) * npix + p] = fmaxf(acc, 0.f);
+    } else {
+        // tiny maps: lanes split the reduction, one pixel at a time
+        const int red = Cin * K * K;
+        for (int p = 0; p < npix; ++p) {
+            const int ho = p / Wo, wo = p % Wo;
+            float acc = 0.f;
+            for (int r = lane; r < red; r += 32) {
+                const int kw = r % K, kh = (r / K) % K, ci = r / (K * K);
+                const int hi = ho * stride + kh - pad, wi = wo * stride + kw - pad;
+                if (hi < 0 || hi >= H || wi < 0 || wi >= W) continue;
+                acc += img[(ci * H + hi) * W + wi] * __ldg(wrow + r);
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) out[(n * Cout + co) * npix + p] = fmaxf(acc + bias[co], 0.f);
+        }
+    }
+}
+
+__global__ void lpips_maxpool_kernel(const float* __restrict__ in, float* __restrict__ out, long long NC, int H, int W,
+                                     int Ho, int Wo) {
+    const long long total = NC * Ho * Wo;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int wo = static_cast<int>(i % Wo);
+        const int ho = static_cast<int>((i / Wo) % Ho);
+        const long long nc = i / (static_cast<long long>(Wo) * Ho);
+        float m = -INFINITY;
+        for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) {
+                const int hi = ho * 2 + kh, wi = wo * 2 + kw;
+                if (hi < H && wi < W) m = fmaxf(m, in[(nc * H + hi) * W + wi]);
+            }
+        out[i] = m;
+    }
+}
+
+struct LpipsFeat {
+    const float* f[5];  // [2B, C_k, npix_k]
+    const float* lin[5];
+    int npix[5];
+};
+
+// One CTA per image pair: sum_k mean_p sum_c lin_k[c] * (f0/(|f0|+eps) - f1/(|f1|+eps))^2
+__global__ void __launch_bounds__(256) lpips_distance_kernel(LpipsFeat F, int B, float* __restrict__ out) {
+    __shared__ float s_red[8];
+    __shared__ float s_total;
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_total = 0.f;
+    __syncthreads();
+    for (int k = 0; k < 5; ++k) {
+        const int Ck = (k == 0) ? 64 : (k == 1 ? 192 : (k == 2 ? 384 : 256));
+        const int np = F.npix[k];
+        const float* f0 = F.f[k] + static_cast<long long>(b) * Ck * np;
+        const float* f1 = F.f[k] + static_cast<long long>(b + B) * Ck * np;
+        float layer = 0.f;  // per-warp partial over its pixels
+        for (int p = warp; p < np; p += 8) {
+            float n0 = 0.f, n1 = 0.f;
+            for (int c = lane; c < Ck; c += 32) {
+                const float a = f0[c * np + p], d = f1[c * np + p];
+                n0 += a * a;
+                n1 += d * d;
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                n0 += __shfl_xor_sync(0xffffffffu, n0, o);
+                n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+            }
+            const float i0 = 1.0f / (sqrtf(n0) + 1e-10f), i1 = 1.0f / (sqrtf(n1) + 1e-10f);
+            float acc = 0.f;
+            for (int c = lane; c < Ck; c += 32) {
+                const float d = f0[c * np + p] * i0 - f1[c * np + p] * i1;
+                acc += F.lin[k][c] * d * d;
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            layer += acc;
+        }
+        if (lane == 0) s_red[warp] = layer;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int i = 0; i < 8; ++i) t += s_red[i];
+            s_total += t / static_cast<float>(np);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[b] = s_total;
+}
+
+// ------------------------------------------------------------------------------------------------ host
+Lpips::Lpips() {}
+Lpips::~Lpips() {
+    if (arena_) cudaFree(arena_);
+}
+
+int Lpips::init() {
+    size_t total = 0;
+    for (int k = 0; k < 5; ++k) total += static_cast<size_t>(kChn[k]) * kCin[k] * kK[k] * kK[k] + kChn[k] + kChn[k];
+    if (cudaMalloc(&arena_, total * sizeof(float)) != cudaSuccess) {
+        set_error("lpips: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return 6;
+    }
+    float* p = arena_;
+    static const char* conv_names[5] = {"net.slice1.0", "net.slice2.3", "net.slice3.6", "net.slice4.8", "net.slice5.10"};
+    for (int k = 0; k < 5; ++k) {
+        w_[k] = p; p += static_cast<size_t>(kChn[k]) * kCin[k] * kK[k] * kK[k];
+        b_[k] = p; p += kChn[k];
+        lin_[k] = p; p += kChn[k];
+        slots_[std::string(conv_names[k]) + ".weight"] = {w_[k], static_cast<long long>(kChn[k]) * kCin[k] * kK[k] * kK[k], false};
+        slots_[std::string(conv_names[k]) + ".bias"] = {b_[k], kChn[k], false};
+        slots_["lin" + std::to_string(k) + ".model.1.weight"] = {lin_[k], kChn[k], false};
+    }
+    return 0;
+}
+
+int Lpips::set_param(const char* name, const float* data, long long numel, cudaStream_t stream) {
+    auto it = slots_.find(name);
+    if (it == slots_.end()) { set_error("lpips: unexpected parameter '%s'", name); return 8; }
+    if (it->second.numel != numel) { set_error("lpips: parameter '%s' has %lld elements, expected %lld", name, numel, it->second.numel); return 8; }
+    cudaError_t e = cudaMemcpyAsync(it->second.dst, data, numel * sizeof(float), cudaMemcpyDeviceToDevice, stream);
+    if (e != cudaSuccess) { set_error("lpips: copy failed: %s", cudaGetErrorString(e)); return 5; }
+    it->second.set = true;
+    return 0;
+}
+
+int Lpips::finalize() {
+    for (auto& kv : slots_)
+        if (!kv.second.set) { set_error("lpips: parameter '%s' was never set", kv.first.c_str()); return 8; }
+    ready_ = true;
+    return 0;
+}
+
+static void lpips_dims(int H, int W, int (&h)[5], int (&w)[5], int (&ph)[2], int (&pw)[2]) {
+    h[0] = (H + 4 - 11) / 4 + 1; w[0] = (W + 4 - 11) / 4 + 1;
+    ph[0] = (h[0] - 3) / 2 + 1;  pw[0] = (w[0] - 3) / 2 + 1;   // maxpool
+    h[1] = ph[0];                w[1] = pw[0];                 // 5x5 pad 2
+    ph[1] = (h[1] - 3) / 2 + 1;  pw[1] = (w[1] - 3) / 2 + 1;
+    h[2] = h[3] = h[4] = ph[1];  w[2] = w[3] = w[4] = pw[1];
+}
+
+size_t Lpips::workspace_bytes(int B, int H, int W) const {
+    int h[5], w[5], ph[2], pw[2];
+    lpips_dims(H, W, h, w, ph, pw);
+    if (H < 11 - 4 || W < 11 - 4 || h[0] < 3 || w[0] < 3 || h[1] < 3 || w[1] < 3) return 0;
+    size_t fl = static_cast<size_t>(2) * B * 3 * H * W;
+    for (int k = 0; k < 5; ++k) fl += static_cast<size_t>(2) * B * kChn[k] * h[k] * w[k];
+    fl += static_cast<size_t>(2) * B * 64 * ph[0] * pw[0] + static_cast<size_t>(2) * B * 192 * ph[1] * pw[1];
+    return fl * sizeof(float) + 16 * 256;
+}
+
+int Lpips::forward(const float* in0, const float* in1, float* out, int B, int C, int H, int W, bool normalize, void* ws,
+                   size_t ws_bytes, cudaStream_t stream) {
+    if (!ready_) { set_error("lpips: forward before finalize()"); return 10; }
+    if (C != 1 && C != 3) { set_error("lpips: %d input channels unsupported (1 or 3)", C); return 2; }
+    const size_t need = workspace_bytes(B, H, W);
+    if (!need) { set_error("lpips: %dx%d input is too small for AlexNet (the reference pads 28x28 to 32x32)", H, W); return 2; }
+    if (need > ws_bytes) { set_error("lpips: workspace too small (%zu < %zu)", ws_bytes, need); return 9; }
+    int h[5], w[5], ph[2], pw[2];
+    lpips_dims(H, W, h, w, ph, pw);
+    const int NB = 2 * B;
+    float* p = static_cast<float*>(ws);
+    auto take = [&](size_t n) { float* r = p; p += (n + 63) & ~size_t(63); return r; };
+    float* x = take(static_cast<size_t>(NB) * 3 * H * W);
+    float* f[5];
+    for (int k = 0; k < 5; ++k) f[k] = take(static_cast<size_t>(NB) * kChn[k] * h[k] * w[k]);
+    float* p0 = take(static_cast<size_t>(NB) * 64 * ph[0] * pw[0]);
+    float* p1 = take(static_cast<size_t>(NB) * 192 * ph[1] * pw[1]);
+
+    auto blocks_for = [](long long n) { long long b = (n + 255) / 256; return static_cast<int>(b > 148 * 16 ? 148 * 16 : b); };
+    lpips_scale_kernel<<<blocks_for(static_cast<long long>(NB) * 3 * H * W), 256, 0, stream>>>(
+        in0, in1, x, B, C, H * W, normalize ? 1 : 0, make_float3(-0.030f, -0.088f, -0.188f),
+        make_float3(0.458f, 0.448f, 0.450f));
+    LP_CHECK("lpips_scale");
+    const float* cur = x;
+    int ch = H, cw = W;
+    for (int k = 0; k < 5; ++k) {
+        if (k == 1 || k == 2) {
+            float* pool = (k == 1) ? p0 : p1;
+            const int oh = ph[k - 1], ow = pw[k - 1];
+            lpips_maxpool_kernel<<<blocks_for(static_cast<long long>(NB) * kCin[k] * oh * ow), 256, 0, stream>>>(
+                cur, pool, static_cast<long long>(NB) * kCin[k], ch, cw, oh, ow);
+            LP_CHECK("lpips_maxpool");
+            cur = pool; ch = oh; cw = ow;
+        }
+        const int npix = h[k] * w[k];
+        const long long warps = static_cast<long long>(NB) * kChn[k] * ((npix + 31) / 32);
+        const long long blocks = (warps * 32 + 255) / 256;
+        lpips_conv_relu_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(cur, w_[k], b_[k], f[k], NB, kCin[k], ch, cw,
+                                                                                  kChn[k], h[k], w[k], kK[k], kStride[k], kPad[k]);
+        LP_CHECK("lpips_conv");
+        cur = f[k]; ch = h[k]; cw = w[k];
+    }
+    LpipsFeat F;
+    for (int k = 0; k < 5; ++k) { F.f[k] = f[k]; F.lin[k] = lin_[k]; F.npix[k] = h[k] * w[k]; }
+    lpips_distance_kernel<<<B, 256, 0, stream>>>(F, B, out);
+    LP_CHECK("lpips_distance");
+    launches_ += 9;
+    return 0;
+}
+
+}  // namespace ddpm

@@ -1,0 +1,135 @@
+"""Minimal host-side data ingest for the reconstruction CLI.
+
+The reference's loader (src/data/get_train_and_val_dataloader.py) is MONAI-based host I/O and is OUT OF SCOPE for the
+accelerated path; this module only restates enough of it for `reconstruct.py` to run end to end
+on the reference's own `.npy` datasets (src/data/get_computer_vision_datasets.py writes [H,W] uint8 for grayscale and
+[3,H,W] uint8 for colour) and to reproduce its multi-GPU image partition (get_train_and_val_dataloader.py:21-31).
+Batches have the reference's structure: {"image": Tensor[B,C,...], "image_meta_dict": {"filename_or_obj": [...]}}.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Iterator, List, Optional, Sequence
+
+import numpy as np
+import pandas as pd
+import torch
+import torch.nn.functional as F
+
+
+def partition_indices(data_len: int, num_partitions: int, rank: int, shuffle: bool = True, seed: int = 0,
+                      drop_last: bool = False, even_divisible: bool = True) -> List[int]:
+    """Restatement of monai.data.partition_dataset(num_partitions=..., shuffle=True, seed=0, drop_last=False,
+    even_divisible=True)[rank] as called at get_train_and_val_dataloader.py:24-31 [3P-RECALL]: seeded shuffle, wrap-pad
+    to a multiple of the world size, then a strided slice per rank."""
+    if data_len < num_partitions:
+        raise RuntimeError(f"there is no enough data to be split into {num_partitions} partitions.")
+    indices = list(range(data_len))
+    if shuffle:
+        np.random.RandomState(seed).shuffle(indices)
+    if drop_last and data_len % num_partitions != 0:
+        num_samples = math.ceil((data_len - num_partitions) / num_partitions)
+    else:
+        num_samples = math.ceil(data_len / num_partitions)
+    total_size = num_samples * num_partitions
+    if even_divisible:
+        if not drop_last and total_size - data_len > 0:
+            indices += indices[: (total_size - data_len)]
+        else:
+            indices = indices[:total_size]
+    return indices[rank:total_size:num_partitions]
+
+
+def get_data_dicts(ids_path: str, first_n=False, rank: Optional[int] = None, world_size: Optional[int] = None):
+    # the split files are ONE csv row of paths; pandas reads it as the header (get_train_and_val_dataloader.py:10-17)
+    paths = list(pd.read_csv(ids_path, sep=","))
+    dicts = [{"image": p} for p in paths]
+    if first_n is not False and first_n is not None:
+        dicts = dicts[: int(first_n)]
+    print(f"Found {len(dicts)} subjects.")
+    if world_size is not None and world_size > 1:
+        idx = partition_indices(len(dicts), world_size, rank)
+        dicts = [dicts[i] for i in idx]
+    return dicts
+
+
+def _load(path: str) -> np.ndarray:
+    if path.endswith(".npy"):
+        return np.load(path)
+    if path.endswith(".pt"):
+        return torch.load(path, map_location="cpu").numpy()
+    raise NotImplementedError(f"only .npy/.pt images are supported by the minimal loader (got {path}); NIfTI needs "
+                              f"nibabel, which is not part of this environment")
+
+
+def _transform(arr: np.ndarray, is_grayscale: bool, spatial_dimension: int, image_size, image_roi, add_vflip: bool,
+               add_hflip: bool) -> torch.Tensor:
+    x = torch.from_numpy(np.ascontiguousarray(arr)).float()
+    if is_grayscale:
+        if x.dim() == spatial_dimension:  # EnsureChannelFirstd
+            x = x[None]
+        x = x[0, None, ...]  # "needed for BRATs data with 4 modalities in 1"
+    if image_roi:
+        roi = [int(r) for r in image_roi]
+        sl = [slice(None)]
+        for d, r in enumerate(roi):
+            size = x.shape[1 + d]
+            if r < 0 or r >= size:
+                sl.append(slice(None))
+            else:
+                start = (size - r) // 2
+                sl.append(slice(start, start + r))
+        x = x[tuple(sl)]
+    if image_size:
+        size = (int(image_size),) * spatial_dimension
+        x = F.interpolate(x[None], size=size, mode="area")[0]  # monai Resize default mode
+    mn, mx = x.min(), x.max()
+    x = (x - mn) / (mx - mn) if mx > mn else x - mn  # ScaleIntensityd(minv=0, maxv=1)
+    if add_vflip:
+        x = torch.flip(x, dims=(1,))
+    if add_hflip:
+        x = torch.flip(x, dims=(2,))
+    return x.contiguous()
+
+
+class SimpleLoader:
+    """Sequential, un-shuffled batches (the reference's val loader: ThreadDataLoader(shuffle=False))."""
+
+    def __init__(self, dicts: Sequence[Dict[str, str]], batch_size: int, drop_last: bool, **tf):
+        self.dicts = list(dicts)
+        self.batch_size = batch_size
+        self.drop_last = drop_last
+        self.tf = tf
+        self._cache: Dict[int, torch.Tensor] = {}
+
+    def __len__(self) -> int:
+        n = len(self.dicts)
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self) -> Iterator[Dict]:
+        n = len(self.dicts)
+        for s in range(0, n, self.batch_size):
+            idx = list(range(s, min(s + self.batch_size, n)))
+            if self.drop_last and len(idx) < self.batch_size:
+                return
+            imgs = []
+            for i in idx:
+                if i not in self._cache:
+                    self._cache[i] = _transform(_load(self.dicts[i]["image"]), **self.tf)
+                imgs.append(self._cache[i])
+            yield {"image": torch.stack(imgs), "image_meta_dict": {"filename_or_obj": [self.dicts[i]["image"] for i in idx]}}
+
+
+def get_training_data_loader(batch_size: int, training_ids: str, validation_ids: str, only_val: bool = False,
+                             augmentation: bool = True, drop_last: bool = False, num_workers: int = 8,
+                             num_val_workers: int = 3, cache_data=True, first_n=None, is_grayscale=False,
+                             add_vflip=False, add_hflip=False, image_size=None, image_roi=None, spatial_dimension=2,
+                             rank: Optional[int] = None, world_size: Optional[int] = None):
+    """Same signature as the reference's get_training_data_loader (get_train_and_val_dataloader.py:36-53); only the
+    validation-style loader (only_val=True) is on the reconstruction path."""
+    if not only_val:
+        raise NotImplementedError("training loaders are out of scope for the reconstruction path")
+    dicts = get_data_dicts(validation_ids, first_n=first_n if first_n else False, rank=rank, world_size=world_size)
+    return SimpleLoader(dicts, batch_size, bool(drop_last), is_grayscale=bool(is_grayscale),
+                        spatial_dimension=spatial_dimension, image_size=image_size, image_roi=image_roi,
+                        add_vflip=add_vflip, add_hflip=add_hflip)

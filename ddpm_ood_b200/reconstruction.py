@@ -1,0 +1,129 @@
+"""The reconstruction hot loop (src/trainers/reconstruct.py:96-204) on the B200 engine.
+
+`BatchReconstructor.score_batch` is what one iteration of the reference's `for batch in loader:` body computes:
+for every t-start of the grid, forward-noise the batch, run the PLMS reverse chain of UNet evaluations (ONE engine call
+per t-start: UNet forward + fused scheduler update per step), un-scale/clamp, LPIPS and MSE. All per-(image, t-start)
+scores stay on the device until the batch is done (the reference syncs with `.item()` 2·B times per t-start).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .schedulers import PNDMScheduler
+
+
+def snr_shift_(scheduler, snr_shift: float) -> None:
+    """src/trainers/base.py:104-116 and src/trainers/reconstruct.py:106-117 (identical blocks)."""
+    if snr_shift == 1:
+        return
+    snr = scheduler.alphas_cumprod / (1 - scheduler.alphas_cumprod)
+    target_snr = snr * snr_shift
+    new_alphas_cumprod = 1 / (torch.pow(target_snr, -1) + 1)
+    new_alphas = torch.zeros_like(new_alphas_cumprod)
+    new_alphas[0] = new_alphas_cumprod[0]
+    for i in range(1, len(new_alphas)):
+        new_alphas[i] = new_alphas_cumprod[i] / new_alphas_cumprod[i - 1]
+    scheduler.betas = 1 - new_alphas
+    scheduler.alphas = new_alphas
+    scheduler.alphas_cumprod = new_alphas_cumprod
+
+
+def clamp_mse(x: torch.Tensor, x0: torch.Tensor, b_scale: float):
+    """recon = clamp(x / b_scale, 0, 1); mse[b] = mean((x0 - recon)^2) — trainers/reconstruct.py:167-168,188-191."""
+    n = x.shape[0]
+    recon = torch.empty_like(x)
+    mse = torch.empty((n,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().ddpm_clamp_mse(x.data_ptr(), x0.data_ptr(), float(b_scale), recon.data_ptr(),
+                                             mse.data_ptr(), n, x.numel() // max(n, 1),
+                                             torch.cuda.current_stream().cuda_stream), "ddpm_clamp_mse")
+    return recon, mse
+
+
+@dataclass
+class ReconConfig:
+    prediction_type: str = "epsilon"
+    beta_schedule: str = "linear"
+    beta_start: float = 1e-4
+    beta_end: float = 2e-2
+    b_scale: float = 1.0
+    snr_shift: float = 1.0
+    spatial_dimension: int = 2
+    num_inference_steps: int = 100  # the reference hard-codes 100 (trainers/reconstruct.py:118)
+    plms_state: str = "carry"       # "carry": scheduler state survives across t-starts (reference-faithful); "reset"
+
+
+class BatchReconstructor:
+    def __init__(self, model, perceptual, cfg: ReconConfig, device, vqvae_model=None, latent_pad=None):
+        self.model = model
+        self.pl = perceptual
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.vqvae_model = vqvae_model
+        self.latent_pad = latent_pad
+        if cfg.plms_state not in ("carry", "reset"):
+            raise ValueError("plms_state must be 'carry' or 'reset'")
+
+    def make_scheduler(self) -> PNDMScheduler:
+        c = self.cfg
+        s = PNDMScheduler(num_train_timesteps=1000, skip_prk_steps=True, prediction_type=c.prediction_type,
+                          schedule=c.beta_schedule, beta_start=c.beta_start, beta_end=c.beta_end)
+        snr_shift_(s, c.snr_shift)
+        s.set_timesteps(c.num_inference_steps)
+        return s
+
+    @torch.no_grad()
+    def score_batch(self, images_original: torch.Tensor, inference_skip_factor: int,
+                    noise_fn: Optional[Callable[[int, int], torch.Tensor]] = None,
+                    keep_recons: bool = False) -> Dict[str, object]:
+        """images_original: [B, C, ...] in [0, 1], host or device. Returns device tensors:
+        {"t": int64 [n_t] (host), "perceptual_difference": fp32 [n_t, B], "mse": fp32 [n_t, B]}."""
+        c = self.cfg
+        sched = self.make_scheduler()
+        timesteps = sched.timesteps
+        starts = reversed(timesteps)[1::inference_skip_factor]  # the t-start grid, trainers/reconstruct.py:119-120
+        images_original = images_original.to(self.device, non_blocking=True).float().contiguous()
+        images = images_original if self.vqvae_model is None else self.vqvae_model.encode_stage_2_inputs(images_original)
+        if self.latent_pad:
+            images = F.pad(input=images, pad=self.latent_pad, mode="constant", value=0)
+        images = images.contiguous()
+        B = images.shape[0]
+        n_t = len(starts)
+        pd_all = torch.empty((n_t, B), dtype=torch.float32, device=self.device)
+        mse_all = torch.empty((n_t, B), dtype=torch.float32, device=self.device)
+        recons = []
+        scaled = images * c.b_scale if c.b_scale != 1 else images
+        for i, t_start in enumerate(starts):
+            if c.plms_state == "reset":
+                sched.reset_chain()
+            start_timesteps = torch.Tensor([t_start] * B).long()
+            noise = noise_fn(i, int(t_start)) if noise_fn is not None else torch.randn_like(images)
+            x = sched.add_noise(original_samples=scaled, noise=noise, timesteps=start_timesteps)
+            chain = [int(s) for s in timesteps[timesteps <= t_start]]
+            sched.run_chain(self.model, x, chain)
+            if self.latent_pad:
+                x = F.pad(input=x, pad=[-p for p in self.latent_pad], mode="constant", value=0).contiguous()
+            if self.vqvae_model is not None:
+                x = self.vqvae_model.decode_stage_2_outputs(x).float().contiguous()
+            recon, mse = clamp_mse(x, images_original, c.b_scale)
+            if c.spatial_dimension == 2:
+                if images_original.shape[3] == 28:
+                    pd = self.pl(F.pad(images_original, (2, 2, 2, 2)), F.pad(recon, (2, 2, 2, 2)))
+                else:
+                    pd = self.pl(images_original, recon)
+                pd_all[i] = pd.reshape(B)
+            else:
+                for b in range(B):  # per item, as the reference does in 3-D (trainers/reconstruct.py:181-187)
+                    pd_all[i, b] = self.pl(images_original[b, None, ...], recon[b, None, ...])
+            mse_all[i] = mse
+            if keep_recons:
+                recons.append(recon)
+        out: Dict[str, object] = {"t": starts.clone(), "perceptual_difference": pd_all, "mse": mse_all}
+        if keep_recons:
+            out["recons"] = recons
+        return out

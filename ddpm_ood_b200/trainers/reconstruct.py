@@ -1,0 +1,136 @@
+"""`Reconstruct` trainer: src/trainers/reconstruct.py on the B200 engine. Same constructor, `get_scores`, `reconstruct`
+and CSV contract (`ood/results_{val,in,<name>}.csv`, columns filename,type,t,perceptual_difference,mse + pandas index).
+
+Differences that do not change results: per-(image, t-start) scores stay on the device until a batch is finished (one
+D2H copy per batch instead of 2·B `.item()` syncs per t-start, reference :192-204); the multi-GPU gather moves the
+score tensor with one NCCL all-gather (+ a host all_gather_object for the file names) instead of pickling every row
+(reference :238-242); no matplotlib figure.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+from pathlib import Path
+
+import pandas as pd
+import torch
+import torch.distributed as dist
+
+from ..data import get_training_data_loader
+from ..losses import PerceptualLoss
+from ..reconstruction import BatchReconstructor, ReconConfig
+from .base import BaseTrainer
+
+
+class Reconstruct(BaseTrainer):
+    def __init__(self, args):
+        super().__init__(args)
+        if not self.found_checkpoint:
+            raise FileNotFoundError("Failed to find a saved model checkpoint.")
+        self.out_dir = self.run_dir / "ood"
+        self.out_dir.mkdir(exist_ok=True)
+        self.args = args
+        self.val_loader = self._loader(args, args.validation_ids, args.first_n_val)
+        self.in_loader = self._loader(args, args.in_ids, args.first_n)
+        self._pl = None
+
+    def _loader(self, args, ids, first_n, **flip):
+        rank = dist.get_rank() if dist.is_initialized() else None
+        world = dist.get_world_size() if dist.is_initialized() else None
+        return get_training_data_loader(
+            batch_size=args.batch_size, training_ids=ids, validation_ids=ids, augmentation=bool(args.augmentation),
+            only_val=True, num_workers=args.num_workers, num_val_workers=args.num_workers,
+            cache_data=bool(args.cache_data), drop_last=bool(args.drop_last),
+            first_n=int(first_n) if first_n else first_n, is_grayscale=bool(args.is_grayscale),
+            spatial_dimension=args.spatial_dimension, image_size=self.image_size, image_roi=args.image_roi,
+            rank=rank, world_size=world, **flip)
+
+    def _engine(self) -> BatchReconstructor:
+        if self._pl is None:
+            self._pl = PerceptualLoss(dimensions=self.spatial_dimension, include_pixel_loss=False,
+                                      is_fake_3d=True if self.spatial_dimension == 3 else False, lpips_normalize=True,
+                                      spatial=False).to(self.device)
+        steps = 100  # hard-coded in the reference (trainers/reconstruct.py:118); --num_inference_steps is parsed, unused
+        if getattr(self.args, "honour_num_inference_steps", 0):
+            steps = int(self.args.num_inference_steps)
+        cfg = ReconConfig(prediction_type=self.prediction_type, beta_schedule=self.beta_schedule,
+                          beta_start=self.beta_start, beta_end=self.beta_end, b_scale=self.b_scale,
+                          snr_shift=self.snr_shift, spatial_dimension=self.spatial_dimension,
+                          num_inference_steps=steps, plms_state=getattr(self.args, "plms_state", "carry"))
+        return BatchReconstructor(self.model, self._pl, cfg, self.device, vqvae_model=None,
+                                  latent_pad=self.latent_pad if self.do_latent_pad else None)
+
+    def get_scores(self, loader, dataset_name, inference_skip_factor):
+        if dist.is_initialized():
+            sys.stdout = sys.__stdout__
+            sys.stderr = sys.__stderr__
+            print(f"{dist.get_rank()}: {dataset_name}")
+        else:
+            print(f"{dataset_name}")
+        engine = self._engine()
+        self.model.eval()
+        names, ts, pds, mses = [], [], [], []
+        for batch in loader:
+            t1 = time.time()
+            res = engine.score_batch(batch["image"], inference_skip_factor)
+            t_grid = res["t"]
+            pd_host = res["perceptual_difference"].cpu()  # one D2H per batch
+            mse_host = res["mse"].cpu()
+            B = pd_host.shape[1]
+            stems = [Path(f).stem.replace(".nii", "").replace(".gz", "")
+                     for f in batch["image_meta_dict"]["filename_or_obj"]]
+            for i in range(len(t_grid)):  # row order of the reference: t-start outer, batch item inner
+                names.extend(stems)
+                ts.append(torch.full((B,), int(t_grid[i]), dtype=torch.float64))
+                pds.append(pd_host[i].double())
+                mses.append(mse_host[i].double())
+            t2 = time.time()
+            if dist.is_initialized():
+                print(f"{dist.get_rank()}: Took {t2-t1}s for a batch size of {B}")
+            else:
+                print(f"Took {t2-t1}s for a batch size of {B}")
+        scores = torch.stack([torch.cat(ts), torch.cat(pds), torch.cat(mses)], dim=1) if ts else torch.zeros((0, 3), dtype=torch.float64)
+        if dist.is_initialized():
+            world = dist.get_world_size()
+            local = scores.to(self.device)
+            gathered = torch.empty((world * local.shape[0], 3), dtype=local.dtype, device=self.device)
+            dist.all_gather_into_tensor(gathered, local)  # NCCL over NVLink; even_divisible partition => equal sizes
+            all_names = [None] * world
+            dist.all_gather_object(all_names, names)
+            names = [n for sub in all_names for n in sub]
+            scores = gathered.cpu()
+            local_rank = int(os.environ["LOCAL_RANK"])
+            if local_rank != 0:
+                f = open(os.devnull, "w")
+                sys.stdout = sys.stderr = f
+        return [
+            {"filename": names[r], "type": dataset_name, "t": int(scores[r, 0]),
+             "perceptual_difference": float(scores[r, 1]), "mse": float(scores[r, 2])}
+            for r in range(scores.shape[0])
+        ]
+
+    def reconstruct(self, args):
+        if bool(args.run_val):
+            pd.DataFrame(self.get_scores(self.val_loader, "val", args.inference_skip_factor)).to_csv(
+                self.out_dir / "results_val.csv")
+        if bool(args.run_in):
+            pd.DataFrame(self.get_scores(self.in_loader, "in", args.inference_skip_factor)).to_csv(
+                self.out_dir / "results_in.csv")
+        if bool(args.run_out):
+            for out in args.out_ids.split(","):
+                print(out)
+                if "vflip" in out:
+                    out = out.replace("_vflip", "")
+                    out_loader = self._loader(args, out, args.first_n, add_vflip=True)
+                    dataset_name = Path(out).stem.split("_")[0] + "_vflip"
+                elif "hflip" in out:
+                    out = out.replace("_hflip", "")
+                    out_loader = self._loader(args, out, args.first_n, add_hflip=True)
+                    dataset_name = Path(out).stem.split("_")[0] + "_hflip"
+                else:
+                    out_loader = self._loader(args, out, args.first_n)
+                    dataset_name = Path(out).stem.split("_")[0]
+                # every out-of-distribution set gets type "out" (reference :328); the name only reaches the file name
+                results_list = self.get_scores(out_loader, "out", args.inference_skip_factor)
+                pd.DataFrame(results_list).to_csv(self.out_dir / f"results_{dataset_name}.csv")

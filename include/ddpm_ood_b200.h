@@ -65,6 +65,84 @@ DDPM_API int ddpm_conv_forward(const ddpm_conv_args* args, void* stream);
 DDPM_API int ddpm_pack_conv_weight(const float* w, int Cout, int Cin, int taps, void* dst, long long ktot, long long koff,
                           void* stream);
 
+/* ------------------------------------------------------------------------------------------------ DiffusionModelUNet
+ * Replaces `DiffusionModelUNet(...)` (src/trainers/base.py:66-86), `load_state_dict` (base.py:145) and
+ * `model(x, timesteps=...)` (src/trainers/reconstruct.py:150-153; kw form src/trainers/ddpm_trainer.py:104).
+ * The handle owns fp16-packed copies of the weights; everything else is caller memory. */
+#define DDPM_MAX_LEVELS 8
+typedef struct ddpm_unet_config {
+    int spatial_dims;                        /* 2 or 3 */
+    int in_channels, out_channels;           /* <= 8, or a multiple of 64 (in) / 128 (out) for latent models */
+    int num_levels;
+    int num_channels[DDPM_MAX_LEVELS];       /* multiples of 128 */
+    int attention_levels[DDPM_MAX_LEVELS];   /* 0 / 1 */
+    int num_res_blocks[DDPM_MAX_LEVELS];
+    int num_head_channels[DDPM_MAX_LEVELS];  /* 256 */
+    int norm_num_groups;                     /* 32 */
+    float norm_eps;                          /* 1e-6 */
+} ddpm_unet_config;
+
+DDPM_API int ddpm_unet_create(const ddpm_unet_config* cfg, void** handle);
+DDPM_API void ddpm_unet_destroy(void* handle);
+/* name: a state_dict key of monai-generative's DiffusionModelUNet ("conv_in.conv.weight", ...); data: device fp32,
+ * contiguous, PyTorch layout. */
+DDPM_API int ddpm_unet_set_param(void* handle, const char* name, const float* data, long long numel, void* stream);
+/* Fails (naming the key) unless every parameter has been set. */
+DDPM_API int ddpm_unet_finalize(void* handle, void* stream);
+/* Bytes of caller-provided scratch needed for a forward of this shape; 0 on error. */
+DDPM_API long long ddpm_unet_workspace_bytes(void* handle, int N, int D, int H, int W);
+/* x: fp32 [N, Cin, (D,) H, W]; timesteps: int64 [N] on the device; out: fp32 like x with Cout channels. */
+DDPM_API int ddpm_unet_forward(void* handle, const float* x, const long long* timesteps, float* out, int N, int D, int H,
+                               int W, void* workspace, long long workspace_bytes, void* stream);
+/* Number of kernels launched by this handle so far (bench.py's gpu_launches). */
+DDPM_API long long ddpm_unet_launch_count(void* handle);
+
+/* ------------------------------------------------------------------------------------------------ scheduler
+ * Replaces `PNDMScheduler.add_noise` (src/trainers/reconstruct.py:143-147) and `PNDMScheduler.step`
+ * (src/trainers/reconstruct.py:155-157). Scheduler STATE (counter, eps history bookkeeping, alphas_cumprod which the
+ * reference overwrites at :107-117) stays with the host-side Python mirror; each call carries the coefficients. */
+typedef struct ddpm_plms_step {
+    float c[4];      /* eps_bar = c0*eps_new + c1*h1 + c2*h2 + c3*h3 (h1 newest history entry before this step) */
+    float vA, vB;    /* model_output' = vA*eps_bar + vB*sample (v-prediction), (1, 0) for epsilon */
+    float A, Bc;     /* prev_sample = A*sample - Bc*model_output' */
+    int use_stash;   /* sample := stashed cur_sample (the counter == 1 corrector step) */
+    int write_stash; /* stash := sample (counter == 0) */
+    int push;        /* append eps_new to the history ring */
+    int slot_new;    /* ring slot receiving eps_new */
+    int slot[3];     /* ring slots of h1, h2, h3 */
+} ddpm_plms_step;
+
+DDPM_API int ddpm_add_noise(const float* x0, const float* noise, const float* alphas_cumprod /*device [T]*/,
+                            const long long* timesteps /*device [N] or NULL*/, int t_uniform, float b_scale, float* out,
+                            int N, long long per_image, void* stream);
+/* ring: fp32 [4][numel]; stash/sample_in/sample_out: fp32 [numel] (sample_out may alias sample_in). */
+DDPM_API int ddpm_plms_update(const float* model_output, const ddpm_plms_step* step, float* ring, float* stash,
+                              const float* sample_in, float* sample_out, long long numel, void* stream);
+/* The inner loop of src/trainers/reconstruct.py:149-157 in one call: for each of the n_steps timesteps (host array,
+ * shared by the whole batch) run the UNet on `sample` and apply the PLMS update, fused after the output conv.
+ * sample is updated in place. */
+DDPM_API int ddpm_unet_run_chain(void* handle, int n_steps, const int* timesteps, const ddpm_plms_step* steps,
+                                 float* sample, float* ring, float* stash, int N, int D, int H, int W, void* workspace,
+                                 long long workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ scoring
+ * recon = clamp(x / b_scale, 0, 1) and mse[n] = mean((x0 - recon)^2): src/trainers/reconstruct.py:167-168,188-191. */
+DDPM_API int ddpm_clamp_mse(const float* x, const float* x0, float b_scale, float* recon, float* mse, int N,
+                            long long per_image, void* stream);
+
+/* LPIPS (AlexNet, v0.1, linear heads, spatial mean): replaces `lpips.LPIPS(...).forward(in0, in1, normalize=...)`
+ * reached through src/losses/perceptual_loss.py:100-102,125,181-183 from src/trainers/reconstruct.py:170-187.
+ * Parameter names are lpips.LPIPS state_dict keys: net.slice{1..5}.{0,3,6,8,10}.{weight,bias}, lin{0..4}.model.1.weight.
+ * in0/in1: fp32 [B, C, H, W] with C in {1, 3} (1 broadcasts, as the ScalingLayer does); out: fp32 [B]. */
+DDPM_API int ddpm_lpips_create(void** handle);
+DDPM_API void ddpm_lpips_destroy(void* handle);
+DDPM_API int ddpm_lpips_set_param(void* handle, const char* name, const float* data, long long numel, void* stream);
+DDPM_API int ddpm_lpips_finalize(void* handle);
+DDPM_API long long ddpm_lpips_workspace_bytes(void* handle, int B, int H, int W);
+DDPM_API int ddpm_lpips_forward(void* handle, const float* in0, const float* in1, float* out, int B, int C, int H, int W,
+                                int normalize, void* workspace, long long workspace_bytes, void* stream);
+DDPM_API long long ddpm_lpips_launch_count(void* handle);
+
 #ifdef __cplusplus
 }
 #endif
