@@ -66,6 +66,22 @@ class PlmsStep(C.Structure):
     ]
 
 
+NUM_OP_TYPES = 9
+OP_TYPE_NAMES = ("conv_in_small", "conv_in_gemm", "groupnorm_silu", "conv_gemm", "attention_core", "upsample",
+                 "conv_out_small_plms", "conv_out_gemm", "time_embed")
+
+
+class OpProfile(C.Structure):
+    _fields_ = [
+        ("ms", C.c_double * NUM_OP_TYPES),
+        ("flops", C.c_double * NUM_OP_TYPES),
+        ("bytes", C.c_double * NUM_OP_TYPES),
+        ("launches", C.c_longlong * NUM_OP_TYPES),
+        ("forwards", C.c_longlong),
+        ("forward_ms", C.c_double),
+    ]
+
+
 class DdpmError(RuntimeError):
     pass
 
@@ -85,6 +101,8 @@ SIGNATURES = {
     "ddpm_unet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]),
     "ddpm_unet_launch_count": (C.c_longlong, [C.c_void_p]),
+    "ddpm_unet_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "ddpm_unet_read_profile": (C.c_int, [C.c_void_p, C.POINTER(OpProfile), C.c_int]),
     "ddpm_add_noise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p,
                                  C.c_int, C.c_longlong, C.c_void_p]),
     "ddpm_plms_update": (C.c_int, [C.c_void_p, C.POINTER(PlmsStep), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

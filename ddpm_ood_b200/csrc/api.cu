@@ -156,6 +156,21 @@ long long ddpm_unet_launch_count(void* handle) {
     return handle ? static_cast<ddpm::UNet*>(handle)->launches() : 0;
 }
 
+int ddpm_unet_set_profile(void* handle, int every) {
+    if (!handle) { ddpm::set_error("ddpm_unet_set_profile: null handle"); return 2; }
+    static_cast<ddpm::UNet*>(handle)->set_profile(every);
+    return 0;
+}
+int ddpm_unet_read_profile(void* handle, ddpm_op_profile* out, int reset) {
+    if (!handle || !out) { ddpm::set_error("ddpm_unet_read_profile: null argument"); return 2; }
+    static_assert(sizeof(ddpm_op_profile) == sizeof(ddpm::OpProfile), "ddpm_op_profile must mirror ddpm::OpProfile");
+    static_assert(DDPM_NUM_OP_TYPES == ddpm::kNumOpTypes, "op type count mismatch");
+    ddpm::OpProfile p;
+    int rc = static_cast<ddpm::UNet*>(handle)->read_profile(&p, reset != 0);
+    memcpy(out, &p, sizeof(p));
+    return rc;
+}
+
 int ddpm_add_noise(const float* x0, const float* noise, const float* alphas_cumprod, const long long* timesteps,
                    int t_uniform, float b_scale, float* out, int N, long long per_image, void* stream) {
     return ddpm::add_noise(x0, noise, alphas_cumprod, timesteps, t_uniform, b_scale, out, N, per_image,

@@ -332,6 +332,18 @@ int UNet::finalize(cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------ planning
+static double conv_flops(const ConvProblem& q) {
+    const int sd3 = q.spatial_dims == 3;
+    const double Wo = (q.W + q.stride - 1) / q.stride, Ho = (q.H + q.stride - 1) / q.stride;
+    const double Do = sd3 ? (q.D + q.stride - 1) / q.stride : q.D;
+    double k = 0;
+    for (int s = 0; s < q.n_seg; ++s) {
+        const int taps = q.seg[s].ksize == 3 ? (sd3 ? 27 : 9) : 1;
+        k += static_cast<double>(taps) * q.seg[s].channels;
+    }
+    return 2.0 * q.N * Do * Ho * Wo * q.Cout * k;
+}
+
 struct UNet::Layout {
     uint8_t* base;
     size_t off = 0;
@@ -381,6 +393,7 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             op.src0 = a.p; op.C0 = a.C;
             op.src1 = b ? b->p : nullptr; op.C1 = b ? b->C : 0;
             op.gamma = g; op.beta = bt; op.dst = dst; op.S = static_cast<int>(a.S()); op.silu = silu;
+            op.bytes = 4.0 * static_cast<double>(cnt);  // one fp16 read + one fp16 write per element
             plan.ops.push_back(op);
         };
         auto gemm = [&](ConvProblem q, bool uses_temb) {
@@ -388,6 +401,7 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             Op op{};
             op.type = Op::GEMM;
             op.uses_temb = uses_temb;
+            op.flops = conv_flops(q);
             int r = conv_prepare(q, sms, &op.conv);
             if (r && !rc) rc = r;
             plan.ops.push_back(op);
@@ -454,6 +468,7 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
                 op.type = Op::ATTN;
                 op.src0 = qkv; op.dst = hB; op.T = static_cast<int>(h.S()); op.C = a.C; op.heads = a.heads;
                 op.scale = 1.0f / sqrtf(static_cast<float>(a.C) / static_cast<float>(a.heads));
+                op.flops = 4.0 * N * static_cast<double>(h.S()) * static_cast<double>(h.S()) * a.C;
                 plan.ops.push_back(op);
             }
             Act out = measure ? Act{nullptr, a.C, h.D, h.H, h.W} : new_act(a.C, h.D, h.H, h.W);
@@ -467,6 +482,8 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             Op op{};
             op.type = in_gemm_ ? Op::CONV_IN_GEMM : Op::CONV_IN_SMALL;
             op.dst = h.p; op.D = D; op.H = H; op.W = W;
+            op.flops = 2.0 * N * D * H * W * c.num_channels[0] * (sd == 3 ? 27.0 : 9.0) * c.in_channels;
+            op.bytes = static_cast<double>(N) * D * H * W * (4.0 * c.in_channels + 2.0 * c.num_channels[0]);
             if (in_gemm_ && !dry) {
                 ConvProblem q{};
                 q.spatial_dims = sd; q.N = N; q.D = D; q.H = H; q.W = W; q.stride = 1; q.n_seg = 1;
@@ -519,6 +536,7 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
                     Op op{};
                     op.type = Op::UPSAMPLE;
                     op.src0 = h.p; op.dst = up.p; op.D = h.D; op.H = h.H; op.W = h.W; op.C = h.C;
+                    op.bytes = 2.0 * cnt + 2.0 * cnt / (4.0 * fd);
                     plan.ops.push_back(op);
                 }
                 Act o = measure ? up : new_act(h.C, up.D, up.H, up.W);
@@ -533,6 +551,8 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             Op op{};
             op.type = out_gemm_ ? Op::CONV_OUT_GEMM : Op::CONV_OUT_SMALL;
             op.src0 = zA; op.D = D; op.H = H; op.W = W; op.C = h.C;
+            op.flops = 2.0 * N * D * H * W * c.out_channels * (sd == 3 ? 27.0 : 9.0) * h.C;
+            op.bytes = static_cast<double>(N) * D * H * W * (2.0 * h.C + 4.0 * c.out_channels);
             if (out_gemm_ && !dry) {
                 ConvProblem q{};
                 q.spatial_dims = sd; q.N = N; q.D = D; q.H = H; q.W = W; q.stride = 1; q.n_seg = 1;
@@ -582,6 +602,16 @@ int UNet::forward(const float* x, const long long* timesteps, int t_uniform, flo
     Plan& plan = *it->second;
     const UNetConfig& c = cfg_;
     const int R = timesteps ? N : 1;
+    const bool prof = profile_every_ > 0 && (profile_tick_++ % profile_every_ == 0);
+    if (prof) {
+        if (plan.events_pending) harvest(plan);
+        if (plan.events.empty()) {
+            plan.events.resize(plan.ops.size() + 2);
+            for (auto& e : plan.events) cudaEventCreate(&e);
+        }
+        cudaEventRecord(plan.events[0], stream);
+    }
+    size_t op_idx = 0;
     int rc = time_embed(timesteps, t_uniform, R, E_, te_w0_, te_b0_, te_w1_, te_b1_, plan.temb_act, stream);
     if (rc) return rc;
     rc = time_proj_all(plan.temb_act, R, 4 * E_, tp_w_, tp_b_, P_, plan.temb_all, stream);
@@ -589,6 +619,8 @@ int UNet::forward(const float* x, const long long* timesteps, int t_uniform, flo
     launches_ += 2;
     const long long S = static_cast<long long>(D) * H * W;
     for (Op& op : plan.ops) {
+        if (prof) cudaEventRecord(plan.events[1 + op_idx], stream);
+        ++op_idx;
         switch (op.type) {
             case Op::CONV_IN_SMALL:
                 rc = conv_in_small(x, conv_in_w_, conv_in_b_, op.dst, N, c.in_channels, D, H, W, c.num_channels[0],
@@ -635,6 +667,40 @@ int UNet::forward(const float* x, const long long* timesteps, int t_uniform, flo
         ++launches_;
         if (rc) return rc;
     }
+    if (prof) {
+        cudaEventRecord(plan.events[1 + op_idx], stream);
+        plan.events_pending = true;
+    }
+    return 0;
+}
+
+void UNet::harvest(Plan& plan) {
+    if (!plan.events_pending) return;
+    const size_t n = plan.ops.size();
+    cudaEventSynchronize(plan.events[n + 1]);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, plan.events[0], plan.events[1]);
+    prof_.ms[kNumOpTypes - 1] += ms;
+    prof_.launches[kNumOpTypes - 1] += 2;
+    for (size_t i = 0; i < n; ++i) {
+        const Op& op = plan.ops[i];
+        cudaEventElapsedTime(&ms, plan.events[1 + i], plan.events[2 + i]);
+        const int t = static_cast<int>(op.type);
+        prof_.ms[t] += ms;
+        prof_.flops[t] += op.flops;
+        prof_.bytes[t] += op.bytes;
+        prof_.launches[t] += 1;
+    }
+    cudaEventElapsedTime(&ms, plan.events[0], plan.events[n + 1]);
+    prof_.forward_ms += ms;
+    prof_.forwards += 1;
+    plan.events_pending = false;
+}
+
+int UNet::read_profile(OpProfile* out, bool reset) {
+    for (auto& kv : plans_) harvest(*kv.second);
+    if (out) *out = prof_;
+    if (reset) memset(&prof_, 0, sizeof(prof_));
     return 0;
 }
 

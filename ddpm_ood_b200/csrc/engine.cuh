@@ -83,12 +83,28 @@ struct Op {
     float scale;
     // UPSAMPLE
     int D, H, W;
+    // profiling: algorithmic FLOPs (2 per MAC, real rows only) for GEMM-type ops, algorithmic bytes otherwise
+    double flops;
+    double bytes;
+};
+
+constexpr int kNumOpTypes = 9;  // Op::Type values + 8 = timestep embedding (2 launches)
+struct OpProfile {
+    double ms[kNumOpTypes];
+    double flops[kNumOpTypes];
+    double bytes[kNumOpTypes];
+    long long launches[kNumOpTypes];
+    long long forwards;  // profiled forwards
+    double forward_ms;   // device time of the profiled forwards (first op start -> last op end)
 };
 
 struct Plan {
+    ~Plan() { for (auto& e : events) cudaEventDestroy(e); }
     int N, D, H, W;
     void* ws;
     std::vector<Op> ops;
+    std::vector<cudaEvent_t> events;  // ops.size() + 2 (time-embed start, each op start, end), created on the first profiled forward
+    bool events_pending = false;
     float* temb_act;  // [N][4E]
     float* temb_all;  // [N][P]
     __half* z_out;    // input of conv_out (small path)
@@ -113,6 +129,10 @@ class UNet {
     const UNetConfig& config() const { return cfg_; }
     int num_params_expected() const { return static_cast<int>(slots_.size()); }
     long long launches() const { return launches_; }
+    // Profile every `every`-th forward with CUDA events around each op (0 = off). Harvesting synchronises the host
+    // with the profiled forward's last event, so keep `every` large inside timed regions.
+    void set_profile(int every) { profile_every_ = every; profile_tick_ = 0; }
+    int read_profile(OpProfile* out, bool reset);
     double flops_per_image(int D, int H, int W) const;
 
    private:
@@ -150,6 +170,10 @@ class UNet {
     bool finalized_ = false;
     mutable std::map<std::tuple<int, int, int, int, void*>, std::unique_ptr<Plan>> plans_;
     long long launches_ = 0;
+    int profile_every_ = 0;
+    long long profile_tick_ = 0;
+    OpProfile prof_{};
+    void harvest(Plan& plan);
 };
 
 }  // namespace ddpm

@@ -303,5 +303,20 @@ class DiffusionModelUNet(nn.Module):
                                                torch.cuda.current_stream().cuda_stream),
                 "ddpm_unet_run_chain")
 
+    def set_profile(self, every: int) -> None:
+        """Time every `every`-th forward per op type with CUDA events (0 = off); see read_profile()."""
+        self.sync_weights()
+        _lib.check(_lib.lib().ddpm_unet_set_profile(self._handle, int(every)), "ddpm_unet_set_profile")
+
+    def read_profile(self, reset: bool = True) -> Dict[str, Dict[str, float]]:
+        p = _lib.OpProfile()
+        _lib.check(_lib.lib().ddpm_unet_read_profile(self._handle, C.byref(p), int(reset)), "ddpm_unet_read_profile")
+        out: Dict[str, Dict[str, float]] = {"_total": {"forwards": int(p.forwards), "ms": float(p.forward_ms)}}
+        for i, name in enumerate(_lib.OP_TYPE_NAMES):
+            if p.launches[i]:
+                out[name] = {"ms": float(p.ms[i]), "flops": float(p.flops[i]), "bytes": float(p.bytes[i]),
+                             "launches": int(p.launches[i])}
+        return out
+
     def launch_count(self) -> int:
         return int(_lib.lib().ddpm_unet_launch_count(self._handle)) if self._handle is not None else 0

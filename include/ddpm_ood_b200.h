@@ -97,6 +97,23 @@ DDPM_API int ddpm_unet_forward(void* handle, const float* x, const long long* ti
 /* Number of kernels launched by this handle so far (bench.py's gpu_launches). */
 DDPM_API long long ddpm_unet_launch_count(void* handle);
 
+/* Per-op-type device timing (CUDA events on the launch stream) of every `every`-th forward; 0 switches it off.
+ * Types: 0 conv_in(small) 1 conv_in(gemm) 2 groupnorm 3 conv/linear gemm 4 attention core 5 upsample 6 conv_out(small,
+ * + fused PLMS) 7 conv_out(gemm) 8 timestep embedding. flops/bytes are the ALGORITHMIC work of the profiled launches.
+ * This is measurement support for bench.py's roofline (no reference counterpart; the reference prints wall seconds per
+ * batch, src/trainers/reconstruct.py:232-236). */
+#define DDPM_NUM_OP_TYPES 9
+typedef struct ddpm_op_profile {
+    double ms[DDPM_NUM_OP_TYPES];
+    double flops[DDPM_NUM_OP_TYPES];
+    double bytes[DDPM_NUM_OP_TYPES];
+    long long launches[DDPM_NUM_OP_TYPES];
+    long long forwards;
+    double forward_ms;
+} ddpm_op_profile;
+DDPM_API int ddpm_unet_set_profile(void* handle, int every);
+DDPM_API int ddpm_unet_read_profile(void* handle, ddpm_op_profile* out, int reset);
+
 /* ------------------------------------------------------------------------------------------------ scheduler
  * Replaces `PNDMScheduler.add_noise` (src/trainers/reconstruct.py:143-147) and `PNDMScheduler.step`
  * (src/trainers/reconstruct.py:155-157). Scheduler STATE (counter, eps history bookkeeping, alphas_cumprod which the

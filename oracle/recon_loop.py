@@ -45,6 +45,7 @@ def reconstruct_batch(
     noise_fn: Callable[[int, int], torch.Tensor],
     cfg: LoopConfig,
     keep_recons: bool = False,
+    t_starts: Optional[List[int]] = None,
 ) -> Dict[str, object]:
     """One batch of trainers/reconstruct.py:97-204 (PassthroughVQVAE, no latent pad).
 
@@ -54,6 +55,8 @@ def reconstruct_batch(
     sched = make_scheduler(cfg)
     timesteps = sched.timesteps
     starts = t_start_grid(timesteps, cfg.inference_skip_factor)
+    if t_starts is not None:  # bounded samples of the grid (bench.py's CPU arm); every entry must be a grid value
+        starts = torch.tensor([int(t) for t in t_starts], dtype=torch.long)
     images = images_original  # PassthroughVQVAE.encode_stage_2_inputs
     B = images.shape[0]
     out_t: List[int] = []
