@@ -221,11 +221,23 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
             } else {
                 const int col_base = n_tile * BN;
                 const float* cadd = p.chan_add ? p.chan_add + static_cast<size_t>(valid ? n : 0) * p.chan_add_stride : nullptr;
+                // GroupNorm partial statistics: all 32 rows of this warp lie in one image (host guarantees it)
+                float* st_base = nullptr;
+                if (p.stats_out) {
+                    const int R = p.bw * p.bh * p.bd;  // pixels of one image inside the tile box (multiple of 32)
+                    const int n_w = tn * p.bn + (q * 32) / R;
+                    if (n_w < p.N) {
+                        const int tile_sp = (td * p.tiles_h + th) * p.tiles_w + tw;
+                        const int part = tile_sp * (R >> 5) + ((q * 32) % R) / 32;
+                        st_base = p.stats_out + (static_cast<size_t>(n_w) * p.stats_parts + part) * (p.Cout >> 1);
+                    }
+                }
                 for (int c = 0; c < BN / 32; ++c) {
                     uint32_t v[32];
                     ptx::tmem_ld_32x32(t_addr + c * 32, v);
                     ptx::tmem_ld_wait();
                     const int col0 = col_base + c * 32;
+                    uint32_t packed[16];
                     if (valid) {
                         float f[32];
 #pragma unroll
@@ -271,7 +283,6 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
 #pragma unroll
                             for (int j = 0; j < 32; ++j) dv[static_cast<size_t>(j) * 128] = __float2half_rn(f[j]);
                         } else {
-                            uint32_t packed[16];
 #pragma unroll
                             for (int j = 0; j < 32; j += 2) {
                                 __half2 hh = __floats2half2_rn(f[j], f[j + 1]);
@@ -281,6 +292,37 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
                                 d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) packed[j] = 0u;
+                    }
+                    if (p.stats_out) {
+                        // per-lane quad sums of the ROUNDED values (what GroupNorm will read back), then a
+                        // transpose-reduce over the warp's 32 pixels: 16 shuffles instead of 80.
+                        float sv[16];
+#pragma unroll
+                        for (int qd = 0; qd < 8; ++qd) {
+                            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&packed[2 * qd]));
+                            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&packed[2 * qd + 1]));
+                            sv[qd] = (a.x + a.y) + (b.x + b.y);
+                            sv[8 + qd] = (a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y);
+                        }
+#pragma unroll
+                        for (int half_n = 8, off = 16; half_n >= 1; half_n >>= 1, off >>= 1) {
+                            const bool hi = (lane & off) != 0;
+#pragma unroll
+                            for (int i = 0; i < half_n; ++i) {
+                                const float send = hi ? sv[i] : sv[i + half_n];
+                                const float keep = hi ? sv[i + half_n] : sv[i];
+                                sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                            }
+                        }
+                        sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
+                        // lane bits: b4 -> sum / sum of squares, b3 b2 b1 -> quad, b0 -> duplicate
+                        if (st_base && (lane & 1) == 0) {
+                            const int quad = (col0 >> 2) + ((lane >> 1) & 7);
+                            st_base[quad * 2 + (lane >> 4)] = sv[0];
                         }
                     }
                 }
@@ -326,6 +368,28 @@ static int pow2ceil(int v) {
     return p;
 }
 
+static void tile_box(int W, int H, int D, int* bw, int* bh, int* bd, int* bn);
+
+int conv_stats_parts(int spatial_dims, int Dout, int Hout, int Wout) {
+    (void)spatial_dims;
+    int bw, bh, bd, bn;
+    tile_box(Wout, Hout, Dout, &bw, &bh, &bd, &bn);
+    const int R = bw * bh * bd;
+    if (R < 32) return 0;
+    return ((Wout + bw - 1) / bw) * ((Hout + bh - 1) / bh) * ((Dout + bd - 1) / bd) * (R / 32);
+}
+
+// tile box: fill W first, then H, D, N; product is always 128 output pixels.
+static void tile_box(int W, int H, int D, int* bw, int* bh, int* bd, int* bn) {
+    *bw = pow2ceil(W) < kBlockM ? pow2ceil(W) : kBlockM;
+    int rem = kBlockM / *bw;
+    *bh = pow2ceil(H) < rem ? pow2ceil(H) : rem;
+    rem /= *bh;
+    *bd = pow2ceil(D) < rem ? pow2ceil(D) : rem;
+    rem /= *bd;
+    *bn = rem;
+}
+
 int conv_prepare(const ConvProblem& q, int num_sms, ConvLaunch* out) {
     PFN_encodeTiled encode = get_encode();
     if (!encode) return 1;
@@ -342,14 +406,7 @@ int conv_prepare(const ConvProblem& q, int num_sms, ConvLaunch* out) {
     p.H = (q.H + sH - 1) / sH;
     p.D = (q.D + sD - 1) / sD;
     p.stride = q.stride;
-    // tile box: fill W first, then H, D, N; product is always 128 output pixels.
-    p.bw = pow2ceil(p.W) < kBlockM ? pow2ceil(p.W) : kBlockM;
-    int rem = kBlockM / p.bw;
-    p.bh = pow2ceil(p.H) < rem ? pow2ceil(p.H) : rem;
-    rem /= p.bh;
-    p.bd = pow2ceil(p.D) < rem ? pow2ceil(p.D) : rem;
-    rem /= p.bd;
-    p.bn = rem;
+    tile_box(p.W, p.H, p.D, &p.bw, &p.bh, &p.bd, &p.bn);
     p.tiles_w = (p.W + p.bw - 1) / p.bw;
     p.tiles_h = (p.H + p.bh - 1) / p.bh;
     p.tiles_d = (p.D + p.bd - 1) / p.bd;
@@ -371,6 +428,14 @@ int conv_prepare(const ConvProblem& q, int num_sms, ConvLaunch* out) {
     p.group = q.group;
     p.vt_col0 = q.vt_col0;
     p.out_vt = static_cast<__half*>(q.out_vt);
+    p.stats_out = nullptr;
+    p.stats_parts = 0;
+    if (q.stats_out) {
+        const int R = p.bw * p.bh * p.bd;
+        if (q.mode != EPI_STORE || R < 32) { set_error("conv: fused GroupNorm statistics unsupported for this shape/mode"); return 2; }
+        p.stats_out = q.stats_out;
+        p.stats_parts = p.tiles_w * p.tiles_h * p.tiles_d * (R / 32);
+    }
     if (q.mode == EPI_SOFTMAX_BD && p.num_n_tiles != 1) { set_error("conv: softmax epilogue needs one N tile"); return 2; }
 
     p.n_seg = q.n_seg;

@@ -56,6 +56,11 @@ struct ConvGemmParams {
     int group;                // EPI_SOFTMAX_BD: tokens per image (block size)
     int vt_col0;              // EPI_STORE_VT: first transposed column
     __half* out_vt;           // EPI_STORE_VT: destination of the transposed columns
+    // EPI_STORE: optional GroupNorm partial statistics of the (fp16-rounded) output, one (sum, sum of squares) pair per
+    // (image, part, 4-channel quad); a part is the 32 output pixels one epilogue warp owns. Layout
+    // [N][stats_parts][Cout/4][2] fp32. Summed in a fixed order: bitwise reproducible.
+    float* stats_out;
+    int stats_parts;
 };
 
 // Host side: filled by conv_prepare(), launched by conv_launch().
@@ -91,7 +96,12 @@ struct ConvProblem {
     int group;
     int vt_col0;
     void* out_vt;
+    float* stats_out;  // or null; must hold N * conv_stats_parts(...) * Cout/4 * 2 floats
 };
+
+// Number of GroupNorm-statistics parts per image the epilogue emits for an OUTPUT of this geometry (0: the tile box
+// holds fewer than 32 pixels of an image, fused statistics unsupported).
+int conv_stats_parts(int spatial_dims, int Dout, int Hout, int Wout);
 
 // returns 0 on success; on failure sets the thread-local error string (see ddpm_last_error()).
 int conv_prepare(const ConvProblem& prob, int num_sms, ConvLaunch* out);

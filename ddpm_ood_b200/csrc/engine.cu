@@ -2,6 +2,7 @@
 #include "engine.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace ddpm {
@@ -49,6 +50,8 @@ __global__ void nhwc_half_to_nchw_kernel(const __half* __restrict__ y, float* __
 UNet::UNet(const UNetConfig& cfg) : cfg_(cfg), E_(cfg.num_channels[0]) {}
 
 UNet::~UNet() {
+    if (temb_table_) cudaFree(temb_table_);
+    if (temb_table_act_) cudaFree(temb_table_act_);
     if (f32_arena_) cudaFree(f32_arena_);
     if (f16_arena_) cudaFree(f16_arena_);
 }
@@ -159,6 +162,10 @@ int UNet::init() {
         if (c.num_channels[i] % 128 != 0) { set_error("unet: num_channels must be multiples of 128 (tcgen05 N tiles)"); return 2; }
     }
     const int taps = c.spatial_dims == 3 ? 27 : 9;
+    fuse_gn_stats_ = c.norm_num_groups > 0;
+    for (int i = 0; i < c.num_levels && fuse_gn_stats_; ++i)
+        fuse_gn_stats_ = (c.num_channels[i] % c.norm_num_groups == 0) && ((c.num_channels[i] / c.norm_num_groups) % 4 == 0);
+    if (const char* e = getenv("DDPM_FUSE_GN")) fuse_gn_stats_ = fuse_gn_stats_ && atoi(e) != 0;  // A/B switch for tests
     in_gemm_ = (c.in_channels % 64 == 0);
     out_gemm_ = (c.out_channels % 128 == 0);
     if (!in_gemm_ && c.in_channels > 8) { set_error("unet: in_channels=%d unsupported (<=8 or multiple of 64)", c.in_channels); return 2; }
@@ -324,6 +331,17 @@ int UNet::finalize(cudaStream_t stream) {
     fold(mid1_);
     fold(mid2_);
     for (auto& L : up_) for (auto& r : L.res) fold(r);
+    // timestep-embedding table: row t = all time_emb_proj outputs for timestep t (depends on weights only)
+    if (!temb_table_) {
+        if (cudaMalloc(&temb_table_, static_cast<size_t>(temb_rows_) * P_ * sizeof(float)) != cudaSuccess ||
+            cudaMalloc(&temb_table_act_, static_cast<size_t>(temb_rows_) * 4 * E_ * sizeof(float)) != cudaSuccess) {
+            set_error("unet: cudaMalloc of the timestep-embedding table failed");
+            return 6;
+        }
+    }
+    int trc = time_embed(nullptr, 0, temb_rows_, E_, te_w0_, te_b0_, te_w1_, te_b1_, temb_table_act_, stream);
+    if (!trc) trc = time_proj_all(temb_table_act_, temb_rows_, 4 * E_, tp_w_, tp_b_, P_, temb_table_, stream);
+    if (trc) return trc;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("unet: finalize failed: %s", cudaGetErrorString(e)); return 5; }
     finalized_ = true;
@@ -361,11 +379,21 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
     const int sd = c.spatial_dims;
     const int sms = num_sms();
     Layout lay{dry ? nullptr : static_cast<uint8_t*>(ws)};
-    struct Act { __half* p; int C, D, H, W; long long S() const { return static_cast<long long>(D) * H * W; } };
-    auto new_act = [&](int C, int d, int h, int w) {
-        Act a{lay.take<__half>(static_cast<size_t>(N) * d * h * w * C), C, d, h, w};
+    // stats/parts: GroupNorm partial statistics written by the tensor's producer (null/0 when unsupported)
+    struct Act { __half* p; int C, D, H, W; float* stats; int parts; long long S() const { return static_cast<long long>(D) * H * W; } };
+    auto take_stats = [&](int C, int parts) -> float* {
+        return parts > 0 ? lay.take<float>(static_cast<size_t>(N) * parts * (C / 4) * 2) : nullptr;
+    };
+    auto new_act = [&](int C, int d, int h, int w, bool want_stats = true) {
+        Act a{lay.take<__half>(static_cast<size_t>(N) * d * h * w * C), C, d, h, w, nullptr, 0};
+        if (want_stats && fuse_gn_stats_) {
+            a.parts = conv_stats_parts(sd, d, h, w);
+            a.stats = take_stats(C, a.parts);
+            if (!a.stats) a.parts = 0;
+        }
         return a;
     };
+    auto shape_act = [&](int C, int d, int h, int w) { return Act{nullptr, C, d, h, w, nullptr, 0}; };
     // scratch sized by a first dry walk: compute maxima analytically while walking (allocate lazily at the end is not
     // possible with a bump allocator, so walk twice: first to find the maxima, then to lay out).
     size_t max_z = 0, max_h = 0, max_qkv = 0, max_up = 0;
@@ -390,24 +418,31 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             if (measure) { if (cnt > max_z) max_z = cnt; return; }
             Op op{};
             op.type = Op::GN;
+            if (a.stats && (!b || b->stats)) {
+                op.st0 = a.stats; op.parts0 = a.parts;
+                op.st1 = b ? b->stats : nullptr; op.parts1 = b ? b->parts : 0;
+            }
             op.src0 = a.p; op.C0 = a.C;
             op.src1 = b ? b->p : nullptr; op.C1 = b ? b->C : 0;
             op.gamma = g; op.beta = bt; op.dst = dst; op.S = static_cast<int>(a.S()); op.silu = silu;
             op.bytes = 4.0 * static_cast<double>(cnt);  // one fp16 read + one fp16 write per element
             plan.ops.push_back(op);
         };
-        auto gemm = [&](ConvProblem q, bool uses_temb) {
+        auto gemm = [&](ConvProblem q, int temb_off) {
+            const bool uses_temb = temb_off >= 0;
             if (measure || dry) { if (!measure) { Op op{}; op.type = Op::GEMM; op.uses_temb = uses_temb; plan.ops.push_back(op); } return; }
             Op op{};
             op.type = Op::GEMM;
             op.uses_temb = uses_temb;
+            op.temb_off = temb_off;
             op.flops = conv_flops(q);
             int r = conv_prepare(q, sms, &op.conv);
             if (r && !rc) rc = r;
             plan.ops.push_back(op);
         };
         auto conv3 = [&](const Act& in, __half* zin, int cin, const __half* w, const float* bias, int cout, int stride,
-                         int temb_off, const __half* residual, __half* out, const Act* raw0, const Act* raw1) {
+                         int temb_off, const __half* residual, __half* out, const Act* raw0, const Act* raw1,
+                         float* stats_out) {
             const float* cadd = (temb_off >= 0 && plan.temb_all) ? plan.temb_all + temb_off : nullptr;
             ConvProblem q{};
             q.spatial_dims = sd;
@@ -421,7 +456,24 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             q.mode = EPI_STORE;
             q.bias = bias; q.chan_add = cadd; q.chan_add_stride = P_;
             q.residual = residual; q.out = out;
-            gemm(q, temb_off >= 0);
+            q.stats_out = stats_out;
+            gemm(q, temb_off);
+        };
+        // 1x1 conv over the real image geometry (same GEMM as `linear`, but tiles are image-structured so the epilogue
+        // can emit per-image GroupNorm statistics)
+        auto conv1x1 = [&](const Act& in, const __half* src, const __half* w, const float* bias, int cout,
+                           const __half* residual, const Act& out) {
+            ConvProblem q{};
+            q.spatial_dims = sd;
+            q.N = N; q.D = in.D; q.H = in.H; q.W = in.W;
+            q.stride = 1;
+            q.n_seg = 1;
+            q.seg[0] = {src, in.C, 1};
+            q.weights = w; q.w_rows = cout; q.Cout = cout;
+            q.mode = EPI_STORE;
+            q.bias = bias; q.residual = residual; q.out = out.p;
+            q.stats_out = out.stats;
+            gemm(q, -1);
         };
         auto linear = [&](const __half* in, long long rows, int cin, const __half* w, const float* bias, int cout,
                           const __half* residual, __half* out) {
@@ -434,7 +486,7 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             q.weights = w; q.w_rows = cout; q.Cout = cout;
             q.mode = EPI_STORE;
             q.bias = bias; q.residual = residual; q.out = out;
-            gemm(q, false);
+            gemm(q, -1);
         };
         auto resblock = [&](const ResW& r, const Act& h, const Act* skip) -> Act {
             const int cin = r.c0 + r.c1;
@@ -443,14 +495,19 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
                 if (ch > max_h) max_h = ch;
             }
             gn(h, skip, r.g1, r.b1, zA, true);
-            Act h1{hB, r.cout, h.D, h.H, h.W};
-            conv3(h, zA, cin, r.w1, r.bias1, r.cout, 1, r.temb_off, nullptr, hB, nullptr, nullptr);
+            Act h1{hB, r.cout, h.D, h.H, h.W, nullptr, 0};
+            if (!measure && fuse_gn_stats_) {
+                h1.parts = conv_stats_parts(sd, h.D, h.H, h.W);
+                h1.stats = take_stats(r.cout, h1.parts);
+                if (!h1.stats) h1.parts = 0;
+            }
+            conv3(h, zA, cin, r.w1, r.bias1, r.cout, 1, r.temb_off, nullptr, hB, nullptr, nullptr, h1.stats);
             gn(h1, nullptr, r.g2, r.b2, zB, true);
-            Act out = measure ? Act{nullptr, r.cout, h.D, h.H, h.W} : new_act(r.cout, h.D, h.H, h.W);
+            Act out = measure ? shape_act(r.cout, h.D, h.H, h.W) : new_act(r.cout, h.D, h.H, h.W);
             if (r.skip_conv)
-                conv3(h, zB, r.cout, r.w2, r.bias2_total, r.cout, 1, -1, nullptr, out.p, &h, skip);
+                conv3(h, zB, r.cout, r.w2, r.bias2_total, r.cout, 1, -1, nullptr, out.p, &h, skip, out.stats);
             else
-                conv3(h, zB, r.cout, r.w2, r.bias2_total, r.cout, 1, -1, h.p, out.p, nullptr, nullptr);
+                conv3(h, zB, r.cout, r.w2, r.bias2_total, r.cout, 1, -1, h.p, out.p, nullptr, nullptr, out.stats);
             return out;
         };
         auto attnblock = [&](const AttnW& a, const Act& h) -> Act {
@@ -471,17 +528,22 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
                 op.flops = 4.0 * N * static_cast<double>(h.S()) * static_cast<double>(h.S()) * a.C;
                 plan.ops.push_back(op);
             }
-            Act out = measure ? Act{nullptr, a.C, h.D, h.H, h.W} : new_act(a.C, h.D, h.H, h.W);
-            linear(hB, rows, a.C, a.wproj, a.bproj, a.C, h.p, out.p);
+            Act out = measure ? shape_act(a.C, h.D, h.H, h.W) : new_act(a.C, h.D, h.H, h.W);
+            conv1x1(h, hB, a.wproj, a.bproj, a.C, h.p, out);
             return out;
         };
 
         // ---- walk
-        Act h = measure ? Act{nullptr, c.num_channels[0], D, H, W} : new_act(c.num_channels[0], D, H, W);
+        Act h = measure ? shape_act(c.num_channels[0], D, H, W) : new_act(c.num_channels[0], D, H, W, in_gemm_);
+        if (!measure && !in_gemm_ && fuse_gn_stats_ && conv_in_has_stats(c.in_channels, c.num_channels[0], sd)) {
+            h.parts = conv_in_stats_parts(D, H, W);
+            h.stats = take_stats(c.num_channels[0], h.parts);
+        }
         if (!measure) {
             Op op{};
             op.type = in_gemm_ ? Op::CONV_IN_GEMM : Op::CONV_IN_SMALL;
             op.dst = h.p; op.D = D; op.H = H; op.W = W;
+            op.st0 = h.stats;
             op.flops = 2.0 * N * D * H * W * c.num_channels[0] * (sd == 3 ? 27.0 : 9.0) * c.in_channels;
             op.bytes = static_cast<double>(N) * D * H * W * (4.0 * c.in_channels + 2.0 * c.num_channels[0]);
             if (in_gemm_ && !dry) {
@@ -490,6 +552,7 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
                 q.seg[0] = {plan.x_half, c.in_channels, 3};
                 q.weights = conv_in_wp_; q.w_rows = c.num_channels[0]; q.Cout = c.num_channels[0];
                 q.mode = EPI_STORE; q.bias = conv_in_b_; q.out = h.p;
+                q.stats_out = h.stats;
                 int r = conv_prepare(q, sms, &op.conv);
                 if (r && !rc) rc = r;
             }
@@ -506,8 +569,8 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             }
             if (L.has_samp) {
                 const int d2 = sd == 3 ? (h.D + 1) / 2 : h.D, h2 = (h.H + 1) / 2, w2 = (h.W + 1) / 2;
-                Act o = measure ? Act{nullptr, h.C, d2, h2, w2} : new_act(h.C, d2, h2, w2);
-                conv3(h, h.p, h.C, L.samp.w, L.samp.bias, h.C, 2, -1, nullptr, o.p, nullptr, nullptr);
+                Act o = measure ? shape_act(h.C, d2, h2, w2) : new_act(h.C, d2, h2, w2);
+                conv3(h, h.p, h.C, L.samp.w, L.samp.bias, h.C, 2, -1, nullptr, o.p, nullptr, nullptr, o.stats);
                 h = o;
                 skips.push_back(h);
             }
@@ -531,7 +594,7 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
                 const int fd = sd == 3 ? 2 : 1;
                 const size_t cnt = static_cast<size_t>(N) * (h.D * fd) * (h.H * 2) * (h.W * 2) * h.C;
                 if (measure && cnt > max_up) max_up = cnt;
-                Act up = measure ? Act{nullptr, h.C, h.D * fd, h.H * 2, h.W * 2} : new_act(h.C, h.D * fd, h.H * 2, h.W * 2);
+                Act up = measure ? shape_act(h.C, h.D * fd, h.H * 2, h.W * 2) : new_act(h.C, h.D * fd, h.H * 2, h.W * 2, false);
                 if (!measure) {
                     Op op{};
                     op.type = Op::UPSAMPLE;
@@ -540,7 +603,7 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
                     plan.ops.push_back(op);
                 }
                 Act o = measure ? up : new_act(h.C, up.D, up.H, up.W);
-                conv3(up, up.p, h.C, L.samp.w, L.samp.bias, h.C, 1, -1, nullptr, o.p, nullptr, nullptr);
+                conv3(up, up.p, h.C, L.samp.w, L.samp.bias, h.C, 1, -1, nullptr, o.p, nullptr, nullptr, o.stats);
                 h = o;
             }
         }
@@ -612,11 +675,23 @@ int UNet::forward(const float* x, const long long* timesteps, int t_uniform, flo
         cudaEventRecord(plan.events[0], stream);
     }
     size_t op_idx = 0;
-    int rc = time_embed(timesteps, t_uniform, R, E_, te_w0_, te_b0_, te_w1_, te_b1_, plan.temb_act, stream);
-    if (rc) return rc;
-    rc = time_proj_all(plan.temb_act, R, 4 * E_, tp_w_, tp_b_, P_, plan.temb_all, stream);
-    if (rc) return rc;
-    launches_ += 2;
+    // Timestep embedding -> all ResnetBlock projections. With one timestep for the whole batch (the reconstruction
+    // chain) the row comes from a table computed once per weight upload; per-sample timesteps run the MLP here.
+    int rc = 0;
+    const float* temb_base;
+    long long temb_stride;
+    if (!timesteps && temb_table_ && t_uniform >= 0 && t_uniform < temb_rows_) {
+        temb_base = temb_table_ + static_cast<size_t>(t_uniform) * P_;
+        temb_stride = 0;
+    } else {
+        rc = time_embed(timesteps, t_uniform, R, E_, te_w0_, te_b0_, te_w1_, te_b1_, plan.temb_act, stream);
+        if (rc) return rc;
+        rc = time_proj_all(plan.temb_act, R, 4 * E_, tp_w_, tp_b_, P_, plan.temb_all, stream);
+        if (rc) return rc;
+        launches_ += 2;
+        temb_base = plan.temb_all;
+        temb_stride = timesteps ? P_ : 0;
+    }
     const long long S = static_cast<long long>(D) * H * W;
     for (Op& op : plan.ops) {
         if (prof) cudaEventRecord(plan.events[1 + op_idx], stream);
@@ -624,7 +699,7 @@ int UNet::forward(const float* x, const long long* timesteps, int t_uniform, flo
         switch (op.type) {
             case Op::CONV_IN_SMALL:
                 rc = conv_in_small(x, conv_in_w_, conv_in_b_, op.dst, N, c.in_channels, D, H, W, c.num_channels[0],
-                                   c.spatial_dims, stream);
+                                   c.spatial_dims, const_cast<float*>(op.st0), stream);
                 break;
             case Op::CONV_IN_GEMM:
                 rc = nchw_to_nhwc_half(x, plan.x_half, N, c.in_channels, S, stream);
@@ -632,11 +707,18 @@ int UNet::forward(const float* x, const long long* timesteps, int t_uniform, flo
                 ++launches_;
                 break;
             case Op::GN:
-                rc = gn_silu(op.src0, op.C0, op.src1, op.C1, op.gamma, op.beta, op.dst, N, op.S, c.norm_num_groups,
-                             c.norm_eps, op.silu, stream);
+                if (op.st0)
+                    rc = gn_apply(op.src0, op.C0, op.st0, op.parts0, op.src1, op.C1, op.st1, op.parts1, op.gamma, op.beta,
+                                  op.dst, N, op.S, c.norm_num_groups, c.norm_eps, op.silu, stream);
+                else
+                    rc = gn_silu(op.src0, op.C0, op.src1, op.C1, op.gamma, op.beta, op.dst, N, op.S, c.norm_num_groups,
+                                 c.norm_eps, op.silu, stream);
                 break;
             case Op::GEMM:
-                if (op.uses_temb) op.conv.p.chan_add_stride = timesteps ? P_ : 0;
+                if (op.uses_temb) {
+                    op.conv.p.chan_add = temb_base + op.temb_off;
+                    op.conv.p.chan_add_stride = temb_stride;
+                }
                 rc = conv_launch(op.conv, stream);
                 break;
             case Op::ATTN:

@@ -72,12 +72,15 @@ struct Op {
     const __half *src0, *src1;
     int C0, C1;
     const float *gamma, *beta;
+    const float *st0, *st1;  // producer-side GroupNorm partial statistics (null: two-pass gn_silu)
+    int parts0, parts1;
     __half* dst;
     int S;
     bool silu;
     // GEMM
     ConvLaunch conv;
     bool uses_temb;
+    int temb_off;
     // ATTN
     int T, C, heads;
     float scale;
@@ -153,6 +156,8 @@ class UNet {
     __half* conv_in_wp_ = nullptr;                        // gemm path
     float *te_w0_, *te_b0_, *te_w1_, *te_b1_;
     float *tp_w_, *tp_b_;
+    float *temb_table_ = nullptr, *temb_table_act_ = nullptr;  // [temb_rows_][P_], [temb_rows_][4E]
+    int temb_rows_ = 1000;                                      // num_train_timesteps of every reference scheduler
     struct Level { std::vector<ResW> res; std::vector<AttnW> attn; bool has_samp; SampW samp; };
     std::vector<Level> down_, up_;
     ResW mid1_, mid2_;
@@ -161,6 +166,7 @@ class UNet {
     float *conv_out_w_ = nullptr, *conv_out_b_ = nullptr;
     __half* conv_out_wp_ = nullptr;
     bool in_gemm_, out_gemm_;
+    bool fuse_gn_stats_ = true;  // GroupNorm statistics from the producers' epilogues (cpg % 4 == 0 required)
     // arenas
     size_t f32_count_ = 0, f16_count_ = 0, f32_used_ = 0, f16_used_ = 0;
     float* f32_arena_ = nullptr;

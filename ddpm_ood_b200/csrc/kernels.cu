@@ -137,6 +137,94 @@ int gn_silu(const __half* src0, int C0, const __half* src1, int C1, const float*
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ GroupNorm apply
+// Second half of the fused GroupNorm: the producers of src0/src1 (conv epilogues, conv_in) have left per-(image, part,
+// 4-channel quad) partial sums; every CTA reduces the partials of its image in a fixed order (bitwise reproducible),
+// derives per-channel scale/shift and streams its pixel chunk once: one fp16 read + one fp16 write per element.
+constexpr int kGnApplyMaxC = 2048;
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ src0, int C0,
+                                                       const float* __restrict__ st0, int parts0,
+                                                       const __half* __restrict__ src1, int C1,
+                                                       const float* __restrict__ st1, int parts1,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       __half* __restrict__ out, int S, int cpg, float eps, int do_silu,
+                                                       int chunk) {
+    __shared__ float s_qs[kGnApplyMaxC / 4], s_qq[kGnApplyMaxC / 4];
+    __shared__ float s_a[kGnApplyMaxC], s_b[kGnApplyMaxC];
+    const int C = C0 + C1;
+    const int Q = C >> 2, Q0 = C0 >> 2, Q1 = C1 >> 2;
+    const int n = blockIdx.y;
+    const int tid = threadIdx.x;
+    for (int qd = tid; qd < Q; qd += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        if (qd < Q0) {
+            const float2* p = reinterpret_cast<const float2*>(st0) + static_cast<size_t>(n) * parts0 * Q0 + qd;
+            for (int i = 0; i < parts0; ++i) { const float2 v = __ldg(p + static_cast<size_t>(i) * Q0); a += v.x; b += v.y; }
+        } else {
+            const float2* p = reinterpret_cast<const float2*>(st1) + static_cast<size_t>(n) * parts1 * Q1 + (qd - Q0);
+            for (int i = 0; i < parts1; ++i) { const float2 v = __ldg(p + static_cast<size_t>(i) * Q1); a += v.x; b += v.y; }
+        }
+        s_qs[qd] = a;
+        s_qq[qd] = b;
+    }
+    __syncthreads();
+    const float inv_n = 1.0f / (static_cast<float>(cpg) * static_cast<float>(S));
+    for (int c = tid; c < C; c += blockDim.x) {
+        const int q0 = (c / cpg) * (cpg >> 2);
+        float sum = 0.f, sq = 0.f;
+        for (int i = 0; i < (cpg >> 2); ++i) { sum += s_qs[q0 + i]; sq += s_qq[q0 + i]; }
+        const float mean = sum * inv_n;
+        float var = sq * inv_n - mean * mean;
+        var = var < 0.f ? 0.f : var;
+        const float rstd = rsqrtf(var + eps);
+        const float a = gamma[c] * rstd;
+        s_a[c] = a;
+        s_b[c] = beta[c] - mean * a;
+    }
+    __syncthreads();
+    const int V = C >> 3;  // uint4 vectors per pixel
+    const int p_begin = blockIdx.x * chunk;
+    const int p_end = min(S, p_begin + chunk);
+    const int total = (p_end - p_begin) * V;
+    const __half* b0 = src0 + static_cast<size_t>(n) * S * C0;
+    const __half* b1 = src1 ? src1 + static_cast<size_t>(n) * S * C1 : nullptr;
+    __half* ob = out + static_cast<size_t>(n) * S * C;
+    for (int i = tid; i < total; i += blockDim.x) {
+        const int pp = p_begin + i / V;
+        const int c = (i % V) * 8;
+        const uint4 raw = (c < C0) ? __ldg(reinterpret_cast<const uint4*>(b0 + static_cast<size_t>(pp) * C0 + c))
+                                   : __ldg(reinterpret_cast<const uint4*>(b1 + static_cast<size_t>(pp) * C1 + (c - C0)));
+        float f[8];
+        unpack8(raw, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float y = f[e] * s_a[c + e] + s_b[c + e];
+            f[e] = do_silu ? silu(y) : y;
+        }
+        *reinterpret_cast<uint4*>(ob + static_cast<size_t>(pp) * C + c) = pack8(f);
+    }
+}
+
+int gn_apply(const __half* src0, int C0, const float* st0, int parts0, const __half* src1, int C1, const float* st1,
+             int parts1, const float* gamma, const float* beta, __half* out, int N, int S, int groups, float eps,
+             bool do_silu, cudaStream_t stream) {
+    const int C = C0 + C1;
+    if (C % groups != 0 || (C / groups) % 4 != 0 || C0 % 8 != 0 || C1 % 8 != 0 || C > kGnApplyMaxC) {
+        set_error("gn_apply: C=%d+%d groups=%d unsupported", C0, C1, groups);
+        return 2;
+    }
+    // ~2 waves of CTAs: chunk of pixels per CTA, at least 32
+    int chunk = S;
+    while (chunk > 32 && static_cast<long long>(N) * ((S + chunk - 1) / chunk) < 2 * 148 && chunk % 2 == 0) chunk >>= 1;
+    while (chunk > 256) chunk = (chunk + 1) >> 1;
+    dim3 grid((S + chunk - 1) / chunk, N);
+    gn_apply_kernel<<<grid, 256, 0, stream>>>(src0, C0, st0, parts0, src1, C1, st1, parts1, gamma, beta, out, S,
+                                              C / groups, eps, do_silu ? 1 : 0, chunk);
+    DDPM_CHECK_LAUNCH("gn_apply");
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ time embedding
 // One CTA per row: sinusoid(E) -> Linear(E,4E)+SiLU -> Linear(4E,4E) -> SiLU. Warp-per-output dot products.
 __global__ void __launch_bounds__(256) time_embed_kernel(const long long* __restrict__ timesteps, int t_uniform, int E,
@@ -148,7 +236,7 @@ __global__ void __launch_bounds__(256) time_embed_kernel(const long long* __rest
     float* s_hid = sm + E;       // [4E]
     const int r = blockIdx.x;
     const int H4 = 4 * E;
-    const float t = timesteps ? static_cast<float>(timesteps[r]) : static_cast<float>(t_uniform);
+    const float t = timesteps ? static_cast<float>(timesteps[r]) : static_cast<float>(t_uniform + r);
     const int half = E / 2;
     for (int i = threadIdx.x; i < half; i += blockDim.x) {
         const float exponent = -logf(10000.0f) * static_cast<float>(i);
@@ -414,9 +502,137 @@ __global__ void __launch_bounds__(256) conv_in_small_kernel(const float* __restr
     }
 }
 
-int conv_in_small(const float* x, const float* w, const float* b, __half* out, int N, int Cin, int D, int H, int W,
-                  int Cout, int spatial_dims, cudaStream_t stream) {
+constexpr int kConvInPart = 256;  // pixels per statistics part
+int conv_in_stats_parts(int D, int H, int W) {
+    const long long S = static_cast<long long>(D) * H * W;
+    return static_cast<int>((S + kConvInPart - 1) / kConvInPart);
+}
+bool conv_in_has_stats(int Cin, int Cout, int spatial_dims) {
     const int kd = spatial_dims == 3 ? 3 : 1;
+    if (kd == 1 && Cin == 1) return Cout % 8 == 0 && Cout <= 2048 && 256 % (Cout / 8) == 0;
+    if (kd == 1 && Cin == 3) return Cout % 4 == 0 && Cout <= 1024 && 256 % (Cout / 4) == 0;
+    if (kd == 3 && Cin == 1) return Cout % 4 == 0 && Cout <= 1024 && 256 % (Cout / 4) == 0;
+    return false;
+}
+
+// Register-weight variant for the image-side shapes that matter (Cin in {1,3}, 2-D; Cin = 1, 3-D): a thread owns CPT
+// output channels for good (its TAPS*CIN*CPT weights live in registers) and walks pixels; the 128/CPT threads of a
+// pixel read the same x values (L1 broadcast) and write one contiguous fp16 row. Bound by the fp16 output write.
+template <int CIN, int KD, int CPT>
+__global__ void __launch_bounds__(256) conv_in_reg_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ b, __half* __restrict__ out,
+                                                          int N, int D, int H, int W, int Cout, float* stats_out,
+                                                          int stats_parts) {
+    constexpr int TAPS = KD * 9;
+    const int G = Cout / CPT;             // threads per pixel
+    const int ppb = blockDim.x / G;       // pixels per block iteration
+    const int g = threadIdx.x % G;
+    const int pl = threadIdx.x / G;
+    float wr[TAPS * CIN][CPT];
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t)
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+            for (int j = 0; j < CPT; ++j)
+                wr[t * CIN + ci][j] = w[(static_cast<size_t>(g * CPT + j) * CIN + ci) * TAPS + t];
+    float bias[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) bias[j] = b[g * CPT + j];
+    const int HW = H * W;
+    const int S = D * HW;
+    // One block iteration = one (image, part of kConvInPart pixels): statistics partials stay image-local.
+    __shared__ float s_red[256 * (CPT / 4) * 2];
+    const int units = N * stats_parts;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        const int n = unit / stats_parts;
+        const int part = unit - n * stats_parts;
+        const int p_begin = part * kConvInPart;
+        const int p_end = min(S, p_begin + kConvInPart);
+        float qs[CPT / 4], qq[CPT / 4];
+#pragma unroll
+        for (int k = 0; k < CPT / 4; ++k) { qs[k] = 0.f; qq[k] = 0.f; }
+        const float* xn = x + static_cast<size_t>(n) * CIN * S;
+        for (int r = p_begin + pl; r < p_end && pl < ppb; r += ppb) {
+            const int dq = r / HW;
+            const int r2 = r - dq * HW;
+            const int hq = r2 / W;
+            const int wq = r2 - hq * W;
+            float acc[CPT];
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) acc[j] = bias[j];
+#pragma unroll
+            for (int t = 0; t < TAPS; ++t) {
+                const int tw = t % 3, th = (t / 3) % 3, td = t / 9;
+                const int ww = wq + tw - 1, hh = hq + th - 1, dd = dq + td - (KD == 3 ? 1 : 0);
+                const bool ok = ww >= 0 && ww < W && hh >= 0 && hh < H && dd >= 0 && dd < D;
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci) {
+                    const float xv = ok ? __ldg(xn + ci * S + dd * HW + hh * W + ww) : 0.f;
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) acc[j] = fmaf(xv, wr[t * CIN + ci][j], acc[j]);
+                }
+            }
+            __half* o = out + (static_cast<size_t>(n) * S + r) * Cout + g * CPT;
+            __half2 hv[CPT / 2];
+#pragma unroll
+            for (int j = 0; j < CPT / 2; ++j) hv[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+            if constexpr (CPT == 8) {
+                *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(hv);
+            } else {
+                static_assert(CPT == 4, "CPT must be 4 or 8");
+                *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(hv);
+            }
+#pragma unroll
+            for (int k = 0; k < CPT / 4; ++k) {
+                const float2 a = __half22float2(hv[2 * k]), c2 = __half22float2(hv[2 * k + 1]);
+                qs[k] += (a.x + a.y) + (c2.x + c2.y);
+                qq[k] += (a.x * a.x + a.y * a.y) + (c2.x * c2.x + c2.y * c2.y);
+            }
+        }
+        if (stats_out) {
+            // fixed-order reduction over the block's pixel lanes
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < CPT / 4; ++k) {
+                s_red[(threadIdx.x * (CPT / 4) + k) * 2] = qs[k];
+                s_red[(threadIdx.x * (CPT / 4) + k) * 2 + 1] = qq[k];
+            }
+            __syncthreads();
+            const int nq = G * (CPT / 4);  // quads per pixel == Cout / 4
+            if (threadIdx.x < nq * 2) {
+                const int quad = threadIdx.x >> 1, which = threadIdx.x & 1;
+                const int gg = quad / (CPT / 4), k = quad % (CPT / 4);
+                float t = 0.f;
+                for (int l = 0; l < ppb; ++l) t += s_red[(((l * G) + gg) * (CPT / 4) + k) * 2 + which];
+                stats_out[(static_cast<size_t>(n) * stats_parts + part) * (Cout >> 1) + quad * 2 + which] = t;
+            }
+        }
+    }
+}
+
+template <int CIN, int KD, int CPT>
+static int launch_conv_in_reg(const float* x, const float* w, const float* b, __half* out, int N, int D, int H, int W,
+                              int Cout, float* stats_out, cudaStream_t stream) {
+    const int parts = conv_in_stats_parts(D, H, W);
+    long long blocks = static_cast<long long>(N) * parts;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    conv_in_reg_kernel<CIN, KD, CPT><<<static_cast<int>(blocks), 256, 0, stream>>>(x, w, b, out, N, D, H, W, Cout,
+                                                                                   stats_out, parts);
+    DDPM_CHECK_LAUNCH("conv_in_reg");
+    return 0;
+}
+
+int conv_in_small(const float* x, const float* w, const float* b, __half* out, int N, int Cin, int D, int H, int W,
+                  int Cout, int spatial_dims, float* stats_out, cudaStream_t stream) {
+    const int kd = spatial_dims == 3 ? 3 : 1;
+    const long long npix = static_cast<long long>(N) * D * H * W;
+    if (conv_in_has_stats(Cin, Cout, spatial_dims)) {
+        if (kd == 1 && Cin == 1) return launch_conv_in_reg<1, 1, 8>(x, w, b, out, N, D, H, W, Cout, stats_out, stream);
+        if (kd == 1 && Cin == 3) return launch_conv_in_reg<3, 1, 4>(x, w, b, out, N, D, H, W, Cout, stats_out, stream);
+        if (kd == 3 && Cin == 1) return launch_conv_in_reg<1, 3, 4>(x, w, b, out, N, D, H, W, Cout, stats_out, stream);
+    }
+    if (stats_out) { set_error("conv_in_small: fused statistics unsupported for Cin=%d", Cin); return 2; }
     const size_t smem = static_cast<size_t>(kd) * 9 * Cin * Cout * sizeof(float);
     if (Cout % 8 || smem > 200 * 1024) { set_error("conv_in_small: Cin=%d Cout=%d unsupported", Cin, Cout); return 2; }
     static size_t smem_set = 48 * 1024;
@@ -425,7 +641,7 @@ int conv_in_small(const float* x, const float* w, const float* b, __half* out, i
         if (e != cudaSuccess) { set_error("conv_in_small: %s", cudaGetErrorString(e)); return 4; }
         smem_set = smem;
     }
-    const long long total = static_cast<long long>(N) * D * H * W * (Cout / 8);
+    const long long total = npix * (Cout / 8);
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     conv_in_small_kernel<<<static_cast<int>(blocks), 256, smem, stream>>>(x, w, b, out, N, Cin, D, H, W, Cout, kd);

@@ -15,6 +15,7 @@ int gn_silu(const __half* src0, int C0, const __half* src1, int C1, const float*
 
 // Sinusoidal embedding -> Linear(E, 4E) -> SiLU -> Linear(4E, 4E) -> SiLU (the SiLU every ResnetBlock applies before its
 // time_emb_proj).  timesteps: [R] int64 on the device, or null for the uniform value t_uniform with R == 1.
+// With timesteps == null and R > 1, row r uses the timestep t_uniform + r (table build).
 // act_out: [R, 4E] fp32.
 int time_embed(const long long* timesteps, int t_uniform, int R, int E, const float* w0, const float* b0,
                const float* w1, const float* b1, float* act_out, cudaStream_t stream);
@@ -31,8 +32,17 @@ int upsample_nearest2(const __half* in, __half* out, int N, int D, int H, int W,
 
 // conv_in for few input channels (Cin <= 8): x fp32 [N, Cin, D, H, W] -> out fp16 [N, D, H, W, Cout]; w fp32
 // [Cout, Cin, taps]; 3x3(x3), pad 1.
+// stats_out (optional, only when conv_in_has_stats()): GroupNorm partial sums [N][conv_in_stats_parts][Cout/4][2].
 int conv_in_small(const float* x, const float* w, const float* b, __half* out, int N, int Cin, int D, int H, int W,
-                  int Cout, int spatial_dims, cudaStream_t stream);
+                  int Cout, int spatial_dims, float* stats_out, cudaStream_t stream);
+int conv_in_stats_parts(int D, int H, int W);
+bool conv_in_has_stats(int Cin, int Cout, int spatial_dims);
+
+// GroupNorm (+ SiLU) from producer-side partial statistics (see ConvGemmParams::stats_out): one read + one write.
+// st0/st1: [N][parts][C/4][2] fp32 partial (sum, sum of squares) per 4-channel quad.
+int gn_apply(const __half* src0, int C0, const float* st0, int parts0, const __half* src1, int C1, const float* st1,
+             int parts1, const float* gamma, const float* beta, __half* out, int N, int S, int groups, float eps,
+             bool silu, cudaStream_t stream);
 
 // Layout conversions for many-channel inputs/outputs (latent models): fp32 [N, C, S] <-> fp16 [N, S, C].
 int nchw_to_nhwc_half(const float* x, __half* out, int N, int C, long long S, cudaStream_t stream);

@@ -169,3 +169,38 @@ if __name__ == "__main__":
                   f"ref_std={float(want.std()):.3f}", flush=True)
         except Exception as e:  # noqa: BLE001
             print(f"{name:28s} EXC {type(e).__name__}: {e}", flush=True)
+
+
+@pytest.mark.parametrize("name", ["fashionmnist_1x32x32", "native_1x28x28", "celeba_3x64x64"])
+def test_fused_groupnorm_statistics_equal_two_pass(name, monkeypatch):
+    """GroupNorm statistics emitted by the producers' epilogues (conv_gemm / conv_in) + gn_apply must reproduce the
+    stand-alone two-pass gn_silu kernel: both sum the same fp16-rounded values in fp32, only the order differs."""
+    case = FWD_CASES[name]
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(case["shape"], generator=g).cuda()
+    t = torch.randint(0, 1000, (case["shape"][0],), generator=g).cuda()
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("DDPM_FUSE_GN", flag)
+        _, ours = _pair(case["sd"], case["ch"])
+        outs[flag] = ours(x, timesteps=t).cpu()
+    rel = _rel(outs["1"], outs["0"])
+    assert rel < 2e-4, (name, rel)
+
+
+def test_uniform_timestep_table_equals_per_sample_path():
+    """run_chain takes the timestep-embedding row from the table built at weight upload; forward() with a timesteps
+    tensor runs the MLP per call. Same kernels, same arithmetic: the fused chain must equal the drop-in loop bitwise
+    (also covered end to end by test_unfused_dropin_loop_equals_fused_chain)."""
+    _, ours = _pair(2, 1)
+    _, sched = _make_scheds()
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn((2, 1, 32, 32), generator=g).cuda()
+    a = x.clone()
+    sched.run_chain(ours, a, [30, 20])
+    _, sched2 = _make_scheds()
+    b = x.clone()
+    for t in (30, 20):
+        eps = ours(b, timesteps=torch.full((2,), t, dtype=torch.long, device="cuda"))
+        b, _ = sched2.step(eps, t, b)
+    assert torch.equal(a, b)
