@@ -36,6 +36,7 @@ class ConvArgs(C.Structure):
         ("group", C.c_int),
         ("vt_col0", C.c_int),
         ("out_vt", C.c_void_p),
+        ("stats_out", C.c_void_p),
     ]
 
 
@@ -91,6 +92,12 @@ SIGNATURES = {
     "ddpm_last_error": (C.c_char_p, []),
     "ddpm_abi_version": (C.c_int, []),
     "ddpm_conv_forward": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    "ddpm_conv_stats_parts": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ddpm_gn_silu": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                               C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]),
+    "ddpm_gn_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                C.c_void_p]),
     "ddpm_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong,
                                         C.c_longlong, C.c_void_p]),
     "ddpm_unet_create": (C.c_int, [C.POINTER(UNetConfig), C.POINTER(C.c_void_p)]),

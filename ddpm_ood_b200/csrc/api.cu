@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include "conv_gemm.cuh"
+#include "kernels.cuh"
 
 namespace ddpm {
 
@@ -42,7 +43,7 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, i
 extern "C" {
 
 const char* ddpm_last_error(void) { return ddpm::last_error(); }
-int ddpm_abi_version(void) { return 1; }
+int ddpm_abi_version(void) { return 2; }
 
 int ddpm_conv_forward(const ddpm_conv_args* a, void* stream) {
     if (!a) { ddpm::set_error("ddpm_conv_forward: null args"); return 2; }
@@ -70,10 +71,28 @@ int ddpm_conv_forward(const ddpm_conv_args* a, void* stream) {
     q.group = a->group;
     q.vt_col0 = a->vt_col0;
     q.out_vt = a->out_vt;
+    q.stats_out = a->stats_out;
     ddpm::ConvLaunch l;
     int rc = ddpm::conv_prepare(q, ddpm::num_sms(), &l);
     if (rc) return rc;
     return ddpm::conv_launch(l, static_cast<cudaStream_t>(stream));
+}
+
+int ddpm_conv_stats_parts(int spatial_dims, int Dout, int Hout, int Wout) {
+    return ddpm::conv_stats_parts(spatial_dims, Dout, Hout, Wout);
+}
+
+int ddpm_gn_silu(const void* src0, int C0, const void* src1, int C1, const float* gamma, const float* beta, void* out,
+                 int N, int S, int groups, float eps, int silu, void* stream) {
+    return ddpm::gn_silu(static_cast<const __half*>(src0), C0, static_cast<const __half*>(src1), C1, gamma, beta,
+                         static_cast<__half*>(out), N, S, groups, eps, silu != 0, static_cast<cudaStream_t>(stream));
+}
+int ddpm_gn_apply(const void* src0, int C0, const float* st0, int parts0, const void* src1, int C1, const float* st1,
+                  int parts1, const float* gamma, const float* beta, void* out, int N, int S, int groups, float eps,
+                  int silu, void* stream) {
+    return ddpm::gn_apply(static_cast<const __half*>(src0), C0, st0, parts0, static_cast<const __half*>(src1), C1, st1,
+                          parts1, gamma, beta, static_cast<__half*>(out), N, S, groups, eps, silu != 0,
+                          static_cast<cudaStream_t>(stream));
 }
 
 int ddpm_pack_conv_weight(const float* w, int Cout, int Cin, int taps, void* dst, long long ktot, long long koff,

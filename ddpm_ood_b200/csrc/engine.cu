@@ -388,8 +388,7 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
         Act a{lay.take<__half>(static_cast<size_t>(N) * d * h * w * C), C, d, h, w, nullptr, 0};
         if (want_stats && fuse_gn_stats_) {
             a.parts = conv_stats_parts(sd, d, h, w);
-            a.stats = take_stats(C, a.parts);
-            if (!a.stats) a.parts = 0;
+            a.stats = take_stats(C, a.parts);  // null in the sizing (dry) pass; `parts` is what decisions key on
         }
         return a;
     };
@@ -418,7 +417,7 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             if (measure) { if (cnt > max_z) max_z = cnt; return; }
             Op op{};
             op.type = Op::GN;
-            if (a.stats && (!b || b->stats)) {
+            if (a.parts > 0 && (!b || b->parts > 0)) {
                 op.st0 = a.stats; op.parts0 = a.parts;
                 op.st1 = b ? b->stats : nullptr; op.parts1 = b ? b->parts : 0;
             }
@@ -499,7 +498,6 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             if (!measure && fuse_gn_stats_) {
                 h1.parts = conv_stats_parts(sd, h.D, h.H, h.W);
                 h1.stats = take_stats(r.cout, h1.parts);
-                if (!h1.stats) h1.parts = 0;
             }
             conv3(h, zA, cin, r.w1, r.bias1, r.cout, 1, r.temb_off, nullptr, hB, nullptr, nullptr, h1.stats);
             gn(h1, nullptr, r.g2, r.b2, zB, true);
@@ -608,11 +606,26 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             }
         }
         if (h.D != D || h.H != H || h.W != W) { set_error("unet: output spatial size mismatch"); return 7; }
-        gn(h, nullptr, out_g_, out_b_, zA, true);
+        const bool out_taps = !measure && !out_gemm_ && h.parts > 0 && conv_out_taps_supported(h.C, c.out_channels, sd);
+        float* dtaps = nullptr;
+        if (out_taps) {
+            // final GroupNorm+SiLU fused with the output conv's channel reduction; no normalised tensor in memory
+            dtaps = lay.take<float>(static_cast<size_t>(N) * D * H * W * 9 * c.out_channels);
+            Op op{};
+            op.type = Op::GN;
+            op.src0 = h.p; op.C0 = h.C; op.st0 = h.stats; op.parts0 = h.parts;
+            op.gamma = out_g_; op.beta = out_b_; op.S = static_cast<int>(h.S()); op.silu = true;
+            op.dtaps = dtaps;
+            op.bytes = static_cast<double>(N) * h.S() * (2.0 * h.C + 36.0 * c.out_channels);
+            plan.ops.push_back(op);
+        } else {
+            gn(h, nullptr, out_g_, out_b_, zA, true);
+        }
         if (!measure) {
             plan.z_out = zA;
             Op op{};
             op.type = out_gemm_ ? Op::CONV_OUT_GEMM : Op::CONV_OUT_SMALL;
+            op.dtaps = dtaps;
             op.src0 = zA; op.D = D; op.H = H; op.W = W; op.C = h.C;
             op.flops = 2.0 * N * D * H * W * c.out_channels * (sd == 3 ? 27.0 : 9.0) * h.C;
             op.bytes = static_cast<double>(N) * D * H * W * (2.0 * h.C + 4.0 * c.out_channels);
@@ -707,7 +720,10 @@ int UNet::forward(const float* x, const long long* timesteps, int t_uniform, flo
                 ++launches_;
                 break;
             case Op::GN:
-                if (op.st0)
+                if (op.dtaps)
+                    rc = gn_apply_taps(op.src0, op.C0, op.st0, op.parts0, op.gamma, op.beta, conv_out_w_, c.out_channels,
+                                       op.dtaps, N, op.S, c.norm_num_groups, c.norm_eps, stream);
+                else if (op.st0)
                     rc = gn_apply(op.src0, op.C0, op.st0, op.parts0, op.src1, op.C1, op.st1, op.parts1, op.gamma, op.beta,
                                   op.dst, N, op.S, c.norm_num_groups, c.norm_eps, op.silu, stream);
                 else
@@ -728,6 +744,11 @@ int UNet::forward(const float* x, const long long* timesteps, int t_uniform, flo
                 rc = upsample_nearest2(op.src0, op.dst, N, op.D, op.H, op.W, op.C, c.spatial_dims, stream);
                 break;
             case Op::CONV_OUT_SMALL:
+                if (op.dtaps) {
+                    rc = conv_out_gather(op.dtaps, conv_out_b_, out, N, H, W, c.out_channels, plms, ring, stash, sample,
+                                         stream);
+                    break;
+                }
                 rc = conv_out_small(op.src0, conv_out_w_, conv_out_b_, out, N, op.C, D, H, W, c.out_channels,
                                     c.spatial_dims, plms, ring, stash, sample, stream);
                 break;

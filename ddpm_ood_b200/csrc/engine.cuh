@@ -74,6 +74,7 @@ struct Op {
     const float *gamma, *beta;
     const float *st0, *st1;  // producer-side GroupNorm partial statistics (null: two-pass gn_silu)
     int parts0, parts1;
+    float* dtaps;  // out norm fused with conv_out: per-pixel tap values (GN op writes, CONV_OUT_SMALL op gathers)
     __half* dst;
     int S;
     bool silu;

@@ -17,6 +17,9 @@ namespace ddpm {
     } while (0)
 
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+// GroupNorm epilogues round to fp16 right after: ex2.approx + rcp.approx (2 ulp in fp32) is exact enough and ~4x cheaper
+// than the IEEE division above.
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
     const __half2* h = reinterpret_cast<const __half2*>(&v);
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(256) gn_silu_kernel(const __half* __restrict__
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float y = f[i] * a[i] + b[i];
-                f[i] = do_silu ? silu(y) : y;
+                f[i] = do_silu ? silu_fast(y) : y;
             }
             *reinterpret_cast<uint4*>(obase + static_cast<size_t>(p) * C) = pack8(f);
         }
@@ -156,17 +159,33 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
     const int Q = C >> 2, Q0 = C0 >> 2, Q1 = C1 >> 2;
     const int n = blockIdx.y;
     const int tid = threadIdx.x;
-    for (int qd = tid; qd < Q; qd += blockDim.x) {
-        float a = 0.f, b = 0.f;
-        if (qd < Q0) {
-            const float2* p = reinterpret_cast<const float2*>(st0) + static_cast<size_t>(n) * parts0 * Q0 + qd;
-            for (int i = 0; i < parts0; ++i) { const float2 v = __ldg(p + static_cast<size_t>(i) * Q0); a += v.x; b += v.y; }
-        } else {
-            const float2* p = reinterpret_cast<const float2*>(st1) + static_cast<size_t>(n) * parts1 * Q1 + (qd - Q0);
-            for (int i = 0; i < parts1; ++i) { const float2 v = __ldg(p + static_cast<size_t>(i) * Q1); a += v.x; b += v.y; }
+    {
+        // fixed-order two-level sum of the partials: J threads per quad take parts j, j+J, ... (independent loads),
+        // then one thread per quad adds the J sub-sums.
+        __shared__ float2 s_sub[256];
+        const int J = Q <= 256 ? 256 / Q : 1;
+        for (int base = 0; base < Q; base += 256) {
+            const int qd = base + tid % (Q < 256 ? Q : 256);
+            const int j = tid / (Q < 256 ? Q : 256);
+            float a = 0.f, b = 0.f;
+            if (qd < Q && j < J) {
+                const float2* p;
+                int parts, Qs;
+                if (qd < Q0) { p = reinterpret_cast<const float2*>(st0) + static_cast<size_t>(n) * parts0 * Q0 + qd; parts = parts0; Qs = Q0; }
+                else { p = reinterpret_cast<const float2*>(st1) + static_cast<size_t>(n) * parts1 * Q1 + (qd - Q0); parts = parts1; Qs = Q1; }
+#pragma unroll 4
+                for (int i = j; i < parts; i += J) { const float2 v = __ldg(p + static_cast<size_t>(i) * Qs); a += v.x; b += v.y; }
+            }
+            s_sub[tid] = make_float2(a, b);
+            __syncthreads();
+            if (tid < 256 && base + tid < Q && tid < (Q < 256 ? Q : 256)) {
+                float sa = 0.f, sb = 0.f;
+                for (int jj = 0; jj < J; ++jj) { const float2 v = s_sub[jj * (Q < 256 ? Q : 256) + tid]; sa += v.x; sb += v.y; }
+                s_qs[base + tid] = sa;
+                s_qq[base + tid] = sb;
+            }
+            __syncthreads();
         }
-        s_qs[qd] = a;
-        s_qq[qd] = b;
     }
     __syncthreads();
     const float inv_n = 1.0f / (static_cast<float>(cpg) * static_cast<float>(S));
@@ -183,26 +202,42 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
         s_b[c] = beta[c] - mean * a;
     }
     __syncthreads();
-    const int V = C >> 3;  // uint4 vectors per pixel
+    // apply: a thread keeps one 8-channel vector (scale/shift in registers) and walks pixels, 4 loads in flight
+    const int V = C >> 3;              // uint4 vectors per pixel
+    const int ppi = blockDim.x / V;    // pixels per block iteration (threads beyond ppi*V idle in this phase)
     const int p_begin = blockIdx.x * chunk;
     const int p_end = min(S, p_begin + chunk);
-    const int total = (p_end - p_begin) * V;
-    const __half* b0 = src0 + static_cast<size_t>(n) * S * C0;
-    const __half* b1 = src1 ? src1 + static_cast<size_t>(n) * S * C1 : nullptr;
-    __half* ob = out + static_cast<size_t>(n) * S * C;
-    for (int i = tid; i < total; i += blockDim.x) {
-        const int pp = p_begin + i / V;
-        const int c = (i % V) * 8;
-        const uint4 raw = (c < C0) ? __ldg(reinterpret_cast<const uint4*>(b0 + static_cast<size_t>(pp) * C0 + c))
-                                   : __ldg(reinterpret_cast<const uint4*>(b1 + static_cast<size_t>(pp) * C1 + (c - C0)));
-        float f[8];
-        unpack8(raw, f);
+    if (tid >= ppi * V) return;
+    const int cv = tid % V, pl = tid / V;
+    const int c = cv * 8;
+    float ga[8], gb[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float y = f[e] * s_a[c + e] + s_b[c + e];
-            f[e] = do_silu ? silu(y) : y;
+    for (int e = 0; e < 8; ++e) { ga[e] = s_a[c + e]; gb[e] = s_b[c + e]; }
+    const bool first = c < C0;
+    const int Cs = first ? C0 : C1;
+    const __half* sb = first ? src0 + static_cast<size_t>(n) * S * C0 + c : src1 + static_cast<size_t>(n) * S * C1 + (c - C0);
+    __half* ob = out + static_cast<size_t>(n) * S * C + c;
+    for (int pp = p_begin + pl; pp < p_end; pp += 4 * ppi) {
+        uint4 raw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int q = pp + u * ppi;
+            if (q < p_end) raw[u] = __ldg(reinterpret_cast<const uint4*>(sb + static_cast<size_t>(q) * Cs));
         }
-        *reinterpret_cast<uint4*>(ob + static_cast<size_t>(pp) * C + c) = pack8(f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int q = pp + u * ppi;
+            if (q < p_end) {
+                float f[8];
+                unpack8(raw[u], f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float y = fmaf(f[e], ga[e], gb[e]);
+                    f[e] = do_silu ? silu_fast(y) : y;
+                }
+                *reinterpret_cast<uint4*>(ob + static_cast<size_t>(q) * C) = pack8(f);
+            }
+        }
     }
 }
 
@@ -804,6 +839,181 @@ int conv_out_small(const __half* z, const float* w, const float* b, float* eps_o
     conv_out_small_kernel<<<static_cast<int>(blocks), 256, smem, stream>>>(z, w, b, eps_out, N, Cin, D, H, W, Cout, kd,
                                                                            plms ? 1 : 0, st, ring, stash, sample);
     DDPM_CHECK_LAUNCH("conv_out_small");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ out norm + conv_out
+// The last GroupNorm+SiLU and the few-channel output conv without materialising the normalised tensor:
+//   (1) gn_apply_taps_kernel reads the last activation once, normalises, and reduces every pixel's C channels against
+//       the 9 taps' weights: d[pixel][co*9 + tap] = sum_c z[pixel][c] * w[co][c][tap]       (fp32, 36 B per pixel)
+//   (2) conv_out_gather_kernel sums the 9 neighbours' tap values, adds the bias and applies the PLMS update.
+// out[q] = sum_t w[t] . z[q + off_t] = sum_t d[q + off_t][t].
+template <int COUT, int CPT, int G>
+__global__ void __launch_bounds__(256) gn_apply_taps_kernel(const __half* __restrict__ src, const float* __restrict__ st,
+                                                            int parts, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, const float* __restrict__ w,
+                                                            float* __restrict__ d_out, int S, int cpg, float eps,
+                                                            int chunk) {
+    constexpr int C = G * CPT;
+    constexpr int NV = 9 * COUT;
+    static_assert(NV <= G, "tap values must fit the pixel's lane group");
+    __shared__ float s_qs[C / 4], s_qq[C / 4];
+    __shared__ float s_a[C], s_b[C];
+    const int n = blockIdx.y;
+    const int tid = threadIdx.x;
+    {
+        __shared__ float2 s_sub[256];
+        constexpr int Q = C / 4;
+        constexpr int J = 256 / Q;
+        const int qd = tid % Q, j = tid / Q;
+        float a = 0.f, b = 0.f;
+        if (j < J) {
+            const float2* p = reinterpret_cast<const float2*>(st) + static_cast<size_t>(n) * parts * Q + qd;
+#pragma unroll 4
+            for (int i = j; i < parts; i += J) { const float2 v = __ldg(p + static_cast<size_t>(i) * Q); a += v.x; b += v.y; }
+        }
+        s_sub[tid] = make_float2(a, b);
+        __syncthreads();
+        if (tid < Q) {
+            float sa = 0.f, sb = 0.f;
+            for (int jj = 0; jj < J; ++jj) { const float2 v = s_sub[jj * Q + tid]; sa += v.x; sb += v.y; }
+            s_qs[tid] = sa;
+            s_qq[tid] = sb;
+        }
+    }
+    __syncthreads();
+    const float inv_n = 1.0f / (static_cast<float>(cpg) * static_cast<float>(S));
+    for (int c = tid; c < C; c += blockDim.x) {
+        const int q0 = (c / cpg) * (cpg >> 2);
+        float sum = 0.f, sq = 0.f;
+        for (int i = 0; i < (cpg >> 2); ++i) { sum += s_qs[q0 + i]; sq += s_qq[q0 + i]; }
+        const float mean = sum * inv_n;
+        float var = sq * inv_n - mean * mean;
+        var = var < 0.f ? 0.f : var;
+        const float a = gamma[c] * rsqrtf(var + eps);
+        s_a[c] = a;
+        s_b[c] = beta[c] - mean * a;
+    }
+    __syncthreads();
+    const int g = tid % G, pl = tid / G;
+    constexpr int ppb = 256 / G;
+    float wr[NV][CPT], ga[CPT], gb[CPT];
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+            wr[k][j] = w[(static_cast<size_t>(k / 9) * C + g * CPT + j) * 9 + (k % 9)];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) { ga[j] = s_a[g * CPT + j]; gb[j] = s_b[g * CPT + j]; }
+    const int p_begin = blockIdx.x * chunk;
+    const int p_end = min(S, p_begin + chunk);
+    const __half* base = src + static_cast<size_t>(n) * S * C + g * CPT;
+    for (int p0 = p_begin; p0 < p_end; p0 += ppb) {  // uniform trip count: the shuffles need every lane
+        const int pp = p0 + pl;
+        const bool live = pp < p_end;
+        float z[CPT];
+        if (live) {
+            if constexpr (CPT == 8) {
+                unpack8(__ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(pp) * C)), z);
+            } else {
+                const uint2 raw = __ldg(reinterpret_cast<const uint2*>(base + static_cast<size_t>(pp) * C));
+                const __half2* h = reinterpret_cast<const __half2*>(&raw);
+                const float2 t0 = __half22float2(h[0]), t1 = __half22float2(h[1]);
+                z[0] = t0.x; z[1] = t0.y; z[2] = t1.x; z[3] = t1.y;
+            }
+#pragma unroll
+            for (int j = 0; j < CPT; ++j)  // fp16 rounding of the normalised value, like the materialised path
+                z[j] = __half2float(__float2half_rn(silu_fast(fmaf(z[j], ga[j], gb[j]))));
+        } else {
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) z[j] = 0.f;
+        }
+        float v[G];
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            float acc = 0.f;
+            if (k < NV) {
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) acc = fmaf(z[j], wr[k < NV ? k : 0][j], acc);
+            }
+            v[k] = acc;
+        }
+        // transpose-reduce over the pixel's G lanes: lane g ends with the total of value g
+#pragma unroll
+        for (int half_n = G / 2, off = G / 2; half_n >= 1; half_n >>= 1, off >>= 1) {
+            const bool hi = (g & off) != 0;
+#pragma unroll
+            for (int i = 0; i < half_n; ++i) {
+                const float send = hi ? v[i] : v[i + half_n];
+                const float keep = hi ? v[i + half_n] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+        }
+        if (live && g < NV) d_out[(static_cast<size_t>(n) * S + pp) * NV + g] = v[0];
+    }
+}
+
+bool conv_out_taps_supported(int C, int Cout, int spatial_dims) {
+    if (spatial_dims != 2) return false;
+    return (C == 128 && (Cout == 1 || Cout == 3)) || (C == 256 && Cout == 1);
+}
+
+int gn_apply_taps(const __half* src, int C, const float* st, int parts, const float* gamma, const float* beta,
+                  const float* w, int Cout, float* d_out, int N, int S, int groups, float eps, cudaStream_t stream) {
+    if (!conv_out_taps_supported(C, Cout, 2) || C % groups || (C / groups) % 4) {
+        set_error("gn_apply_taps: C=%d Cout=%d unsupported", C, Cout);
+        return 2;
+    }
+    int chunk = S;
+    while (chunk > 32 && static_cast<long long>(N) * ((S + chunk - 1) / chunk) < 2 * 148 && chunk % 2 == 0) chunk >>= 1;
+    while (chunk > 256) chunk = (chunk + 1) >> 1;
+    dim3 grid((S + chunk - 1) / chunk, N);
+    const int cpg = C / groups;
+    if (C == 128 && Cout == 1)
+        gn_apply_taps_kernel<1, 8, 16><<<grid, 256, 0, stream>>>(src, st, parts, gamma, beta, w, d_out, S, cpg, eps, chunk);
+    else if (C == 128 && Cout == 3)
+        gn_apply_taps_kernel<3, 4, 32><<<grid, 256, 0, stream>>>(src, st, parts, gamma, beta, w, d_out, S, cpg, eps, chunk);
+    else
+        gn_apply_taps_kernel<1, 8, 32><<<grid, 256, 0, stream>>>(src, st, parts, gamma, beta, w, d_out, S, cpg, eps, chunk);
+    DDPM_CHECK_LAUNCH("gn_apply_taps");
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) conv_out_gather_kernel(const float* __restrict__ d, const float* __restrict__ b,
+                                                              float* __restrict__ eps_out, int N, int H, int W, int Cout,
+                                                              int fuse, PlmsStep st, float* ring, float* stash,
+                                                              float* sample) {
+    const int S = H * W;
+    const int NV = 9 * Cout;
+    const long long numel = static_cast<long long>(N) * Cout * S;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < numel;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int sp = static_cast<int>(idx % S);
+        const int nc = static_cast<int>(idx / S);
+        const int co = nc % Cout, n = nc / Cout;
+        const int hq = sp / W, wq = sp - hq * W;
+        float e = b[co];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int hh = hq + t / 3 - 1, ww = wq + t % 3 - 1;
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                e += __ldg(d + (static_cast<size_t>(n) * S + hh * W + ww) * NV + co * 9 + t);
+        }
+        if (eps_out) eps_out[idx] = e;
+        if (fuse) plms_apply(st, e, idx, numel, ring, stash, sample, sample);
+    }
+}
+
+int conv_out_gather(const float* d, const float* b, float* eps_out, int N, int H, int W, int Cout, const PlmsStep* plms,
+                    float* ring, float* stash, float* sample, cudaStream_t stream) {
+    const long long numel = static_cast<long long>(N) * Cout * H * W;
+    long long blocks = (numel + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    PlmsStep st{};
+    if (plms) st = *plms;
+    conv_out_gather_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(d, b, eps_out, N, H, W, Cout, plms ? 1 : 0, st,
+                                                                         ring, stash, sample);
+    DDPM_CHECK_LAUNCH("conv_out_gather");
     return 0;
 }
 

@@ -67,6 +67,14 @@ struct PlmsStep {
 int conv_out_small(const __half* z, const float* w, const float* b, float* eps_out, int N, int Cin, int D, int H,
                    int W, int Cout, int spatial_dims, const PlmsStep* plms, float* ring, float* stash, float* sample,
                    cudaStream_t stream);
+// Final GroupNorm+SiLU fused with the few-channel output conv's channel reduction (2-D): d_out[N*S][9*Cout] fp32 tap
+// values, then conv_out_gather sums the 3x3 neighbourhood, adds the bias and (optionally) applies the PLMS update.
+bool conv_out_taps_supported(int C, int Cout, int spatial_dims);
+int gn_apply_taps(const __half* src, int C, const float* st, int parts, const float* gamma, const float* beta,
+                  const float* w /*fp32 [Cout][C][9]*/, int Cout, float* d_out, int N, int S, int groups, float eps,
+                  cudaStream_t stream);
+int conv_out_gather(const float* d, const float* b, float* eps_out, int N, int H, int W, int Cout, const PlmsStep* plms,
+                    float* ring, float* stash, float* sample, cudaStream_t stream);
 // Stand-alone PLMS update (model output produced elsewhere, e.g. the drop-in scheduler.step()).
 int plms_update(const float* eps_new, const PlmsStep& st, float* ring, float* stash, const float* sample_in,
                 float* sample_out, long long numel, cudaStream_t stream);

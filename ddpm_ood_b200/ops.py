@@ -47,6 +47,7 @@ def conv_forward(
     group: int = 0,
     vt_col0: int = 0,
     out_vt: Optional[torch.Tensor] = None,
+    stats_out: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
     """segs: fp16 channels-last tensors [N, (D,) H, W, C]; weights: packed fp16 [rows, Ktot]."""
     x0 = segs[0]
@@ -84,5 +85,38 @@ def conv_forward(
     a.group = group
     a.vt_col0 = vt_col0
     a.out_vt = _ptr(out_vt)
+    a.stats_out = _ptr(stats_out)
     check(lib().ddpm_conv_forward(C.byref(a), current_stream_ptr()), "ddpm_conv_forward")
+    return out
+
+
+def conv_stats_parts(spatial_dims: int, d: int, h: int, w: int) -> int:
+    """GroupNorm-statistics parts per image that conv_forward(stats_out=...) emits for an output of this geometry."""
+    return int(lib().ddpm_conv_stats_parts(spatial_dims, d, h, w))
+
+
+def gn_silu(src0: torch.Tensor, src1: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, groups: int,
+            eps: float, silu: bool = True) -> torch.Tensor:
+    """Two-pass GroupNorm(+SiLU) over cat(src0, src1) (channels-last fp16 [N, ..., C])."""
+    n = src0.shape[0]
+    c0 = src0.shape[-1]
+    c1 = 0 if src1 is None else src1.shape[-1]
+    s = src0.numel() // (n * c0)
+    out = torch.empty(src0.shape[:-1] + (c0 + c1,), dtype=torch.float16, device=src0.device)
+    check(lib().ddpm_gn_silu(src0.data_ptr(), c0, _ptr(src1), c1, gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), n, s,
+                             groups, eps, int(silu), current_stream_ptr()), "ddpm_gn_silu")
+    return out
+
+
+def gn_apply(src0: torch.Tensor, st0: torch.Tensor, src1: Optional[torch.Tensor], st1: Optional[torch.Tensor],
+             gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool = True) -> torch.Tensor:
+    """One-pass GroupNorm(+SiLU) from producer-side partial statistics st* [N, parts, C/4, 2] fp32."""
+    n = src0.shape[0]
+    c0 = src0.shape[-1]
+    c1 = 0 if src1 is None else src1.shape[-1]
+    s = src0.numel() // (n * c0)
+    out = torch.empty(src0.shape[:-1] + (c0 + c1,), dtype=torch.float16, device=src0.device)
+    check(lib().ddpm_gn_apply(src0.data_ptr(), c0, st0.data_ptr(), st0.shape[1], _ptr(src1), c1, _ptr(st1),
+                              0 if st1 is None else st1.shape[1], gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), n, s,
+                              groups, eps, int(silu), current_stream_ptr()), "ddpm_gn_apply")
     return out

@@ -57,8 +57,24 @@ typedef struct ddpm_conv_args {
     int group;               /* mode 1: tokens per image */
     int vt_col0;             /* mode 2 */
     void* out_vt;            /* mode 2 */
+    float* stats_out;        /* mode 0, optional: GroupNorm partial statistics of the fp16-rounded output,
+                                [N][ddpm_conv_stats_parts()][Cout/4][2] fp32 = (sum, sum of squares) per 4-channel quad
+                                and 32-pixel part of an image; consumed by ddpm_gn_apply() */
 } ddpm_conv_args;
 DDPM_API int ddpm_conv_forward(const ddpm_conv_args* args, void* stream);
+/* Parts per image that ddpm_conv_forward emits for an output of this geometry (0: unsupported, use ddpm_gn_silu). */
+DDPM_API int ddpm_conv_stats_parts(int spatial_dims, int Dout, int Hout, int Wout);
+
+/* GroupNorm(groups, eps) (+ SiLU) over the channel concatenation of up to two channels-last fp16 tensors
+ * src0 [N,S,C0], src1 [N,S,C1] (or NULL) -> out [N,S,C0+C1] fp16: the norm in front of every conv of
+ * DiffusionModelUNet (ResnetBlock norm1/norm2, AttentionBlock norm, out.0).
+ * ddpm_gn_silu computes the statistics itself (two passes); ddpm_gn_apply takes the producers' partial statistics
+ * (st0/st1 as written through ddpm_conv_args.stats_out) and makes one pass. */
+DDPM_API int ddpm_gn_silu(const void* src0, int C0, const void* src1, int C1, const float* gamma, const float* beta,
+                          void* out, int N, int S, int groups, float eps, int silu, void* stream);
+DDPM_API int ddpm_gn_apply(const void* src0, int C0, const float* st0, int parts0, const void* src1, int C1,
+                           const float* st1, int parts1, const float* gamma, const float* beta, void* out, int N, int S,
+                           int groups, float eps, int silu, void* stream);
 
 /* fp32 PyTorch conv weight [Cout][Cin][taps] (or Linear weight with taps == 1) -> fp16 rows of a packed matrix:
  * dst[co * ktot + koff + tap * Cin + ci]. */

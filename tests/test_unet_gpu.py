@@ -185,7 +185,11 @@ def test_fused_groupnorm_statistics_equal_two_pass(name, monkeypatch):
         _, ours = _pair(case["sd"], case["ch"])
         outs[flag] = ours(x, timesteps=t).cpu()
     rel = _rel(outs["1"], outs["0"])
-    assert rel < 2e-4, (name, rel)
+    # Not bitwise: a 1e-6 relative perturbation anywhere re-randomises the fp16 rounding decisions downstream and
+    # saturates at the fp16 noise floor (~1e-3 relative L2, measured with a perturbed input on B200), the same size as
+    # the distance to the fp32 oracle. The kernel-level equivalence (99.8% of elements bit-identical) is asserted in
+    # tests/test_groupnorm_gpu.py.
+    assert rel < 2.5e-3, (name, rel)
 
 
 def test_uniform_timestep_table_equals_per_sample_path():
