@@ -20,26 +20,30 @@ void set_error(const char* fmt, ...) {
 const char* last_error() { return g_err; }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int BN>
+// MT = M tiles (128 pixels each) a CTA works on at once, sharing every weight tile: <256,1> and <128,2> both move
+// 48 KB per 64-wide k-block for 2*128*256*64 MACs; <128,1> moves 32 KB for half the MACs and is TMA/shared-memory
+// feed-bound at ~50 % of the tensor pipe (measured, profiles/r01_*), so it is kept only for problems too small to pair.
+template <int BN, int MT>
 struct Cfg {
-    static constexpr int kStages = (BN == 256) ? 4 : 6;
-    static constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
+    static constexpr int kStages = (BN * MT == 256) ? 4 : 6;
+    static constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB per M tile
     static constexpr int kBBytes = BN * kBlockK * 2;
-    static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
+    static constexpr int kStageBytes = MT * kABytes + kBBytes;
+    static constexpr int kAccCols = MT * BN;      // TMEM columns of one accumulator stage
+    static constexpr int kTmemCols = 2 * kAccCols;  // two accumulator stages
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
-template <int BN>
+template <int BN, int MT>
 __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, MT>;
     extern __shared__ uint8_t smem_raw[];
     // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + C::kStages * C::kABytes;
+    uint8_t* smem_a = smem;                                  // [kStages][MT][16 KB]
+    uint8_t* smem_b = smem + C::kStages * MT * C::kABytes;   // [kStages][BN * 128 B]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
     uint64_t* full_bar = bars;                     // [kStages]  TMA -> MMA
     uint64_t* empty_bar = bars + C::kStages;       // [kStages]  MMA -> TMA
@@ -71,7 +75,8 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int num_m_groups = (p.num_m_tiles + MT - 1) / MT;  // a work item = MT consecutive M tiles x one N tile
+    const int total_tiles = num_m_groups * p.num_n_tiles;
 
     if (warp == 0) {
         // ================================================================= TMA producer (one thread)
@@ -79,17 +84,21 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m_tile = tile / p.num_n_tiles;
-                const int n_tile = tile - m_tile * p.num_n_tiles;
-                int t = m_tile;
-                const int tw = t % p.tiles_w; t /= p.tiles_w;
-                const int th = t % p.tiles_h; t /= p.tiles_h;
-                const int td = t % p.tiles_d; t /= p.tiles_d;
-                const int tn = t;
-                const int w0 = tw * p.bw * p.stride, h0 = th * p.bh * p.stride;
-                const int d0 = td * p.bd * (p.D > 1 ? p.stride : 1);
-                const int n0 = tn * p.bn;
-                const int brow = n_tile * BN + m_tile * p.b_rows_per_mtile;
+                const int m_group = tile / p.num_n_tiles;
+                const int n_tile = tile - m_group * p.num_n_tiles;
+                int w0[MT], h0[MT], d0[MT], n0[MT];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    int t = m_group * MT + mt;  // may run one past the last tile: its box is all out-of-bounds (zeros)
+                    const int tw = t % p.tiles_w; t /= p.tiles_w;
+                    const int th = t % p.tiles_h; t /= p.tiles_h;
+                    const int td = t % p.tiles_d; t /= p.tiles_d;
+                    w0[mt] = tw * p.bw * p.stride;
+                    h0[mt] = th * p.bh * p.stride;
+                    d0[mt] = td * p.bd * (p.D > 1 ? p.stride : 1);
+                    n0[mt] = t * p.bn;
+                }
+                const int brow = n_tile * BN + m_group * p.b_rows_per_mtile;
                 int seg = 0, seg_begin = 0;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     while (kb >= p.seg_kb_end[seg]) { seg_begin = p.seg_kb_end[seg]; ++seg; }
@@ -104,8 +113,11 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
                     const CUtensorMap* ma = seg == 0 ? &p.tmA[0] : (seg == 1 ? &p.tmA[1] : &p.tmA[2]);
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-                    ptx::tma_load_5d(smem_a + stage * C::kABytes, ma, &full_bar[stage], chunk * kBlockK,
-                                     w0 + iw - (kw >> 1), h0 + ih - (kh >> 1), d0 + id - (kd >> 1), n0);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+                        ptx::tma_load_5d(smem_a + (stage * MT + mt) * C::kABytes, ma, &full_bar[stage], chunk * kBlockK,
+                                         w0[mt] + iw - (kw >> 1), h0[mt] + ih - (kh >> 1), d0[mt] + id - (kd >> 1),
+                                         n0[mt]);
                     ptx::tma_load_2d(smem_b + stage * C::kBBytes, &p.tmB, &full_bar[stage], kb * kBlockK, brow);
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
@@ -122,16 +134,20 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
+                const uint32_t d_tmem = tmem_base + as * C::kAccCols;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
-                    const uint64_t da = ptx::make_desc_k128(ptx::smem_u32(smem_a + stage * C::kABytes));
                     const uint64_t db = ptx::make_desc_k128(ptx::smem_u32(smem_b + stage * C::kBBytes));
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
-                        // +32 bytes (>>4 = 2) per 16-element K step inside the 128B swizzle row
-                        ptx::umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const uint64_t da =
+                                ptx::make_desc_k128(ptx::smem_u32(smem_a + (stage * MT + mt) * C::kABytes));
+                            // +32 bytes (>>4 = 2) per 16-element K step inside the 128B swizzle row
+                            ptx::umma_f16(d_tmem + mt * BN, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        }
                     }
                     ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -147,8 +163,13 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_tile = tile / p.num_n_tiles;
-            const int n_tile = tile - m_tile * p.num_n_tiles;
+            const int m_group = tile / p.num_n_tiles;
+            const int n_tile = tile - m_group * p.num_n_tiles;
+            ptx::mbar_wait(&tfull_bar[as], aphase);
+            ptx::tc_fence_after();
+#pragma unroll 1
+            for (int mt = 0; mt < MT; ++mt) {
+            const int m_tile = m_group * MT + mt;
             int t = m_tile;
             const int tw = t % p.tiles_w; t /= p.tiles_w;
             const int th = t % p.tiles_h; t /= p.tiles_h;
@@ -161,10 +182,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
             const int n = tn * p.bn + r;
             const bool valid = (w < p.W) && (h < p.H) && (d < p.D) && (n < p.N);
             const size_t pix = ((static_cast<size_t>(n) * p.D + d) * p.H + h) * p.W + w;
-
-            ptx::mbar_wait(&tfull_bar[as], aphase);
-            ptx::tc_fence_after();
-            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * C::kAccCols + mt * BN;
 
             if (p.mode == EPI_SOFTMAX_BD) {
                 // Attention probabilities. Row = query token; its keys are the `group` columns of its own image:
@@ -327,6 +345,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
                     }
                 }
             }
+            }  // mt
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
@@ -483,7 +502,12 @@ int conv_prepare(const ConvProblem& q, int num_sms, ConvLaunch* out) {
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv: cuTensorMapEncodeTiled(B) failed: %d", (int)r); return 3; }
     }
-    const int total = p.num_m_tiles * p.num_n_tiles;
+    // Pair M tiles (MT = 2) for 128-wide outputs when there is enough work to keep every SM busy with pairs.
+    out->m_tiles_per_cta = 1;
+    if (BN == 128 && q.b_rows_per_mtile == 0 && q.mode == EPI_STORE && p.num_m_tiles * p.num_n_tiles >= 2 * num_sms)
+        out->m_tiles_per_cta = 2;
+    const int groups = (p.num_m_tiles + out->m_tiles_per_cta - 1) / out->m_tiles_per_cta;
+    const int total = groups * p.num_n_tiles;
     out->grid = total < num_sms ? total : num_sms;
     return 0;
 }
@@ -491,20 +515,25 @@ int conv_prepare(const ConvProblem& q, int num_sms, ConvLaunch* out) {
 static bool g_attr_set = false;
 int conv_launch(const ConvLaunch& l, cudaStream_t stream) {
     if (!g_attr_set) {
-        cudaError_t e1 = cudaFuncSetAttribute(conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              Cfg<128>::kSmemBytes);
-        cudaError_t e2 = cudaFuncSetAttribute(conv_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              Cfg<256>::kSmemBytes);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) {
-            set_error("conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        cudaError_t e1 = cudaFuncSetAttribute(conv_gemm_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              Cfg<128, 1>::kSmemBytes);
+        cudaError_t e2 = cudaFuncSetAttribute(conv_gemm_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              Cfg<256, 1>::kSmemBytes);
+        cudaError_t e3 = cudaFuncSetAttribute(conv_gemm_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              Cfg<128, 2>::kSmemBytes);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+            set_error("conv: cudaFuncSetAttribute failed: %s",
+                      cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
             return 4;
         }
         g_attr_set = true;
     }
     if (l.block_n == 256)
-        conv_gemm_kernel<256><<<l.grid, 256, Cfg<256>::kSmemBytes, stream>>>(l.p);
+        conv_gemm_kernel<256, 1><<<l.grid, 256, Cfg<256, 1>::kSmemBytes, stream>>>(l.p);
+    else if (l.m_tiles_per_cta == 2)
+        conv_gemm_kernel<128, 2><<<l.grid, 256, Cfg<128, 2>::kSmemBytes, stream>>>(l.p);
     else
-        conv_gemm_kernel<128><<<l.grid, 256, Cfg<128>::kSmemBytes, stream>>>(l.p);
+        conv_gemm_kernel<128, 1><<<l.grid, 256, Cfg<128, 1>::kSmemBytes, stream>>>(l.p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("conv: launch failed: %s", cudaGetErrorString(e)); return 5; }
     return 0;

@@ -66,7 +66,8 @@ struct ConvGemmParams {
 // Host side: filled by conv_prepare(), launched by conv_launch().
 struct ConvLaunch {
     ConvGemmParams p;
-    int block_n;  // 128 or 256
+    int block_n;          // 128 or 256
+    int m_tiles_per_cta;  // 1, or 2 (block_n == 128 only): two 128-pixel tiles share each weight tile
     int grid;
 };
 

@@ -78,6 +78,11 @@ CASES = {
     "3x3x3_stride2_8to4": dict(sd=3, n=3, sp=(8, 8, 8), segs=[(128, 3)], cout=256, stride=2),
     "3x3x3_2vox_256": dict(sd=3, n=20, sp=(2, 2, 2), segs=[(256, 3)], cout=256),
     "many_tiles_persistent": dict(sd=2, n=64, sp=(32, 32), segs=[(128, 3)], cout=128, use_res=True),
+    # >= 2 tiles per SM with Cout = 128: CTAs take PAIRS of M tiles sharing each weight tile (conv_gemm_kernel<128, 2>);
+    # 43 images x 7 tiles = 301 tiles, so the last pair is half empty
+    "paired_m_tiles_odd_count_28px": dict(sd=2, n=43, sp=(28, 28), segs=[(128, 3)], cout=128, use_cadd=True),
+    "paired_m_tiles_concat_skip": dict(sd=2, n=40, sp=(32, 32), segs=[(128, 3), (128, 1), (128, 1)], cout=128,
+                                       use_res=False),
 }
 
 

@@ -32,6 +32,7 @@ CASES = [
     dict(n=2, sp=(28, 28), c0=128, c1=0),     # ragged tile boxes (28 -> 32)
     dict(n=3, sp=(7, 7), c0=256, c1=0),
     dict(n=2, sp=(64, 64), c0=256, c1=128),
+    dict(n=40, sp=(32, 32), c0=128, c1=0),    # enough 128-wide tiles for the paired-M-tile conv kernel variant
 ]
 
 
