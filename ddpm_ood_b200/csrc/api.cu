@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <string.h>
 
+#include "attention.cuh"
 #include "conv_gemm.cuh"
 #include "kernels.cuh"
 
@@ -93,6 +94,19 @@ int ddpm_gn_apply(const void* src0, int C0, const float* st0, int parts0, const 
     return ddpm::gn_apply(static_cast<const __half*>(src0), C0, st0, parts0, static_cast<const __half*>(src1), C1, st1,
                           parts1, gamma, beta, static_cast<__half*>(out), N, S, groups, eps, silu != 0,
                           static_cast<cudaStream_t>(stream));
+}
+
+int ddpm_attention(const void* qkv, void* out, int N, int T, int C, int heads, float scale, int impl, void* stream) {
+    if (!qkv || !out) { ddpm::set_error("ddpm_attention: null argument"); return 2; }
+    if (impl == 0 && ddpm::attention_tc_supported(T, C, heads)) {
+        ddpm::AttnTcLaunch l;
+        int rc = ddpm::attention_tc_prepare(static_cast<const __half*>(qkv), static_cast<__half*>(out), N, T, C, heads,
+                                            scale, &l);
+        if (rc) return rc;
+        return ddpm::attention_tc_launch(l, static_cast<cudaStream_t>(stream));
+    }
+    return ddpm::attention_core(static_cast<const __half*>(qkv), static_cast<__half*>(out), N, T, C, heads, scale,
+                                static_cast<cudaStream_t>(stream));
 }
 
 int ddpm_pack_conv_weight(const float* w, int Cout, int Cin, int taps, void* dst, long long ktot, long long koff,

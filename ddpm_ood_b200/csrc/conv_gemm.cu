@@ -362,11 +362,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode() {
+PFN_encodeTiled get_encode() {
     static PFN_encodeTiled fn = nullptr;
     if (!fn) {
         void* ptr = nullptr;

@@ -108,6 +108,12 @@ int conv_stats_parts(int spatial_dims, int Dout, int Hout, int Wout);
 int conv_prepare(const ConvProblem& prob, int num_sms, ConvLaunch* out);
 int conv_launch(const ConvLaunch& l, cudaStream_t stream);
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency); null + error if absent.
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode();
+
 void set_error(const char* fmt, ...);
 const char* last_error();
 

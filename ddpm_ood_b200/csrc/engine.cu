@@ -165,6 +165,7 @@ int UNet::init() {
     fuse_gn_stats_ = c.norm_num_groups > 0;
     for (int i = 0; i < c.num_levels && fuse_gn_stats_; ++i)
         fuse_gn_stats_ = (c.num_channels[i] % c.norm_num_groups == 0) && ((c.num_channels[i] / c.norm_num_groups) % 4 == 0);
+    if (const char* e = getenv("DDPM_ATTN_TC")) use_attn_tc_ = atoi(e) != 0;  // A/B switch for tests
     if (const char* e = getenv("DDPM_FUSE_GN")) fuse_gn_stats_ = fuse_gn_stats_ && atoi(e) != 0;  // A/B switch for tests
     in_gemm_ = (c.in_channels % 64 == 0);
     out_gemm_ = (c.out_channels % 128 == 0);
@@ -524,6 +525,11 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
                 op.src0 = qkv; op.dst = hB; op.T = static_cast<int>(h.S()); op.C = a.C; op.heads = a.heads;
                 op.scale = 1.0f / sqrtf(static_cast<float>(a.C) / static_cast<float>(a.heads));
                 op.flops = 4.0 * N * static_cast<double>(h.S()) * static_cast<double>(h.S()) * a.C;
+                op.attn_tc = !dry && use_attn_tc_ && attention_tc_supported(op.T, op.C, op.heads);
+                if (op.attn_tc) {
+                    int r = attention_tc_prepare(qkv, hB, N, op.T, op.C, op.heads, op.scale, &op.attn);
+                    if (r && !rc) rc = r;
+                }
                 plan.ops.push_back(op);
             }
             Act out = measure ? shape_act(a.C, h.D, h.H, h.W) : new_act(a.C, h.D, h.H, h.W);
@@ -738,7 +744,8 @@ int UNet::forward(const float* x, const long long* timesteps, int t_uniform, flo
                 rc = conv_launch(op.conv, stream);
                 break;
             case Op::ATTN:
-                rc = attention_core(op.src0, op.dst, N, op.T, op.C, op.heads, op.scale, stream);
+                rc = op.attn_tc ? attention_tc_launch(op.attn, stream)
+                                : attention_core(op.src0, op.dst, N, op.T, op.C, op.heads, op.scale, stream);
                 break;
             case Op::UPSAMPLE:
                 rc = upsample_nearest2(op.src0, op.dst, N, op.D, op.H, op.W, op.C, c.spatial_dims, stream);

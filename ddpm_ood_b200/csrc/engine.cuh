@@ -11,6 +11,7 @@
 #include <tuple>
 #include <vector>
 
+#include "attention.cuh"
 #include "conv_gemm.cuh"
 #include "kernels.cuh"
 
@@ -85,6 +86,8 @@ struct Op {
     // ATTN
     int T, C, heads;
     float scale;
+    bool attn_tc;       // tcgen05 kernel (attention.cu) instead of the generic CUDA-core one
+    AttnTcLaunch attn;
     // UPSAMPLE
     int D, H, W;
     // profiling: algorithmic FLOPs (2 per MAC, real rows only) for GEMM-type ops, algorithmic bytes otherwise
@@ -167,6 +170,7 @@ class UNet {
     float *conv_out_w_ = nullptr, *conv_out_b_ = nullptr;
     __half* conv_out_wp_ = nullptr;
     bool in_gemm_, out_gemm_;
+    bool use_attn_tc_ = true;
     bool fuse_gn_stats_ = true;  // GroupNorm statistics from the producers' epilogues (cpg % 4 == 0 required)
     // arenas
     size_t f32_count_ = 0, f16_count_ = 0, f32_used_ = 0, f16_used_ = 0;

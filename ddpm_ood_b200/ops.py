@@ -120,3 +120,13 @@ def gn_apply(src0: torch.Tensor, st0: torch.Tensor, src1: Optional[torch.Tensor]
                               0 if st1 is None else st1.shape[1], gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), n, s,
                               groups, eps, int(silu), current_stream_ptr()), "ddpm_gn_apply")
     return out
+
+
+def attention(qkv: torch.Tensor, n: int, t: int, heads: int, scale: float, impl: int = 0) -> torch.Tensor:
+    """qkv: fp16 [n*t, 3C] (q | k | v); returns fp16 [n*t, C] = softmax(q k^T * scale) v per (image, head)."""
+    assert qkv.dtype == torch.float16 and qkv.is_contiguous() and qkv.shape[0] == n * t
+    c = qkv.shape[1] // 3
+    out = torch.empty((n * t, c), dtype=torch.float16, device=qkv.device)
+    check(lib().ddpm_attention(qkv.data_ptr(), out.data_ptr(), n, t, c, heads, scale, impl, current_stream_ptr()),
+          "ddpm_attention")
+    return out

@@ -76,6 +76,12 @@ DDPM_API int ddpm_gn_apply(const void* src0, int C0, const float* st0, int parts
                            const float* st1, int parts1, const float* gamma, const float* beta, void* out, int N, int S,
                            int groups, float eps, int silu, void* stream);
 
+/* Attention core of monai-generative's AttentionBlock (one head = 256 channels): out = softmax(q k^T * scale) v per
+ * (image, head). qkv: fp16 [N*T, 3C] rows = tokens, columns q | k | v; out: fp16 [N*T, C].
+ * impl: 0 = pick (tcgen05 kernel when 128 % T == 0 or T == 256, else the generic kernel), 1 = force generic. */
+DDPM_API int ddpm_attention(const void* qkv, void* out, int N, int T, int C, int heads, float scale, int impl,
+                            void* stream);
+
 /* fp32 PyTorch conv weight [Cout][Cin][taps] (or Linear weight with taps == 1) -> fp16 rows of a packed matrix:
  * dst[co * ktot + koff + tap * Cin + ci]. */
 DDPM_API int ddpm_pack_conv_weight(const float* w, int Cout, int Cin, int taps, void* dst, long long ktot, long long koff,
