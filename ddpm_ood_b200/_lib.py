@@ -36,6 +36,7 @@ class ConvArgs(C.Structure):
         ("group", C.c_int),
         ("vt_col0", C.c_int),
         ("out_vt", C.c_void_p),
+        ("upsample2", C.c_int),
         ("stats_out", C.c_void_p),
     ]
 
@@ -98,6 +99,7 @@ SIGNATURES = {
     "ddpm_gn_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                 C.c_void_p]),
+    "ddpm_pack_upconv_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ddpm_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                  C.c_void_p]),
     "ddpm_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong,

@@ -39,6 +39,46 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, i
     }
 }
 
+// Sub-pixel phase weights of conv3x3(nearest_upsample_x2(.)): dst[phase][co][tap2][ci] (fp16) where per dim a phase
+// bit p and a tap bit a select the 3-tap subset {0} / {1,2} (p = 0) or {0,1} / {2} (p = 1); members are summed in fp32.
+__global__ void pack_upconv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int dims,
+                                          __half* __restrict__ dst) {
+    const int phases = 1 << dims, taps2 = 1 << dims;
+    int taps3 = 1;
+    for (int i = 0; i < dims; ++i) taps3 *= 3;
+    const long long total = static_cast<long long>(phases) * Cout * taps2 * Cin;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ci = static_cast<int>(i % Cin);
+        long long r = i / Cin;
+        const int tap2 = static_cast<int>(r % taps2); r /= taps2;
+        const int co = static_cast<int>(r % Cout);
+        const int phase = static_cast<int>(r / Cout);
+        const float* wp = w + (static_cast<long long>(co) * Cin + ci) * taps3;
+        // per dim (0 = w fastest): range of 3-tap indices
+        int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+        for (int d = 0; d < dims; ++d) {
+            const int pb = (phase >> d) & 1, a = (tap2 >> d) & 1;
+            if (pb == 0) { lo[d] = a ? 1 : 0; hi[d] = a ? 2 : 0; }
+            else         { lo[d] = a ? 2 : 0; hi[d] = a ? 2 : 1; }
+        }
+        float acc = 0.f;
+        for (int td = lo[2]; td <= hi[2]; ++td)
+            for (int th = lo[1]; th <= hi[1]; ++th)
+                for (int tw = lo[0]; tw <= hi[0]; ++tw) acc += wp[(td * 3 + th) * 3 + tw];
+        dst[i] = __float2half_rn(acc);
+    }
+}
+
+int pack_upconv_weight(const float* w, int Cout, int Cin, int dims, __half* dst, cudaStream_t stream) {
+    const long long total = (1LL << (2 * dims)) * Cout * Cin;
+    int blocks = static_cast<int>((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
+    pack_upconv_weight_kernel<<<blocks, 256, 0, stream>>>(w, Cout, Cin, dims, dst);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("pack_upconv_weight: %s", cudaGetErrorString(e)); return 5; }
+    return 0;
+}
+
 }  // namespace ddpm
 
 extern "C" {
@@ -73,6 +113,7 @@ int ddpm_conv_forward(const ddpm_conv_args* a, void* stream) {
     q.vt_col0 = a->vt_col0;
     q.out_vt = a->out_vt;
     q.stats_out = a->stats_out;
+    q.upsample2 = a->upsample2;
     ddpm::ConvLaunch l;
     int rc = ddpm::conv_prepare(q, ddpm::num_sms(), &l);
     if (rc) return rc;
@@ -94,6 +135,11 @@ int ddpm_gn_apply(const void* src0, int C0, const float* st0, int parts0, const 
     return ddpm::gn_apply(static_cast<const __half*>(src0), C0, st0, parts0, static_cast<const __half*>(src1), C1, st1,
                           parts1, gamma, beta, static_cast<__half*>(out), N, S, groups, eps, silu != 0,
                           static_cast<cudaStream_t>(stream));
+}
+
+int ddpm_pack_upconv_weight(const float* w, int Cout, int Cin, int spatial_dims, void* dst, void* stream) {
+    if (!w || !dst || (spatial_dims != 2 && spatial_dims != 3)) { ddpm::set_error("ddpm_pack_upconv_weight: bad argument"); return 2; }
+    return ddpm::pack_upconv_weight(w, Cout, Cin, spatial_dims, static_cast<__half*>(dst), static_cast<cudaStream_t>(stream));
 }
 
 int ddpm_attention(const void* qkv, void* out, int N, int T, int C, int heads, float scale, int impl, void* stream) {

@@ -75,8 +75,8 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_m_groups = (p.num_m_tiles + MT - 1) / MT;  // a work item = MT consecutive M tiles x one N tile
-    const int total_tiles = num_m_groups * p.num_n_tiles;
+    const int gpp = (p.num_m_tiles + MT - 1) / MT;  // a work item = MT consecutive M tiles (of one phase) x one N tile
+    const int total_tiles = gpp * p.num_phases * p.num_n_tiles;
 
     if (warp == 0) {
         // ================================================================= TMA producer (one thread)
@@ -84,8 +84,12 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m_group = tile / p.num_n_tiles;
-                const int n_tile = tile - m_group * p.num_n_tiles;
+                const int g = tile / p.num_n_tiles;
+                const int n_tile = tile - g * p.num_n_tiles;
+                const int sub = g / gpp;  // sub-pixel phase
+                const int m_group = g - sub * gpp;
+                const bool phased = p.num_phases > 1;
+                const int pofw = (sub & 1) - 1, pofh = ((sub >> 1) & 1) - 1, pofd = p.phase3d ? ((sub >> 2) & 1) - 1 : 0;
                 int w0[MT], h0[MT], d0[MT], n0[MT];
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
@@ -98,7 +102,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
                     d0[mt] = td * p.bd * (p.D > 1 ? p.stride : 1);
                     n0[mt] = t * p.bn;
                 }
-                const int brow = n_tile * BN + m_group * p.b_rows_per_mtile;
+                const int brow = n_tile * BN + m_group * p.b_rows_per_mtile + sub * p.Cout;
                 int seg = 0, seg_begin = 0;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     while (kb >= p.seg_kb_end[seg]) { seg_begin = p.seg_kb_end[seg]; ++seg; }
@@ -116,8 +120,9 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt)
                         ptx::tma_load_5d(smem_a + (stage * MT + mt) * C::kABytes, ma, &full_bar[stage], chunk * kBlockK,
-                                         w0[mt] + iw - (kw >> 1), h0[mt] + ih - (kh >> 1), d0[mt] + id - (kd >> 1),
-                                         n0[mt]);
+                                         w0[mt] + iw + (phased ? pofw : -(kw >> 1)),
+                                         h0[mt] + ih + (phased ? pofh : -(kh >> 1)),
+                                         d0[mt] + id + (phased ? pofd : -(kd >> 1)), n0[mt]);
                     ptx::tma_load_2d(smem_b + stage * C::kBBytes, &p.tmB, &full_bar[stage], kb * kBlockK, brow);
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
@@ -163,8 +168,10 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_group = tile / p.num_n_tiles;
-            const int n_tile = tile - m_group * p.num_n_tiles;
+            const int g = tile / p.num_n_tiles;
+            const int n_tile = tile - g * p.num_n_tiles;
+            const int sub = g / gpp;  // sub-pixel phase
+            const int m_group = g - sub * gpp;
             ptx::mbar_wait(&tfull_bar[as], aphase);
             ptx::tc_fence_after();
 #pragma unroll 1
@@ -181,7 +188,15 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
             const int d = td * p.bd + r % p.bd; r /= p.bd;
             const int n = tn * p.bn + r;
             const bool valid = (w < p.W) && (h < p.H) && (d < p.D) && (n < p.N);
-            const size_t pix = ((static_cast<size_t>(n) * p.D + d) * p.H + h) * p.W + w;
+            size_t pix;
+            if (p.num_phases > 1) {  // sub-pixel scatter into the doubled output grid
+                const int od = p.phase3d ? 2 * d + ((sub >> 2) & 1) : d;
+                const int Do = p.phase3d ? 2 * p.D : p.D;
+                pix = ((static_cast<size_t>(n) * Do + od) * (2 * p.H) + (2 * h + ((sub >> 1) & 1))) * (2 * p.W) +
+                      (2 * w + (sub & 1));
+            } else {
+                pix = ((static_cast<size_t>(n) * p.D + d) * p.H + h) * p.W + w;
+            }
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * C::kAccCols + mt * BN;
 
             if (p.mode == EPI_SOFTMAX_BD) {
@@ -246,7 +261,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
                     const int n_w = tn * p.bn + (q * 32) / R;
                     if (n_w < p.N) {
                         const int tile_sp = (td * p.tiles_h + th) * p.tiles_w + tw;
-                        const int part = tile_sp * (R >> 5) + ((q * 32) % R) / 32;
+                        const int part = sub * (p.stats_parts / p.num_phases) + tile_sp * (R >> 5) + ((q * 32) % R) / 32;
                         st_base = p.stats_out + (static_cast<size_t>(n_w) * p.stats_parts + part) * (p.Cout >> 1);
                     }
                 }
@@ -412,6 +427,11 @@ int conv_prepare(const ConvProblem& q, int num_sms, ConvLaunch* out) {
     ConvGemmParams& p = out->p;
     if (q.n_seg < 1 || q.n_seg > kMaxSeg) { set_error("conv: n_seg=%d out of range", q.n_seg); return 2; }
     if (q.stride != 1 && q.stride != 2) { set_error("conv: stride %d unsupported", q.stride); return 2; }
+    if (q.upsample2 && (q.n_seg != 1 || q.seg[0].ksize != 2 || q.stride != 1 || q.mode != EPI_STORE || q.residual ||
+                        q.b_rows_per_mtile)) {
+        set_error("conv: upsample2 needs one 2x2 segment, stride 1, store epilogue, no residual");
+        return 2;
+    }
     const int sd = q.spatial_dims;
     if (sd != 2 && sd != 3) { set_error("conv: spatial_dims %d unsupported", sd); return 2; }
     if (sd == 2 && q.D != 1) { set_error("conv: 2-D problem needs D == 1"); return 2; }
@@ -443,13 +463,15 @@ int conv_prepare(const ConvProblem& q, int num_sms, ConvLaunch* out) {
     p.group = q.group;
     p.vt_col0 = q.vt_col0;
     p.out_vt = static_cast<__half*>(q.out_vt);
+    p.num_phases = q.upsample2 ? (sd == 3 ? 8 : 4) : 1;
+    p.phase3d = (q.upsample2 && sd == 3) ? 1 : 0;
     p.stats_out = nullptr;
     p.stats_parts = 0;
     if (q.stats_out) {
         const int R = p.bw * p.bh * p.bd;
         if (q.mode != EPI_STORE || R < 32) { set_error("conv: fused GroupNorm statistics unsupported for this shape/mode"); return 2; }
         p.stats_out = q.stats_out;
-        p.stats_parts = p.tiles_w * p.tiles_h * p.tiles_d * (R / 32);
+        p.stats_parts = p.tiles_w * p.tiles_h * p.tiles_d * (R / 32) * p.num_phases;
     }
     if (q.mode == EPI_SOFTMAX_BD && p.num_n_tiles != 1) { set_error("conv: softmax epilogue needs one N tile"); return 2; }
 
@@ -459,7 +481,7 @@ int conv_prepare(const ConvProblem& q, int num_sms, ConvLaunch* out) {
     for (int s = 0; s < q.n_seg; ++s) {
         const ConvSegment& g = q.seg[s];
         if (g.channels % kBlockK != 0) { set_error("conv: segment channels %d not a multiple of 64", g.channels); return 2; }
-        if (g.ksize != 1 && g.ksize != 3) { set_error("conv: ksize %d unsupported", g.ksize); return 2; }
+        if (g.ksize != 1 && g.ksize != 3 && !(g.ksize == 2 && q.upsample2)) { set_error("conv: ksize %d unsupported", g.ksize); return 2; }
         p.seg_chunks[s] = g.channels / kBlockK;
         p.seg_kw[s] = g.ksize;
         p.seg_kh[s] = g.ksize;
@@ -500,10 +522,11 @@ int conv_prepare(const ConvProblem& q, int num_sms, ConvLaunch* out) {
     }
     // Pair M tiles (MT = 2) for 128-wide outputs when there is enough work to keep every SM busy with pairs.
     out->m_tiles_per_cta = 1;
-    if (BN == 128 && q.b_rows_per_mtile == 0 && q.mode == EPI_STORE && p.num_m_tiles * p.num_n_tiles >= 2 * num_sms)
+    if (BN == 128 && q.b_rows_per_mtile == 0 && q.mode == EPI_STORE &&
+        p.num_m_tiles * p.num_n_tiles * p.num_phases >= 2 * num_sms)
         out->m_tiles_per_cta = 2;
     const int groups = (p.num_m_tiles + out->m_tiles_per_cta - 1) / out->m_tiles_per_cta;
-    const int total = groups * p.num_n_tiles;
+    const int total = groups * p.num_phases * p.num_n_tiles;
     out->grid = total < num_sms ? total : num_sms;
     return 0;
 }

@@ -61,6 +61,11 @@ struct ConvGemmParams {
     // [N][stats_parts][Cout/4][2] fp32. Summed in a fixed order: bitwise reproducible.
     float* stats_out;
     int stats_parts;
+    // Nearest-x2-upsample + 3x3(x3) conv as 2^dims sub-pixel phases: phase (pd, ph, pw) is a 2x2(x2) conv over the
+    // LOW-resolution input at tap offsets {p-1, p} per dim with pre-summed weights (rows [phase][Cout] of B), scattered
+    // to output pixel 2*x + p. num_phases == 1: ordinary conv.
+    int num_phases;
+    int phase3d;
 };
 
 // Host side: filled by conv_prepare(), launched by conv_launch().
@@ -74,7 +79,7 @@ struct ConvLaunch {
 struct ConvSegment {
     const void* ptr;  // NDHWC fp16
     int channels;     // multiple of 64
-    int ksize;        // 1 or 3 (per spatial dim)
+    int ksize;        // 1 or 3 (per spatial dim); 2 only with ConvProblem::upsample2
 };
 
 struct ConvProblem {
@@ -98,11 +103,18 @@ struct ConvProblem {
     int vt_col0;
     void* out_vt;
     float* stats_out;  // or null; must hold N * conv_stats_parts(...) * Cout/4 * 2 floats
+    // 1: the op is conv3x3(nearest_upsample_x2(input)); N,D,H,W are the LOW-resolution input extents, seg[0].ksize
+    // is 2, weights are phase-packed [2^dims * Cout][2^dims * C] (pack_upconv_weight), out has the doubled extents and
+    // statistics come in 2^dims * conv_stats_parts(low-res extents) parts.
+    int upsample2;
 };
 
 // Number of GroupNorm-statistics parts per image the epilogue emits for an OUTPUT of this geometry (0: the tile box
 // holds fewer than 32 pixels of an image, fused statistics unsupported).
 int conv_stats_parts(int spatial_dims, int Dout, int Hout, int Wout);
+
+// fp32 [Cout][Cin][3^dims] -> fp16 [2^dims phases][Cout][2^dims taps][Cin] (api.cu)
+int pack_upconv_weight(const float* w, int Cout, int Cin, int dims, __half* dst, cudaStream_t stream);
 
 // returns 0 on success; on failure sets the thread-local error string (see ddpm_last_error()).
 int conv_prepare(const ConvProblem& prob, int num_sms, ConvLaunch* out);

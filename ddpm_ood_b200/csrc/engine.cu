@@ -165,6 +165,7 @@ int UNet::init() {
     fuse_gn_stats_ = c.norm_num_groups > 0;
     for (int i = 0; i < c.num_levels && fuse_gn_stats_; ++i)
         fuse_gn_stats_ = (c.num_channels[i] % c.norm_num_groups == 0) && ((c.num_channels[i] / c.norm_num_groups) % 4 == 0);
+    if (const char* e = getenv("DDPM_UPCONV_PHASES")) upconv_phases_ = atoi(e) != 0;  // A/B switch for tests
     if (const char* e = getenv("DDPM_ATTN_TC")) use_attn_tc_ = atoi(e) != 0;  // A/B switch for tests
     if (const char* e = getenv("DDPM_FUSE_GN")) fuse_gn_stats_ = fuse_gn_stats_ && atoi(e) != 0;  // A/B switch for tests
     in_gemm_ = (c.in_channels % 64 == 0);
@@ -270,9 +271,16 @@ int UNet::init() {
             if (L.has_samp) {
                 L.samp.C = oc;
                 L.samp.w = arena_alloc<__half>(static_cast<size_t>(oc) * taps * oc, true);
+                const int ph = 1 << c.spatial_dims;
+                L.samp.w_up = arena_alloc<__half>(static_cast<size_t>(ph) * oc * ph * oc, true);
                 L.samp.bias = arena_alloc<float>(oc, false);
                 const std::string pre = "up_blocks." + std::to_string(i) + ".upsampler.conv.conv";
                 add_pack(pre + ".weight", L.samp.w, oc, oc, taps, static_cast<long long>(taps) * oc, 0);
+                if (!sizing_) {
+                    ParamSlot& sl = slots_[pre + ".weight"];
+                    sl.kind = ParamSlot::PACK_UPCONV;
+                    sl.dst2 = L.samp.w_up;
+                }
                 add_copy(pre + ".bias", L.samp.bias, oc);
             }
             up_.push_back(std::move(L));
@@ -315,6 +323,10 @@ int UNet::set_param(const char* name, const float* data, long long numel, cudaSt
                                                                                static_cast<__half*>(s.dst), s.ktot, s.koff);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { set_error("unet: pack of '%s' failed: %s", name, cudaGetErrorString(e)); return 5; }
+        if (s.kind == ParamSlot::PACK_UPCONV) {
+            int rc = pack_upconv_weight(data, s.Cout, s.Cin, cfg_.spatial_dims, static_cast<__half*>(s.dst2), stream);
+            if (rc) return rc;
+        }
     }
     s.set = true;
     finalized_ = false;
@@ -357,10 +369,11 @@ static double conv_flops(const ConvProblem& q) {
     const double Do = sd3 ? (q.D + q.stride - 1) / q.stride : q.D;
     double k = 0;
     for (int s = 0; s < q.n_seg; ++s) {
-        const int taps = q.seg[s].ksize == 3 ? (sd3 ? 27 : 9) : 1;
+        const int taps = q.seg[s].ksize == 3 ? (sd3 ? 27 : 9) : (q.seg[s].ksize == 2 ? (sd3 ? 8 : 4) : 1);
         k += static_cast<double>(taps) * q.seg[s].channels;
     }
-    return 2.0 * q.N * Do * Ho * Wo * q.Cout * k;
+    const double phases = q.upsample2 ? (sd3 ? 8 : 4) : 1;  // executed MACs (4/9 resp. 8/27 of the reference op's)
+    return 2.0 * q.N * Do * Ho * Wo * phases * q.Cout * k;
 }
 
 struct UNet::Layout {
@@ -596,19 +609,44 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             }
             if (L.has_samp) {
                 const int fd = sd == 3 ? 2 : 1;
-                const size_t cnt = static_cast<size_t>(N) * (h.D * fd) * (h.H * 2) * (h.W * 2) * h.C;
-                if (measure && cnt > max_up) max_up = cnt;
-                Act up = measure ? shape_act(h.C, h.D * fd, h.H * 2, h.W * 2) : new_act(h.C, h.D * fd, h.H * 2, h.W * 2, false);
-                if (!measure) {
-                    Op op{};
-                    op.type = Op::UPSAMPLE;
-                    op.src0 = h.p; op.dst = up.p; op.D = h.D; op.H = h.H; op.W = h.W; op.C = h.C;
-                    op.bytes = 2.0 * cnt + 2.0 * cnt / (4.0 * fd);
-                    plan.ops.push_back(op);
+                if (upconv_phases_) {
+                    // nearest x2 + 3x3 conv == 2^d sub-pixel 2x2 convs over the low-res tensor (no upsampled tensor)
+                    Act o = shape_act(h.C, h.D * fd, h.H * 2, h.W * 2);
+                    if (!measure) {
+                        o = new_act(h.C, h.D * fd, h.H * 2, h.W * 2, false);
+                        if (fuse_gn_stats_) {
+                            o.parts = conv_stats_parts(sd, h.D, h.H, h.W) * (1 << sd);
+                            o.stats = take_stats(h.C, o.parts);
+                        }
+                    }
+                    ConvProblem q{};
+                    q.spatial_dims = sd;
+                    q.N = N; q.D = h.D; q.H = h.H; q.W = h.W;
+                    q.stride = 1;
+                    q.n_seg = 1;
+                    q.seg[0] = {h.p, h.C, 2};
+                    q.weights = L.samp.w_up; q.w_rows = (1 << sd) * h.C; q.Cout = h.C;
+                    q.mode = EPI_STORE;
+                    q.bias = L.samp.bias; q.out = o.p;
+                    q.stats_out = o.stats;
+                    q.upsample2 = 1;
+                    gemm(q, -1);
+                    h = o;
+                } else {
+                    const size_t cnt = static_cast<size_t>(N) * (h.D * fd) * (h.H * 2) * (h.W * 2) * h.C;
+                    if (measure && cnt > max_up) max_up = cnt;
+                    Act up = measure ? shape_act(h.C, h.D * fd, h.H * 2, h.W * 2) : new_act(h.C, h.D * fd, h.H * 2, h.W * 2, false);
+                    if (!measure) {
+                        Op op{};
+                        op.type = Op::UPSAMPLE;
+                        op.src0 = h.p; op.dst = up.p; op.D = h.D; op.H = h.H; op.W = h.W; op.C = h.C;
+                        op.bytes = 2.0 * cnt + 2.0 * cnt / (4.0 * fd);
+                        plan.ops.push_back(op);
+                    }
+                    Act o = measure ? up : new_act(h.C, up.D, up.H, up.W);
+                    conv3(up, up.p, h.C, L.samp.w, L.samp.bias, h.C, 1, -1, nullptr, o.p, nullptr, nullptr, o.stats);
+                    h = o;
                 }
-                Act o = measure ? up : new_act(h.C, up.D, up.H, up.W);
-                conv3(up, up.p, h.C, L.samp.w, L.samp.bias, h.C, 1, -1, nullptr, o.p, nullptr, nullptr, o.stats);
-                h = o;
             }
         }
         if (h.D != D || h.H != H || h.W != W) { set_error("unet: output spatial size mismatch"); return 7; }

@@ -55,11 +55,13 @@ struct AttnW {
 struct SampW {  // down / up sampler conv
     int C;
     __half* w;
+    __half* w_up;  // up sampler only: sub-pixel phase weights [2^d * C][2^d * C]
     float* bias;
 };
 
 struct ParamSlot {
-    enum Kind { COPY_F32, PACK_CONV } kind;
+    enum Kind { COPY_F32, PACK_CONV, PACK_UPCONV } kind;
+    void* dst2;          // PACK_UPCONV: phase-packed destination (dst keeps the plain 3x3 packing)
     void* dst;
     long long numel;     // expected element count of the source tensor
     int Cout, Cin, taps; // PACK_CONV
@@ -171,6 +173,7 @@ class UNet {
     __half* conv_out_wp_ = nullptr;
     bool in_gemm_, out_gemm_;
     bool use_attn_tc_ = true;
+    bool upconv_phases_ = true;  // nearest-x2 + conv as sub-pixel 2x2 convs (4/9 of the MACs, no upsampled tensor)
     bool fuse_gn_stats_ = true;  // GroupNorm statistics from the producers' epilogues (cpg % 4 == 0 required)
     // arenas
     size_t f32_count_ = 0, f16_count_ = 0, f32_used_ = 0, f16_used_ = 0;

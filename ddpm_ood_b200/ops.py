@@ -48,6 +48,7 @@ def conv_forward(
     vt_col0: int = 0,
     out_vt: Optional[torch.Tensor] = None,
     stats_out: Optional[torch.Tensor] = None,
+    upsample2: bool = False,
 ) -> torch.Tensor:
     """segs: fp16 channels-last tensors [N, (D,) H, W, C]; weights: packed fp16 [rows, Ktot]."""
     x0 = segs[0]
@@ -76,7 +77,8 @@ def conv_forward(
     a.bias = _ptr(bias)
     a.chan_add = _ptr(chan_add)
     a.residual = _ptr(residual)
-    so = lambda v: (v + stride - 1) // stride  # noqa: E731
+    a.upsample2 = int(upsample2)
+    so = (lambda v: 2 * v) if upsample2 else (lambda v: (v + stride - 1) // stride)  # noqa: E731
     if out is None:
         shape = (n, so(h), so(w), cout) if sd == 2 else (n, so(d), so(h), so(w), cout)
         out = torch.empty(shape, dtype=torch.float16, device=x0.device)
@@ -130,3 +132,14 @@ def attention(qkv: torch.Tensor, n: int, t: int, heads: int, scale: float, impl:
     check(lib().ddpm_attention(qkv.data_ptr(), out.data_ptr(), n, t, c, heads, scale, impl, current_stream_ptr()),
           "ddpm_attention")
     return out
+
+
+def pack_upconv_weight(w: torch.Tensor) -> torch.Tensor:
+    """w: fp32 [Cout, Cin, 3(,3),3] -> fp16 [2^d * Cout, 2^d * Cin] sub-pixel phase weights for conv_forward(upsample2=True)."""
+    assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
+    sd = w.dim() - 2
+    cout, cin = w.shape[0], w.shape[1]
+    dst = torch.empty(((1 << sd) * cout, (1 << sd) * cin), dtype=torch.float16, device=w.device)
+    check(lib().ddpm_pack_upconv_weight(w.data_ptr(), cout, cin, sd, dst.data_ptr(), current_stream_ptr()),
+          "ddpm_pack_upconv_weight")
+    return dst

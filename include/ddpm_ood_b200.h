@@ -57,6 +57,9 @@ typedef struct ddpm_conv_args {
     int group;               /* mode 1: tokens per image */
     int vt_col0;             /* mode 2 */
     void* out_vt;            /* mode 2 */
+    int upsample2;           /* 1: out = conv3x3(nearest_upsample_x2(input)) computed as 2^dims sub-pixel 2x2 convs over the
+                                low-resolution input (N,D,H,W = low-res extents, one segment with ksize 2, weights from
+                                ddpm_pack_upconv_weight); the Upsample block of DiffusionModelUNet. 4/9 (8/27) of the MACs. */
     float* stats_out;        /* mode 0, optional: GroupNorm partial statistics of the fp16-rounded output,
                                 [N][ddpm_conv_stats_parts()][Cout/4][2] fp32 = (sum, sum of squares) per 4-channel quad
                                 and 32-pixel part of an image; consumed by ddpm_gn_apply() */
@@ -75,6 +78,9 @@ DDPM_API int ddpm_gn_silu(const void* src0, int C0, const void* src1, int C1, co
 DDPM_API int ddpm_gn_apply(const void* src0, int C0, const float* st0, int parts0, const void* src1, int C1,
                            const float* st1, int parts1, const float* gamma, const float* beta, void* out, int N, int S,
                            int groups, float eps, int silu, void* stream);
+
+/* fp32 conv weight [Cout][Cin][3^dims] -> fp16 sub-pixel phase weights [2^dims * Cout][2^dims * Cin] for upsample2. */
+DDPM_API int ddpm_pack_upconv_weight(const float* w, int Cout, int Cin, int spatial_dims, void* dst, void* stream);
 
 /* Attention core of monai-generative's AttentionBlock (one head = 256 channels): out = softmax(q k^T * scale) v per
  * (image, head). qkv: fp16 [N*T, 3C] rows = tokens, columns q | k | v; out: fp16 [N*T, C].

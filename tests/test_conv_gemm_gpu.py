@@ -102,3 +102,47 @@ if __name__ == "__main__":
             print(f"{name:40s} rel_l2={rel:.3e} max={mx:.3e}", flush=True)
         except Exception as e:  # noqa: BLE001
             print(f"{name:40s} EXC {type(e).__name__}: {e}", flush=True)
+
+
+UP_CASES = {
+    "up2d_8to16_256": dict(sd=2, n=5, sp=(8, 8), c=256),
+    "up2d_16to32_256_paired": dict(sd=2, n=6, sp=(16, 16), c=256),
+    "up2d_14to28_128": dict(sd=2, n=3, sp=(14, 14), c=128),
+    "up2d_7to14_256": dict(sd=2, n=3, sp=(7, 7), c=256),
+    "up2d_16to32_128_many": dict(sd=2, n=40, sp=(16, 16), c=128),
+    "up3d_4to8_128": dict(sd=3, n=2, sp=(4, 4, 4), c=128),
+}
+
+
+@pytest.mark.parametrize("name", list(UP_CASES))
+def test_upsample_conv_as_subpixel_phases(name):
+    """conv3x3(nearest_upsample_x2(x)) (the Upsample block of the UNet) computed as 2^d sub-pixel 2x2 convs over the
+    low-res input with pre-summed weights, against PyTorch's interpolate + conv on the same fp16 input. The phase
+    weights are sums of fp32 weights rounded once to fp16, so the comparison uses the fp32 weights on the torch side."""
+    from ddpm_ood_b200 import ops
+
+    case = UP_CASES[name]
+    sd, n, sp, c = case["sd"], case["n"], case["sp"], case["c"]
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn((n, c) + tuple(sp), generator=g, device="cuda")
+    w = torch.randn((c, c) + (3,) * sd, generator=g, device="cuda") * (1.0 / (c * 3 ** sd) ** 0.5)
+    bias = torch.randn(c, generator=g, device="cuda")
+    x16 = _nhwc(x)
+    wp = ops.pack_upconv_weight(w.contiguous())
+    parts = ops.conv_stats_parts(sd, 1 if sd == 2 else sp[0], sp[-2], sp[-1]) * (1 << sd)
+    st = torch.full((n, parts, c // 4, 2), float("nan"), device="cuda") if parts else None
+    out = ops.conv_forward([x16], [2], wp, c, bias=bias, upsample2=True, stats_out=st)
+    torch.cuda.synchronize()
+    conv = F.conv2d if sd == 2 else F.conv3d
+    ref = conv(F.interpolate(_to_ncx(x16), scale_factor=2, mode="nearest"), w, bias=bias, padding=1)
+    got = _to_ncx(out)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    rel = ((got - ref).norm() / ref.norm()).item()
+    mx = ((got - ref).abs().max() / ref.abs().max()).item()
+    assert rel < 8e-4, (name, rel, mx)   # fp16 rounding of the summed weights + fp16 output
+    assert mx < 4e-3, (name, rel, mx)
+    if st is not None:
+        assert torch.isfinite(st).all()
+        o = out.float().reshape(n, -1, c // 4, 4)
+        assert torch.allclose(st.sum(1)[..., 0], o.sum(dim=(1, 3)), rtol=1e-5, atol=1e-2)
+        assert torch.allclose(st.sum(1)[..., 1], (o * o).sum(dim=(1, 3)), rtol=1e-5, atol=1e-2)
