@@ -37,6 +37,7 @@ class ConvArgs(C.Structure):
         ("vt_col0", C.c_int),
         ("out_vt", C.c_void_p),
         ("upsample2", C.c_int),
+        ("impl", C.c_int),
         ("stats_out", C.c_void_p),
     ]
 

@@ -114,6 +114,7 @@ int ddpm_conv_forward(const ddpm_conv_args* a, void* stream) {
     q.out_vt = a->out_vt;
     q.stats_out = a->stats_out;
     q.upsample2 = a->upsample2;
+    q.impl = a->impl;
     ddpm::ConvLaunch l;
     int rc = ddpm::conv_prepare(q, ddpm::num_sms(), &l);
     if (rc) return rc;

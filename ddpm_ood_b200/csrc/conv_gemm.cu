@@ -3,6 +3,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ptx.cuh"
@@ -36,147 +37,13 @@ struct Cfg {
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
-template <int BN, int MT>
-__global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-    using C = Cfg<BN, MT>;
-    extern __shared__ uint8_t smem_raw[];
-    // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment.
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* smem_a = smem;                                  // [kStages][MT][16 KB]
-    uint8_t* smem_b = smem + C::kStages * MT * C::kABytes;   // [kStages][BN * 128 B]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
-    uint64_t* full_bar = bars;                     // [kStages]  TMA -> MMA
-    uint64_t* empty_bar = bars + C::kStages;       // [kStages]  MMA -> TMA
-    uint64_t* tfull_bar = bars + 2 * C::kStages;   // [2]        MMA -> epilogue
-    uint64_t* tempty_bar = tfull_bar + 2;          // [2]        epilogue -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+// Epilogue of one 128-pixel x BN-channel accumulator tile; executed by the 4 epilogue warps (q = TMEM lane quarter),
+// one output pixel (row) per thread. t_addr: TMEM address of the tile for this warp's lanes. sub: sub-pixel phase.
+template <int BN>
+__device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint32_t t_addr, int m_tile, int n_tile,
+                                                   int sub, int q, int lane) {
+            const int row = q * 32 + lane;
 
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-
-    if (warp == 0 && lane == 0) {
-        for (int s = 0; s < p.n_seg; ++s) ptx::prefetch_tmap(&p.tmA[s]);
-        ptx::prefetch_tmap(&p.tmB);
-    }
-    if (warp == 1 && lane == 0) {
-        for (int i = 0; i < C::kStages; ++i) {
-            ptx::mbar_init(&full_bar[i], 1);
-            ptx::mbar_init(&empty_bar[i], 1);
-        }
-        for (int i = 0; i < 2; ++i) {
-            ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
-        }
-        ptx::fence_mbar_init();
-    }
-    if (warp == 2) ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    const int gpp = (p.num_m_tiles + MT - 1) / MT;  // a work item = MT consecutive M tiles (of one phase) x one N tile
-    const int total_tiles = gpp * p.num_phases * p.num_n_tiles;
-
-    if (warp == 0) {
-        // ================================================================= TMA producer (one thread)
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int g = tile / p.num_n_tiles;
-                const int n_tile = tile - g * p.num_n_tiles;
-                const int sub = g / gpp;  // sub-pixel phase
-                const int m_group = g - sub * gpp;
-                const bool phased = p.num_phases > 1;
-                const int pofw = (sub & 1) - 1, pofh = ((sub >> 1) & 1) - 1, pofd = p.phase3d ? ((sub >> 2) & 1) - 1 : 0;
-                int w0[MT], h0[MT], d0[MT], n0[MT];
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    int t = m_group * MT + mt;  // may run one past the last tile: its box is all out-of-bounds (zeros)
-                    const int tw = t % p.tiles_w; t /= p.tiles_w;
-                    const int th = t % p.tiles_h; t /= p.tiles_h;
-                    const int td = t % p.tiles_d; t /= p.tiles_d;
-                    w0[mt] = tw * p.bw * p.stride;
-                    h0[mt] = th * p.bh * p.stride;
-                    d0[mt] = td * p.bd * (p.D > 1 ? p.stride : 1);
-                    n0[mt] = t * p.bn;
-                }
-                const int brow = n_tile * BN + m_group * p.b_rows_per_mtile + sub * p.Cout;
-                int seg = 0, seg_begin = 0;
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                    while (kb >= p.seg_kb_end[seg]) { seg_begin = p.seg_kb_end[seg]; ++seg; }
-                    const int local = kb - seg_begin;
-                    const int chunks = p.seg_chunks[seg];
-                    const int tap = local / chunks;
-                    const int chunk = local - tap * chunks;
-                    const int kw = p.seg_kw[seg], kh = p.seg_kh[seg], kd = p.seg_kd[seg];
-                    const int iw = tap % kw;
-                    const int ih = (tap / kw) % kh;
-                    const int id = tap / (kw * kh);
-                    const CUtensorMap* ma = seg == 0 ? &p.tmA[0] : (seg == 1 ? &p.tmA[1] : &p.tmA[2]);
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt)
-                        ptx::tma_load_5d(smem_a + (stage * MT + mt) * C::kABytes, ma, &full_bar[stage], chunk * kBlockK,
-                                         w0[mt] + iw + (phased ? pofw : -(kw >> 1)),
-                                         h0[mt] + ih + (phased ? pofh : -(kh >> 1)),
-                                         d0[mt] + id + (phased ? pofd : -(kd >> 1)), n0[mt]);
-                    ptx::tma_load_2d(smem_b + stage * C::kBBytes, &p.tmB, &full_bar[stage], kb * kBlockK, brow);
-                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ================================================================= MMA issuer (one thread)
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_f16(kBlockM, BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int as = 0;
-            uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
-                ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * C::kAccCols;
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                    ptx::mbar_wait(&full_bar[stage], phase);
-                    ptx::tc_fence_after();
-                    const uint64_t db = ptx::make_desc_k128(ptx::smem_u32(smem_b + stage * C::kBBytes));
-#pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-#pragma unroll
-                        for (int mt = 0; mt < MT; ++mt) {
-                            const uint64_t da =
-                                ptx::make_desc_k128(ptx::smem_u32(smem_a + (stage * MT + mt) * C::kABytes));
-                            // +32 bytes (>>4 = 2) per 16-element K step inside the 128B swizzle row
-                            ptx::umma_f16(d_tmem + mt * BN, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                        }
-                    }
-                    ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
-                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
-                }
-                ptx::umma_commit(&tfull_bar[as]);  // accumulator ready for the epilogue
-                if (++as == 2) { as = 0; aphase ^= 1; }
-            }
-        }
-    } else if (warp >= 4) {
-        // ================================================================= epilogue (4 warps, 1 row per thread)
-        const int q = warp - 4;  // TMEM lane quarter == warp % 4
-        const int row = q * 32 + lane;
-        int as = 0;
-        uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int g = tile / p.num_n_tiles;
-            const int n_tile = tile - g * p.num_n_tiles;
-            const int sub = g / gpp;  // sub-pixel phase
-            const int m_group = g - sub * gpp;
-            ptx::mbar_wait(&tfull_bar[as], aphase);
-            ptx::tc_fence_after();
-#pragma unroll 1
-            for (int mt = 0; mt < MT; ++mt) {
-            const int m_tile = m_group * MT + mt;
             int t = m_tile;
             const int tw = t % p.tiles_w; t /= p.tiles_w;
             const int th = t % p.tiles_h; t /= p.tiles_h;
@@ -197,7 +64,6 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
             } else {
                 pix = ((static_cast<size_t>(n) * p.D + d) * p.H + h) * p.W + w;
             }
-            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * C::kAccCols + mt * BN;
 
             if (p.mode == EPI_SOFTMAX_BD) {
                 // Attention probabilities. Row = query token; its keys are the `group` columns of its own image:
@@ -360,6 +226,149 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
                     }
                 }
             }
+}
+template <int BN, int MT>
+__global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+    using C = Cfg<BN, MT>;
+    extern __shared__ uint8_t smem_raw[];
+    // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment.
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;                                  // [kStages][MT][16 KB]
+    uint8_t* smem_b = smem + C::kStages * MT * C::kABytes;   // [kStages][BN * 128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+    uint64_t* full_bar = bars;                     // [kStages]  TMA -> MMA
+    uint64_t* empty_bar = bars + C::kStages;       // [kStages]  MMA -> TMA
+    uint64_t* tfull_bar = bars + 2 * C::kStages;   // [2]        MMA -> epilogue
+    uint64_t* tempty_bar = tfull_bar + 2;          // [2]        epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.n_seg; ++s) ptx::prefetch_tmap(&p.tmA[s]);
+        ptx::prefetch_tmap(&p.tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < C::kStages; ++i) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tfull_bar[i], 1);
+            ptx::mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int gpp = (p.num_m_tiles + MT - 1) / MT;  // a work item = MT consecutive M tiles (of one phase) x one N tile
+    const int total_tiles = gpp * p.num_phases * p.num_n_tiles;
+
+    if (warp == 0) {
+        // ================================================================= TMA producer (one thread)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int g = tile / p.num_n_tiles;
+                const int n_tile = tile - g * p.num_n_tiles;
+                const int sub = g / gpp;  // sub-pixel phase
+                const int m_group = g - sub * gpp;
+                const bool phased = p.num_phases > 1;
+                const int pofw = (sub & 1) - 1, pofh = ((sub >> 1) & 1) - 1, pofd = p.phase3d ? ((sub >> 2) & 1) - 1 : 0;
+                int w0[MT], h0[MT], d0[MT], n0[MT];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    int t = m_group * MT + mt;  // may run one past the last tile: its box is all out-of-bounds (zeros)
+                    const int tw = t % p.tiles_w; t /= p.tiles_w;
+                    const int th = t % p.tiles_h; t /= p.tiles_h;
+                    const int td = t % p.tiles_d; t /= p.tiles_d;
+                    w0[mt] = tw * p.bw * p.stride;
+                    h0[mt] = th * p.bh * p.stride;
+                    d0[mt] = td * p.bd * (p.D > 1 ? p.stride : 1);
+                    n0[mt] = t * p.bn;
+                }
+                const int brow = n_tile * BN + m_group * p.b_rows_per_mtile + sub * p.Cout;
+                int seg = 0, seg_begin = 0;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    while (kb >= p.seg_kb_end[seg]) { seg_begin = p.seg_kb_end[seg]; ++seg; }
+                    const int local = kb - seg_begin;
+                    const int chunks = p.seg_chunks[seg];
+                    const int tap = local / chunks;
+                    const int chunk = local - tap * chunks;
+                    const int kw = p.seg_kw[seg], kh = p.seg_kh[seg], kd = p.seg_kd[seg];
+                    const int iw = tap % kw;
+                    const int ih = (tap / kw) % kh;
+                    const int id = tap / (kw * kh);
+                    const CUtensorMap* ma = seg == 0 ? &p.tmA[0] : (seg == 1 ? &p.tmA[1] : &p.tmA[2]);
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+                        ptx::tma_load_5d(smem_a + (stage * MT + mt) * C::kABytes, ma, &full_bar[stage], chunk * kBlockK,
+                                         w0[mt] + iw + (phased ? pofw : -(kw >> 1)),
+                                         h0[mt] + ih + (phased ? pofh : -(kh >> 1)),
+                                         d0[mt] + id + (phased ? pofd : -(kd >> 1)), n0[mt]);
+                    ptx::tma_load_2d(smem_b + stage * C::kBBytes, &p.tmB, &full_bar[stage], kb * kBlockK, brow);
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_f16(kBlockM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * C::kAccCols;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint64_t db = ptx::make_desc_k128(ptx::smem_u32(smem_b + stage * C::kBBytes));
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const uint64_t da =
+                                ptx::make_desc_k128(ptx::smem_u32(smem_a + (stage * MT + mt) * C::kABytes));
+                            // +32 bytes (>>4 = 2) per 16-element K step inside the 128B swizzle row
+                            ptx::umma_f16(d_tmem + mt * BN, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        }
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(&tfull_bar[as]);  // accumulator ready for the epilogue
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================================================= epilogue (4 warps, 1 row per thread)
+        const int q = warp - 4;  // TMEM lane quarter == warp % 4
+        const int row = q * 32 + lane;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int g = tile / p.num_n_tiles;
+            const int n_tile = tile - g * p.num_n_tiles;
+            const int sub = g / gpp;  // sub-pixel phase
+            const int m_group = g - sub * gpp;
+            ptx::mbar_wait(&tfull_bar[as], aphase);
+            ptx::tc_fence_after();
+#pragma unroll 1
+            for (int mt = 0; mt < MT; ++mt) {
+            conv_epilogue_tile<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * C::kAccCols + mt * BN,
+                                   m_group * MT + mt, n_tile, sub, q, lane);
             }  // mt
             ptx::tc_fence_before();
             __syncwarp();
@@ -373,6 +382,183 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
     if (warp == 2) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ CTA-pair kernel
+// Same contract, run by clusters of two CTAs driving ONE tcgen05.mma.cta_group::2 stream (M = 256): each CTA stages
+// its own 128-pixel A tile(s) but only HALF of every weight tile, so the L2 -> SM traffic per MAC drops from
+// (16 + 32) KB to (16 + 16) KB per 128x256x64 block (BN = 256) - the feed, not the tensor pipe, bounds the single-CTA
+// kernel (profiles/r01_conv_ncu_full.md). The even CTA (leader) issues the MMAs; its full barriers collect the TMA
+// bytes of both CTAs; tcgen05.commit multicasts "stage free" / "accumulator ready" to both.
+template <int BN, int MT>
+struct Cfg2 {
+    static constexpr int kABytes = kBlockM * kBlockK * 2;
+    static constexpr int kBHalfBytes = (BN / 2) * kBlockK * 2;
+    static constexpr int kStageBytes = MT * kABytes + kBHalfBytes;  // per CTA
+    static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+    static constexpr int kAccCols = MT * BN;
+    static constexpr int kTmemCols = 2 * kAccCols;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN, int MT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+    conv_gemm_2cta_kernel(const __grid_constant__ ConvGemmParams p) {
+    using C = Cfg2<BN, MT>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;                                      // [kStages][MT][16 KB]
+    uint8_t* smem_b = smem + C::kStages * MT * C::kABytes;       // [kStages][BN/2 rows x 128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+    uint64_t* full_bar = bars;                    // leader's copy is used: TMA of both CTAs -> MMA
+    uint64_t* empty_bar = bars + C::kStages;      // per CTA: MMA (multicast commit) -> this CTA's producer
+    uint64_t* tfull_bar = bars + 2 * C::kStages;  // per CTA: MMA (multicast commit) -> this CTA's epilogue
+    uint64_t* tempty_bar = tfull_bar + 2;         // leader's copy: epilogue warps of both CTAs -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();  // 0 = leader
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.n_seg; ++s) ptx::prefetch_tmap(&p.tmA[s]);
+        ptx::prefetch_tmap(&p.tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < C::kStages; ++i) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tfull_bar[i], 1);
+            ptx::mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp of both CTAs
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) ptx::tmem_alloc_2cta<C::kTmemCols>(tmem_slot);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync_all();  // the peer's barriers must exist before anything is signalled across the pair
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // work item = 2*MT consecutive M tiles (MT per CTA) of one sub-pixel phase x one N tile
+    const int gpp = (p.num_m_tiles + 2 * MT - 1) / (2 * MT);
+    const int total_items = gpp * p.num_phases * p.num_n_tiles;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // ================================================================= TMA producer (one thread per CTA)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t parity = 0;
+            for (int item = cluster_id; item < total_items; item += num_clusters) {
+                const int g = item / p.num_n_tiles;
+                const int n_tile = item - g * p.num_n_tiles;
+                const int sub = g / gpp;
+                const int m_group = g - sub * gpp;
+                const bool phased = p.num_phases > 1;
+                const int pofw = (sub & 1) - 1, pofh = ((sub >> 1) & 1) - 1, pofd = p.phase3d ? ((sub >> 2) & 1) - 1 : 0;
+                int w0[MT], h0[MT], d0[MT], n0[MT];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    int t = (m_group * 2 + static_cast<int>(rank)) * MT + mt;  // past-the-end tiles read zeros
+                    const int tw = t % p.tiles_w; t /= p.tiles_w;
+                    const int th = t % p.tiles_h; t /= p.tiles_h;
+                    const int td = t % p.tiles_d; t /= p.tiles_d;
+                    w0[mt] = tw * p.bw * p.stride;
+                    h0[mt] = th * p.bh * p.stride;
+                    d0[mt] = td * p.bd * (p.D > 1 ? p.stride : 1);
+                    n0[mt] = t * p.bn;
+                }
+                const int brow = n_tile * BN + static_cast<int>(rank) * (BN / 2) + sub * p.Cout;
+                int seg = 0, seg_begin = 0;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    while (kb >= p.seg_kb_end[seg]) { seg_begin = p.seg_kb_end[seg]; ++seg; }
+                    const int local = kb - seg_begin;
+                    const int chunks = p.seg_chunks[seg];
+                    const int tap = local / chunks;
+                    const int chunk = local - tap * chunks;
+                    const int kw = p.seg_kw[seg], kh = p.seg_kh[seg], kd = p.seg_kd[seg];
+                    const int iw = tap % kw;
+                    const int ih = (tap / kw) % kh;
+                    const int id = tap / (kw * kh);
+                    const CUtensorMap* ma = seg == 0 ? &p.tmA[0] : (seg == 1 ? &p.tmA[1] : &p.tmA[2]);
+                    ptx::mbar_wait(&empty_bar[stage], parity ^ 1);
+                    if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+                        ptx::tma_load_5d_2cta(smem_a + (stage * MT + mt) * C::kABytes, ma, &full_bar[stage],
+                                              chunk * kBlockK, w0[mt] + iw + (phased ? pofw : -(kw >> 1)),
+                                              h0[mt] + ih + (phased ? pofh : -(kh >> 1)),
+                                              d0[mt] + id + (phased ? pofd : -(kd >> 1)), n0[mt]);
+                    ptx::tma_load_2d_2cta(smem_b + stage * C::kBHalfBytes, &p.tmB, &full_bar[stage], kb * kBlockK, brow);
+                    if (++stage == C::kStages) { stage = 0; parity ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer (one thread of the leader CTA)
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_f16(2 * kBlockM, BN);
+            int stage = 0;
+            uint32_t parity = 0;
+            int as = 0;
+            uint32_t aparity = 0;
+            for (int item = cluster_id; item < total_items; item += num_clusters) {
+                ptx::mbar_wait(&tempty_bar[as], aparity ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * C::kAccCols;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], parity);
+                    ptx::tc_fence_after();
+                    const uint64_t db = ptx::make_desc_k128(ptx::smem_u32(smem_b + stage * C::kBHalfBytes));
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const uint64_t da =
+                                ptx::make_desc_k128(ptx::smem_u32(smem_a + (stage * MT + mt) * C::kABytes));
+                            ptx::umma_f16_2cta(d_tmem + mt * BN, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        }
+                    }
+                    ptx::umma_commit_2cta(&empty_bar[stage]);  // frees this stage in both CTAs
+                    if (++stage == C::kStages) { stage = 0; parity ^= 1; }
+                }
+                ptx::umma_commit_2cta(&tfull_bar[as]);  // accumulators ready, both CTAs
+                if (++as == 2) { as = 0; aparity ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================================================= epilogue (4 warps per CTA, own 128 rows)
+        const int q = warp - 4;
+        int as = 0;
+        uint32_t aparity = 0;
+        for (int item = cluster_id; item < total_items; item += num_clusters) {
+            const int g = item / p.num_n_tiles;
+            const int n_tile = item - g * p.num_n_tiles;
+            const int sub = g / gpp;
+            const int m_group = g - sub * gpp;
+            ptx::mbar_wait(&tfull_bar[as], aparity);
+            ptx::tc_fence_after();
+#pragma unroll 1
+            for (int mt = 0; mt < MT; ++mt)
+                conv_epilogue_tile<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * C::kAccCols + mt * BN,
+                                       (m_group * 2 + static_cast<int>(rank)) * MT + mt, n_tile, sub, q, lane);
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_leader(&tempty_bar[as]);
+            if (++as == 2) { as = 0; aparity ^= 1; }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync_all();  // neither CTA may retire while the other can still signal into it
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc_2cta<C::kTmemCols>(tmem_base);
     }
 }
 
@@ -510,20 +696,39 @@ int conv_prepare(const ConvProblem& q, int num_sms, ConvLaunch* out) {
     }
     for (int s = q.n_seg; s < kMaxSeg; ++s) p.seg_kb_end[s] = kb;
     p.num_kb = kb;
+    static int allow_pair = -1;
+    if (allow_pair < 0) {
+        const char* e = getenv("DDPM_CONV_2CTA");
+        allow_pair = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    const int tiles = p.num_m_tiles * p.num_phases;  // 128-pixel tiles per N tile
+    out->m_tiles_per_cta = 1;
+    out->cta_pair = 0;
+    if (allow_pair && q.impl == 0 && q.b_rows_per_mtile == 0 && q.mode == EPI_STORE && p.num_m_tiles >= 2) {
+        // CTA pairs share every weight tile (and, for 128-wide outputs with enough work, two M tiles per CTA as well)
+        out->cta_pair = 1;
+        if (BN == 128 && tiles * p.num_n_tiles >= 4 * num_sms) out->m_tiles_per_cta = 2;
+    }
     {
         cuuint64_t gdim[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(q.w_rows)};
         cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ktot) * 2};
-        cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(BN)};
+        // a CTA of a pair stages half of the weight tile's rows
+        cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(out->cta_pair ? BN / 2 : BN)};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = encode(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(q.weights), gdim, gstr, box,
                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv: cuTensorMapEncodeTiled(B) failed: %d", (int)r); return 3; }
     }
-    // Pair M tiles (MT = 2) for 128-wide outputs when there is enough work to keep every SM busy with pairs.
-    out->m_tiles_per_cta = 1;
-    if (BN == 128 && q.b_rows_per_mtile == 0 && q.mode == EPI_STORE &&
-        p.num_m_tiles * p.num_n_tiles * p.num_phases >= 2 * num_sms)
+    if (out->cta_pair) {
+        const int per_item = 2 * out->m_tiles_per_cta;
+        const int items = ((p.num_m_tiles + per_item - 1) / per_item) * p.num_phases * p.num_n_tiles;
+        const int clusters = items < num_sms / 2 ? items : num_sms / 2;
+        out->grid = 2 * clusters;
+        return 0;
+    }
+    // single-CTA kernel; pair M tiles (MT = 2) for 128-wide outputs when there is enough work
+    if (BN == 128 && q.b_rows_per_mtile == 0 && q.mode == EPI_STORE && tiles * p.num_n_tiles >= 2 * num_sms)
         out->m_tiles_per_cta = 2;
     const int groups = (p.num_m_tiles + out->m_tiles_per_cta - 1) / out->m_tiles_per_cta;
     const int total = groups * p.num_phases * p.num_n_tiles;
@@ -540,14 +745,29 @@ int conv_launch(const ConvLaunch& l, cudaStream_t stream) {
                                               Cfg<256, 1>::kSmemBytes);
         cudaError_t e3 = cudaFuncSetAttribute(conv_gemm_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               Cfg<128, 2>::kSmemBytes);
-        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
-            set_error("conv: cudaFuncSetAttribute failed: %s",
-                      cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
-            return 4;
+        cudaError_t e4 = cudaFuncSetAttribute(conv_gemm_2cta_kernel<256, 1>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<256, 1>::kSmemBytes);
+        cudaError_t e5 = cudaFuncSetAttribute(conv_gemm_2cta_kernel<128, 1>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<128, 1>::kSmemBytes);
+        cudaError_t e6 = cudaFuncSetAttribute(conv_gemm_2cta_kernel<128, 2>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<128, 2>::kSmemBytes);
+        const cudaError_t es[6] = {e1, e2, e3, e4, e5, e6};
+        for (cudaError_t e : es) {
+            if (e != cudaSuccess) {
+                set_error("conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+                return 4;
+            }
         }
         g_attr_set = true;
     }
-    if (l.block_n == 256)
+    if (l.cta_pair) {
+        if (l.block_n == 256)
+            conv_gemm_2cta_kernel<256, 1><<<l.grid, 256, Cfg2<256, 1>::kSmemBytes, stream>>>(l.p);
+        else if (l.m_tiles_per_cta == 2)
+            conv_gemm_2cta_kernel<128, 2><<<l.grid, 256, Cfg2<128, 2>::kSmemBytes, stream>>>(l.p);
+        else
+            conv_gemm_2cta_kernel<128, 1><<<l.grid, 256, Cfg2<128, 1>::kSmemBytes, stream>>>(l.p);
+    } else if (l.block_n == 256)
         conv_gemm_kernel<256, 1><<<l.grid, 256, Cfg<256, 1>::kSmemBytes, stream>>>(l.p);
     else if (l.m_tiles_per_cta == 2)
         conv_gemm_kernel<128, 2><<<l.grid, 256, Cfg<128, 2>::kSmemBytes, stream>>>(l.p);

@@ -73,6 +73,7 @@ struct ConvLaunch {
     ConvGemmParams p;
     int block_n;          // 128 or 256
     int m_tiles_per_cta;  // 1, or 2 (block_n == 128 only): two 128-pixel tiles share each weight tile
+    int cta_pair;         // 1: conv_gemm_2cta_kernel (clusters of 2, tcgen05 cta_group::2)
     int grid;
 };
 
@@ -107,6 +108,7 @@ struct ConvProblem {
     // is 2, weights are phase-packed [2^dims * Cout][2^dims * C] (pack_upconv_weight), out has the doubled extents and
     // statistics come in 2^dims * conv_stats_parts(low-res extents) parts.
     int upsample2;
+    int impl;  // 0: pick; 1: single-CTA kernel only (A/B tests of the CTA-pair kernel)
 };
 
 // Number of GroupNorm-statistics parts per image the epilogue emits for an OUTPUT of this geometry (0: the tile box

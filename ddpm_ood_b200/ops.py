@@ -49,6 +49,7 @@ def conv_forward(
     out_vt: Optional[torch.Tensor] = None,
     stats_out: Optional[torch.Tensor] = None,
     upsample2: bool = False,
+    impl: int = 0,
 ) -> torch.Tensor:
     """segs: fp16 channels-last tensors [N, (D,) H, W, C]; weights: packed fp16 [rows, Ktot]."""
     x0 = segs[0]
@@ -78,6 +79,7 @@ def conv_forward(
     a.chan_add = _ptr(chan_add)
     a.residual = _ptr(residual)
     a.upsample2 = int(upsample2)
+    a.impl = impl
     so = (lambda v: 2 * v) if upsample2 else (lambda v: (v + stride - 1) // stride)  # noqa: E731
     if out is None:
         shape = (n, so(h), so(w), cout) if sd == 2 else (n, so(d), so(h), so(w), cout)

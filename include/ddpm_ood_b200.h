@@ -60,6 +60,8 @@ typedef struct ddpm_conv_args {
     int upsample2;           /* 1: out = conv3x3(nearest_upsample_x2(input)) computed as 2^dims sub-pixel 2x2 convs over the
                                 low-resolution input (N,D,H,W = low-res extents, one segment with ksize 2, weights from
                                 ddpm_pack_upconv_weight); the Upsample block of DiffusionModelUNet. 4/9 (8/27) of the MACs. */
+    int impl;                /* 0: pick the kernel variant; 1: single-CTA kernel only (the CTA-pair kernel is the default
+                                whenever at least two 128-pixel tiles exist) */
     float* stats_out;        /* mode 0, optional: GroupNorm partial statistics of the fp16-rounded output,
                                 [N][ddpm_conv_stats_parts()][Cout/4][2] fp32 = (sum, sum of squares) per 4-channel quad
                                 and 32-pixel part of an image; consumed by ddpm_gn_apply() */

@@ -17,7 +17,7 @@ def _to_ncx(y):  # channels-last -> [N,C,*sp] fp32
     return y.permute(*perm).float()
 
 
-def _run_case(sd, n, sp, segs, cout, stride=1, use_bias=True, use_cadd=False, use_res=False, seed=0):
+def _run_case(sd, n, sp, segs, cout, stride=1, use_bias=True, use_cadd=False, use_res=False, seed=0, impl=0):
     """segs: list of (channels, ksize). Returns (rel_l2, max_abs_err/max_ref)."""
     from ddpm_ood_b200 import ops
 
@@ -52,7 +52,7 @@ def _run_case(sd, n, sp, segs, cout, stride=1, use_bias=True, use_cadd=False, us
         res16 = _nhwc(res)
         ref = ref + _to_ncx(res16)
     out = ops.conv_forward(xs, [k for _, k in segs], wp, cout, stride=stride, bias=bias, chan_add=cadd,
-                           residual=res16)
+                           residual=res16, impl=impl)
     torch.cuda.synchronize()
     got = _to_ncx(out)
     assert got.shape == ref.shape, (got.shape, ref.shape)
@@ -83,12 +83,18 @@ CASES = {
     "paired_m_tiles_odd_count_28px": dict(sd=2, n=43, sp=(28, 28), segs=[(128, 3)], cout=128, use_cadd=True),
     "paired_m_tiles_concat_skip": dict(sd=2, n=40, sp=(32, 32), segs=[(128, 3), (128, 1), (128, 1)], cout=128,
                                        use_res=False),
+    # >= 4 tiles per SM with Cout = 128: CTA pairs with two M tiles per CTA (conv_gemm_2cta_kernel<128, 2>), ragged end
+    "cta_pair_two_m_tiles_odd": dict(sd=2, n=85, sp=(28, 28), segs=[(128, 3)], cout=128, use_res=True),
+    "cta_pair_256_many": dict(sd=2, n=70, sp=(16, 16), segs=[(256, 3), (128, 1)], cout=256, use_cadd=True),
 }
 
 
+@pytest.mark.parametrize("impl", [0, 1], ids=["auto_cta_pair", "single_cta"])
 @pytest.mark.parametrize("name", list(CASES))
-def test_conv_case(name):
-    rel, mx = _run_case(**CASES[name])
+def test_conv_case(name, impl):
+    """impl 0 picks the CTA-pair kernel (tcgen05 cta_group::2) whenever two 128-pixel tiles exist; impl 1 forces the
+    single-CTA kernel."""
+    rel, mx = _run_case(**CASES[name], impl=impl)
     # fp16 operands are shared with the reference; what remains is fp32 accumulation order + the fp16 output rounding
     # (2^-11 relative).
     assert rel < 6e-4, (name, rel, mx)
