@@ -39,6 +39,8 @@ class ConvArgs(C.Structure):
         ("upsample2", C.c_int),
         ("impl", C.c_int),
         ("stats_out", C.c_void_p),
+        ("gn_scale_shift", C.c_void_p),
+        ("gn_channels", C.c_int),
     ]
 
 
@@ -95,6 +97,9 @@ SIGNATURES = {
     "ddpm_abi_version": (C.c_int, []),
     "ddpm_conv_forward": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "ddpm_conv_stats_parts": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ddpm_conv_halo_stats_parts": (C.c_int, [C.c_int, C.c_int]),
+    "ddpm_gn_finalize": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "ddpm_gn_silu": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]),
     "ddpm_gn_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,

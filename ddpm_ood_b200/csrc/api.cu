@@ -7,6 +7,7 @@
 
 #include "attention.cuh"
 #include "conv_gemm.cuh"
+#include "conv_halo.cuh"
 #include "kernels.cuh"
 
 namespace ddpm {
@@ -84,7 +85,7 @@ int pack_upconv_weight(const float* w, int Cout, int Cin, int dims, __half* dst,
 extern "C" {
 
 const char* ddpm_last_error(void) { return ddpm::last_error(); }
-int ddpm_abi_version(void) { return 2; }
+int ddpm_abi_version(void) { return 3; }
 
 int ddpm_conv_forward(const ddpm_conv_args* a, void* stream) {
     if (!a) { ddpm::set_error("ddpm_conv_forward: null args"); return 2; }
@@ -115,6 +116,13 @@ int ddpm_conv_forward(const ddpm_conv_args* a, void* stream) {
     q.stats_out = a->stats_out;
     q.upsample2 = a->upsample2;
     q.impl = a->impl;
+    if (a->impl == 3) {
+        ddpm::ConvHaloLaunch hl;
+        int rc = ddpm::conv_halo_prepare(q, a->gn_scale_shift, a->gn_channels, ddpm::num_sms(), &hl);
+        if (rc) return rc;
+        return ddpm::conv_halo_launch(hl, static_cast<cudaStream_t>(stream));
+    }
+    if (a->gn_scale_shift) { ddpm::set_error("ddpm_conv_forward: gn_scale_shift needs impl 3"); return 2; }
     ddpm::ConvLaunch l;
     int rc = ddpm::conv_prepare(q, ddpm::num_sms(), &l);
     if (rc) return rc;
@@ -123,6 +131,14 @@ int ddpm_conv_forward(const ddpm_conv_args* a, void* stream) {
 
 int ddpm_conv_stats_parts(int spatial_dims, int Dout, int Hout, int Wout) {
     return ddpm::conv_stats_parts(spatial_dims, Dout, Hout, Wout);
+}
+
+int ddpm_conv_halo_stats_parts(int Hout, int Wout) { return ddpm::conv_halo_stats_parts(Hout, Wout); }
+
+int ddpm_gn_finalize(int C0, const float* st0, int parts0, int C1, const float* st1, int parts1, const float* gamma,
+                     const float* beta, float* ab, int N, int S, int groups, float eps, void* stream) {
+    return ddpm::gn_finalize(C0, st0, parts0, C1, st1, parts1, gamma, beta, ab, N, S, groups, eps,
+                             static_cast<cudaStream_t>(stream));
 }
 
 int ddpm_gn_silu(const void* src0, int C0, const void* src1, int C1, const float* gamma, const float* beta, void* out,

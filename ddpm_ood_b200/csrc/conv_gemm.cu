@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "conv_epilogue.cuh"
 #include "ptx.cuh"
 
 namespace ddpm {
@@ -35,198 +36,6 @@ struct Cfg {
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-
-// Epilogue of one 128-pixel x BN-channel accumulator tile; executed by the 4 epilogue warps (q = TMEM lane quarter),
-// one output pixel (row) per thread. t_addr: TMEM address of the tile for this warp's lanes. sub: sub-pixel phase.
-template <int BN>
-__device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint32_t t_addr, int m_tile, int n_tile,
-                                                   int sub, int q, int lane) {
-            const int row = q * 32 + lane;
-
-            int t = m_tile;
-            const int tw = t % p.tiles_w; t /= p.tiles_w;
-            const int th = t % p.tiles_h; t /= p.tiles_h;
-            const int td = t % p.tiles_d; t /= p.tiles_d;
-            const int tn = t;
-            int r = row;
-            const int w = tw * p.bw + r % p.bw; r /= p.bw;
-            const int h = th * p.bh + r % p.bh; r /= p.bh;
-            const int d = td * p.bd + r % p.bd; r /= p.bd;
-            const int n = tn * p.bn + r;
-            const bool valid = (w < p.W) && (h < p.H) && (d < p.D) && (n < p.N);
-            size_t pix;
-            if (p.num_phases > 1) {  // sub-pixel scatter into the doubled output grid
-                const int od = p.phase3d ? 2 * d + ((sub >> 2) & 1) : d;
-                const int Do = p.phase3d ? 2 * p.D : p.D;
-                pix = ((static_cast<size_t>(n) * Do + od) * (2 * p.H) + (2 * h + ((sub >> 1) & 1))) * (2 * p.W) +
-                      (2 * w + (sub & 1));
-            } else {
-                pix = ((static_cast<size_t>(n) * p.D + d) * p.H + h) * p.W + w;
-            }
-
-            if (p.mode == EPI_SOFTMAX_BD) {
-                // Attention probabilities. Row = query token; its keys are the `group` columns of its own image:
-                // columns [g0, g0+group) of this tile when group <= 128 (block diagonal), all BN columns otherwise.
-                const int G = p.group < BN ? p.group : BN;
-                const int g0 = p.group < BN ? (row / G) * G : 0;
-                float mx = -INFINITY;
-                for (int c = 0; c < BN / 32; ++c) {
-                    uint32_t v[32];
-                    ptx::tmem_ld_32x32(t_addr + c * 32, v);
-                    ptx::tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = c * 32 + j;
-                        if (col >= g0 && col < g0 + G) mx = fmaxf(mx, __uint_as_float(v[j]) * p.scale);
-                    }
-                }
-                float sum = 0.f;
-                for (int c = 0; c < BN / 32; ++c) {
-                    uint32_t v[32];
-                    ptx::tmem_ld_32x32(t_addr + c * 32, v);
-                    ptx::tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = c * 32 + j;
-                        if (col >= g0 && col < g0 + G) sum += __expf(__uint_as_float(v[j]) * p.scale - mx);
-                    }
-                }
-                const float inv = 1.0f / sum;
-                __half* dst = p.out + pix * static_cast<size_t>(p.Cout) + static_cast<size_t>(n_tile) * BN;
-                for (int c = 0; c < BN / 32; ++c) {
-                    uint32_t v[32];
-                    ptx::tmem_ld_32x32(t_addr + c * 32, v);
-                    ptx::tmem_ld_wait();
-                    if (valid) {
-                        uint32_t packed[16];
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            const int col = c * 32 + j;
-                            float a = 0.f, b = 0.f;
-                            if (col >= g0 && col < g0 + G) {
-                                a = __expf(__uint_as_float(v[j]) * p.scale - mx) * inv;
-                                b = __expf(__uint_as_float(v[j + 1]) * p.scale - mx) * inv;
-                            }
-                            __half2 hh = __floats2half2_rn(a, b);
-                            packed[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
-                        }
-                        uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-                    }
-                }
-            } else {
-                const int col_base = n_tile * BN;
-                const float* cadd = p.chan_add ? p.chan_add + static_cast<size_t>(valid ? n : 0) * p.chan_add_stride : nullptr;
-                // GroupNorm partial statistics: all 32 rows of this warp lie in one image (host guarantees it)
-                float* st_base = nullptr;
-                if (p.stats_out) {
-                    const int R = p.bw * p.bh * p.bd;  // pixels of one image inside the tile box (multiple of 32)
-                    const int n_w = tn * p.bn + (q * 32) / R;
-                    if (n_w < p.N) {
-                        const int tile_sp = (td * p.tiles_h + th) * p.tiles_w + tw;
-                        const int part = sub * (p.stats_parts / p.num_phases) + tile_sp * (R >> 5) + ((q * 32) % R) / 32;
-                        st_base = p.stats_out + (static_cast<size_t>(n_w) * p.stats_parts + part) * (p.Cout >> 1);
-                    }
-                }
-                for (int c = 0; c < BN / 32; ++c) {
-                    uint32_t v[32];
-                    ptx::tmem_ld_32x32(t_addr + c * 32, v);
-                    ptx::tmem_ld_wait();
-                    const int col0 = col_base + c * 32;
-                    uint32_t packed[16];
-                    if (valid) {
-                        float f[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                        if (p.bias) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-                            }
-                        }
-                        if (cadd) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(cadd + col0 + j));
-                                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-                            }
-                        }
-                        if (p.residual) {
-                            const uint4* r4 =
-                                reinterpret_cast<const uint4*>(p.residual + pix * static_cast<size_t>(p.Cout) + col0);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const uint4 rv = __ldg(r4 + j);
-                                const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float2 ff = __half22float2(h2[e]);
-                                    f[8 * j + 2 * e] += ff.x;
-                                    f[8 * j + 2 * e + 1] += ff.y;
-                                }
-                            }
-                        }
-                        if (p.mode == EPI_STORE_VT && col0 >= p.vt_col0) {
-                            // transposed store for the attention V operand: out_vt[pair][c][token-in-pair], where a
-                            // "pair" is the 128 consecutive tokens of one M tile.
-                            const size_t tok = pix;  // token index == pixel index (N*T rows)
-                            const size_t pair = tok >> 7;
-                            const int tin = static_cast<int>(tok & 127);
-                            const int vc = col0 - p.vt_col0;
-                            const int vC = p.Cout - p.vt_col0;
-                            __half* dv = p.out_vt + (pair * vC + vc) * 128 + tin;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) dv[static_cast<size_t>(j) * 128] = __float2half_rn(f[j]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 2) {
-                                __half2 hh = __floats2half2_rn(f[j], f[j + 1]);
-                                packed[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
-                            }
-                            uint4* d4 = reinterpret_cast<uint4*>(p.out + pix * static_cast<size_t>(p.Cout) + col0);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) packed[j] = 0u;
-                    }
-                    if (p.stats_out) {
-                        // per-lane quad sums of the ROUNDED values (what GroupNorm will read back), then a
-                        // transpose-reduce over the warp's 32 pixels: 16 shuffles instead of 80.
-                        float sv[16];
-#pragma unroll
-                        for (int qd = 0; qd < 8; ++qd) {
-                            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&packed[2 * qd]));
-                            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&packed[2 * qd + 1]));
-                            sv[qd] = (a.x + a.y) + (b.x + b.y);
-                            sv[8 + qd] = (a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y);
-                        }
-#pragma unroll
-                        for (int half_n = 8, off = 16; half_n >= 1; half_n >>= 1, off >>= 1) {
-                            const bool hi = (lane & off) != 0;
-#pragma unroll
-                            for (int i = 0; i < half_n; ++i) {
-                                const float send = hi ? sv[i] : sv[i + half_n];
-                                const float keep = hi ? sv[i + half_n] : sv[i];
-                                sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                            }
-                        }
-                        sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
-                        // lane bits: b4 -> sum / sum of squares, b3 b2 b1 -> quad, b0 -> duplicate
-                        if (st_base && (lane & 1) == 0) {
-                            const int quad = (col0 >> 2) + ((lane >> 1) & 7);
-                            st_base[quad * 2 + (lane >> 4)] = sv[0];
-                        }
-                    }
-                }
-            }
-}
 template <int BN, int MT>
 __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     using C = Cfg<BN, MT>;
@@ -320,8 +129,9 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
             }
         }
     } else if (warp == 1) {
-        // ================================================================= MMA issuer (one thread)
-        if (lane == 0) {
+        // ================================================================= MMA issuer (one elected lane issues; the whole
+        // warp walks the loop so descriptors / barrier addresses stay in uniform registers, no R2UR waterfall per MMA)
+        {
             constexpr uint32_t idesc = ptx::make_idesc_f16(kBlockM, BN);
             int stage = 0;
             uint32_t phase = 0;
@@ -332,30 +142,32 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * C::kAccCols;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
+                    const uint64_t db = ptx::make_desc_k128(ptx::smem_u32(smem_b + stage * C::kBBytes));
+                    const uint64_t da = ptx::make_desc_k128(ptx::smem_u32(smem_a + stage * MT * C::kABytes));
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
-                    const uint64_t db = ptx::make_desc_k128(ptx::smem_u32(smem_b + stage * C::kBBytes));
+                    if (ptx::elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        for (int k = 0; k < kBlockK / 16; ++k) {
 #pragma unroll
-                        for (int mt = 0; mt < MT; ++mt) {
-                            const uint64_t da =
-                                ptx::make_desc_k128(ptx::smem_u32(smem_a + (stage * MT + mt) * C::kABytes));
-                            // +32 bytes (>>4 = 2) per 16-element K step inside the 128B swizzle row
-                            ptx::umma_f16(d_tmem + mt * BN, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            for (int mt = 0; mt < MT; ++mt) {
+                                // +32 bytes (>>4 = 2) per 16-element K step inside the 128B swizzle row
+                                ptx::umma_f16(d_tmem + mt * BN, da + (mt * (C::kABytes >> 4) + 2 * k), db + 2 * k, idesc,
+                                              (kb | k) != 0);
+                            }
                         }
+                        ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+                        if (kb == p.num_kb - 1) ptx::umma_commit(&tfull_bar[as]);  // accumulator ready for the epilogue
                     }
-                    ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+                    __syncwarp();
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
-                ptx::umma_commit(&tfull_bar[as]);  // accumulator ready for the epilogue
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
         }
     } else if (warp >= 4) {
         // ================================================================= epilogue (4 warps, 1 row per thread)
         const int q = warp - 4;  // TMEM lane quarter == warp % 4
-        const int row = q * 32 + lane;
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -499,8 +311,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
             }
         }
     } else if (warp == 1) {
-        // ================================================================= MMA issuer (one thread of the leader CTA)
-        if (lane == 0 && rank == 0) {
+        // ================================================================= MMA issuer (leader CTA; one elected lane)
+        if (rank == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_f16(2 * kBlockM, BN);
             int stage = 0;
             uint32_t parity = 0;
@@ -511,22 +323,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * C::kAccCols;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
+                    const uint64_t db = ptx::make_desc_k128(ptx::smem_u32(smem_b + stage * C::kBHalfBytes));
+                    const uint64_t da = ptx::make_desc_k128(ptx::smem_u32(smem_a + stage * MT * C::kABytes));
                     ptx::mbar_wait(&full_bar[stage], parity);
                     ptx::tc_fence_after();
-                    const uint64_t db = ptx::make_desc_k128(ptx::smem_u32(smem_b + stage * C::kBHalfBytes));
+                    if (ptx::elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        for (int k = 0; k < kBlockK / 16; ++k) {
 #pragma unroll
-                        for (int mt = 0; mt < MT; ++mt) {
-                            const uint64_t da =
-                                ptx::make_desc_k128(ptx::smem_u32(smem_a + (stage * MT + mt) * C::kABytes));
-                            ptx::umma_f16_2cta(d_tmem + mt * BN, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            for (int mt = 0; mt < MT; ++mt)
+                                ptx::umma_f16_2cta(d_tmem + mt * BN, da + (mt * (C::kABytes >> 4) + 2 * k), db + 2 * k, idesc,
+                                                   (kb | k) != 0);
                         }
+                        ptx::umma_commit_2cta(&empty_bar[stage]);  // frees this stage in both CTAs
+                        if (kb == p.num_kb - 1) ptx::umma_commit_2cta(&tfull_bar[as]);  // accumulators ready, both CTAs
                     }
-                    ptx::umma_commit_2cta(&empty_bar[stage]);  // frees this stage in both CTAs
+                    __syncwarp();
                     if (++stage == C::kStages) { stage = 0; parity ^= 1; }
                 }
-                ptx::umma_commit_2cta(&tfull_bar[as]);  // accumulators ready, both CTAs
                 if (++as == 2) { as = 0; aparity ^= 1; }
             }
         }

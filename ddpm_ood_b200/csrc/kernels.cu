@@ -146,23 +146,20 @@ int gn_silu(const __half* src0, int C0, const __half* src1, int C1, const float*
 // derives per-channel scale/shift and streams its pixel chunk once: one fp16 read + one fp16 write per element.
 constexpr int kGnApplyMaxC = 2048;
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ src0, int C0,
-                                                       const float* __restrict__ st0, int parts0,
-                                                       const __half* __restrict__ src1, int C1,
-                                                       const float* __restrict__ st1, int parts1,
-                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       __half* __restrict__ out, int S, int cpg, float eps, int do_silu,
-                                                       int chunk) {
-    __shared__ float s_qs[kGnApplyMaxC / 4], s_qq[kGnApplyMaxC / 4];
-    __shared__ float s_a[kGnApplyMaxC], s_b[kGnApplyMaxC];
+// Per-channel scale/shift of image n from the producers' partial statistics, into shared memory (s_a, s_b): the
+// common front half of gn_apply_kernel and gn_finalize_kernel (identical summation order -> identical bits).
+__device__ __forceinline__ void gn_scale_shift_from_parts(int n, int C0, const float* __restrict__ st0, int parts0,
+                                                          int C1, const float* __restrict__ st1, int parts1,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, int S, int cpg, float eps,
+                                                          float* s_qs, float* s_qq, float2* s_sub, float* s_a,
+                                                          float* s_b) {
     const int C = C0 + C1;
     const int Q = C >> 2, Q0 = C0 >> 2, Q1 = C1 >> 2;
-    const int n = blockIdx.y;
     const int tid = threadIdx.x;
     {
         // fixed-order two-level sum of the partials: J threads per quad take parts j, j+J, ... (independent loads),
         // then one thread per quad adds the J sub-sums.
-        __shared__ float2 s_sub[256];
         const int J = Q <= 256 ? 256 / Q : 1;
         for (int base = 0; base < Q; base += 256) {
             const int qd = base + tid % (Q < 256 ? Q : 256);
@@ -202,6 +199,22 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
         s_b[c] = beta[c] - mean * a;
     }
     __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ src0, int C0,
+                                                       const float* __restrict__ st0, int parts0,
+                                                       const __half* __restrict__ src1, int C1,
+                                                       const float* __restrict__ st1, int parts1,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       __half* __restrict__ out, int S, int cpg, float eps, int do_silu,
+                                                       int chunk) {
+    __shared__ float s_qs[kGnApplyMaxC / 4], s_qq[kGnApplyMaxC / 4];
+    __shared__ float s_a[kGnApplyMaxC], s_b[kGnApplyMaxC];
+    __shared__ float2 s_sub[256];
+    const int C = C0 + C1;
+    const int n = blockIdx.y;
+    const int tid = threadIdx.x;
+    gn_scale_shift_from_parts(n, C0, st0, parts0, C1, st1, parts1, gamma, beta, S, cpg, eps, s_qs, s_qq, s_sub, s_a, s_b);
     // apply: a thread keeps one 8-channel vector (scale/shift in registers) and walks pixels, 4 loads in flight
     const int V = C >> 3;              // uint4 vectors per pixel
     const int ppi = blockDim.x / V;    // pixels per block iteration (threads beyond ppi*V idle in this phase)
@@ -257,6 +270,34 @@ int gn_apply(const __half* src0, int C0, const float* st0, int parts0, const __h
     gn_apply_kernel<<<grid, 256, 0, stream>>>(src0, C0, st0, parts0, src1, C1, st1, parts1, gamma, beta, out, S,
                                               C / groups, eps, do_silu ? 1 : 0, chunk);
     DDPM_CHECK_LAUNCH("gn_apply");
+    return 0;
+}
+
+// GroupNorm statistics -> per-(image, channel) (scale, shift) table for consumers that normalise on the fly
+// (conv_halo.cu's transform warps): ab[n][c] = (gamma[c] * rstd, beta[c] - mean * gamma[c] * rstd).
+__global__ void __launch_bounds__(256) gn_finalize_kernel(int C0, const float* __restrict__ st0, int parts0, int C1,
+                                                          const float* __restrict__ st1, int parts1,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float2* __restrict__ ab, int S, int cpg, float eps) {
+    __shared__ float s_qs[kGnApplyMaxC / 4], s_qq[kGnApplyMaxC / 4];
+    __shared__ float s_a[kGnApplyMaxC], s_b[kGnApplyMaxC];
+    __shared__ float2 s_sub[256];
+    const int C = C0 + C1;
+    const int n = blockIdx.x;
+    gn_scale_shift_from_parts(n, C0, st0, parts0, C1, st1, parts1, gamma, beta, S, cpg, eps, s_qs, s_qq, s_sub, s_a, s_b);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) ab[static_cast<size_t>(n) * C + c] = make_float2(s_a[c], s_b[c]);
+}
+
+int gn_finalize(int C0, const float* st0, int parts0, int C1, const float* st1, int parts1, const float* gamma,
+                const float* beta, float* ab, int N, int S, int groups, float eps, cudaStream_t stream) {
+    const int C = C0 + C1;
+    if (C % groups != 0 || (C / groups) % 4 != 0 || C0 % 8 != 0 || C1 % 8 != 0 || C > kGnApplyMaxC) {
+        set_error("gn_finalize: C=%d+%d groups=%d unsupported", C0, C1, groups);
+        return 2;
+    }
+    gn_finalize_kernel<<<N, 256, 0, stream>>>(C0, st0, parts0, C1, st1, parts1, gamma, beta,
+                                              reinterpret_cast<float2*>(ab), S, C / groups, eps);
+    DDPM_CHECK_LAUNCH("gn_finalize");
     return 0;
 }
 

@@ -44,6 +44,11 @@ int gn_apply(const __half* src0, int C0, const float* st0, int parts0, const __h
              int parts1, const float* gamma, const float* beta, __half* out, int N, int S, int groups, float eps,
              bool silu, cudaStream_t stream);
 
+// The same statistics -> (scale, shift) table ab[N][C0+C1][2] fp32 (y = x * scale + shift is GroupNorm's affine output)
+// for consumers that normalise their input on the fly (conv_halo.cuh). Bitwise the values gn_apply uses.
+int gn_finalize(int C0, const float* st0, int parts0, int C1, const float* st1, int parts1, const float* gamma,
+                const float* beta, float* ab, int N, int S, int groups, float eps, cudaStream_t stream);
+
 // Layout conversions for many-channel inputs/outputs (latent models): fp32 [N, C, S] <-> fp16 [N, S, C].
 int nchw_to_nhwc_half(const float* x, __half* out, int N, int C, long long S, cudaStream_t stream);
 

@@ -50,8 +50,10 @@ def conv_forward(
     stats_out: Optional[torch.Tensor] = None,
     upsample2: bool = False,
     impl: int = 0,
+    gn_scale_shift: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
-    """segs: fp16 channels-last tensors [N, (D,) H, W, C]; weights: packed fp16 [rows, Ktot]."""
+    """segs: fp16 channels-last tensors [N, (D,) H, W, C]; weights: packed fp16 [rows, Ktot].
+    impl 3 = halo-tile kernel; gn_scale_shift (fp32 [N, C3x3, 2], impl 3 only) normalises the 3x3 segments on the fly."""
     x0 = segs[0]
     sd = x0.dim() - 2
     assert sd in (2, 3)
@@ -90,6 +92,8 @@ def conv_forward(
     a.vt_col0 = vt_col0
     a.out_vt = _ptr(out_vt)
     a.stats_out = _ptr(stats_out)
+    a.gn_scale_shift = _ptr(gn_scale_shift)
+    a.gn_channels = 0 if gn_scale_shift is None else gn_scale_shift.shape[1]
     check(lib().ddpm_conv_forward(C.byref(a), current_stream_ptr()), "ddpm_conv_forward")
     return out
 
@@ -97,6 +101,24 @@ def conv_forward(
 def conv_stats_parts(spatial_dims: int, d: int, h: int, w: int) -> int:
     """GroupNorm-statistics parts per image that conv_forward(stats_out=...) emits for an output of this geometry."""
     return int(lib().ddpm_conv_stats_parts(spatial_dims, d, h, w))
+
+
+def conv_halo_stats_parts(h: int, w: int) -> int:
+    """Parts per image emitted by conv_forward(impl=3, stats_out=...) for an h x w output."""
+    return int(lib().ddpm_conv_halo_stats_parts(h, w))
+
+
+def gn_finalize(st0: torch.Tensor, st1: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, spatial: int,
+                groups: int, eps: float) -> torch.Tensor:
+    """Partial statistics st* [N, parts, C*/4, 2] -> GroupNorm (scale, shift) table fp32 [N, C0+C1, 2]."""
+    n = st0.shape[0]
+    c0 = st0.shape[2] * 4
+    c1 = 0 if st1 is None else st1.shape[2] * 4
+    ab = torch.empty((n, c0 + c1, 2), dtype=torch.float32, device=st0.device)
+    check(lib().ddpm_gn_finalize(c0, st0.data_ptr(), st0.shape[1], c1, _ptr(st1), 0 if st1 is None else st1.shape[1],
+                                 gamma.data_ptr(), beta.data_ptr(), ab.data_ptr(), n, spatial, groups, eps,
+                                 current_stream_ptr()), "ddpm_gn_finalize")
+    return ab
 
 
 def gn_silu(src0: torch.Tensor, src1: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, groups: int,

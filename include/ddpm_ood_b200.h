@@ -60,15 +60,23 @@ typedef struct ddpm_conv_args {
     int upsample2;           /* 1: out = conv3x3(nearest_upsample_x2(input)) computed as 2^dims sub-pixel 2x2 convs over the
                                 low-resolution input (N,D,H,W = low-res extents, one segment with ksize 2, weights from
                                 ddpm_pack_upconv_weight); the Upsample block of DiffusionModelUNet. 4/9 (8/27) of the MACs. */
-    int impl;                /* 0: pick the kernel variant; 1: single-CTA kernel only (the CTA-pair kernel is the default
-                                whenever at least two 128-pixel tiles exist) */
+    int impl;                /* 0: im2col-tile kernels, variant picked (CTA pairs whenever two 128-pixel tiles exist);
+                                1: single-CTA im2col kernel only; 3: halo-tile kernel (stride-1 2-D 3x3 convs on images of
+                                at least 16 x 8 pixels: the input is staged once per 64 channels as a haloed tile and the
+                                9 taps read shifted views of it) */
     float* stats_out;        /* mode 0, optional: GroupNorm partial statistics of the fp16-rounded output,
                                 [N][ddpm_conv_stats_parts()][Cout/4][2] fp32 = (sum, sum of squares) per 4-channel quad
-                                and 32-pixel part of an image; consumed by ddpm_gn_apply() */
+                                and 32-pixel part of an image; consumed by ddpm_gn_apply() / ddpm_gn_finalize();
+                                impl 3 emits ddpm_conv_halo_stats_parts() parts instead */
+    const float* gn_scale_shift; /* impl 3, optional: [N][gn_channels][2] fp32 (scale, shift) from ddpm_gn_finalize(); the
+                                3x3 segments' inputs are normalised on the fly, z = silu(x * scale + shift) -> fp16,
+                                i.e. the conv consumes GroupNorm+SiLU of its raw input without that tensor existing */
+    int gn_channels;         /* total channels of the 3x3 segments */
 } ddpm_conv_args;
 DDPM_API int ddpm_conv_forward(const ddpm_conv_args* args, void* stream);
 /* Parts per image that ddpm_conv_forward emits for an output of this geometry (0: unsupported, use ddpm_gn_silu). */
 DDPM_API int ddpm_conv_stats_parts(int spatial_dims, int Dout, int Hout, int Wout);
+DDPM_API int ddpm_conv_halo_stats_parts(int Hout, int Wout);
 
 /* GroupNorm(groups, eps) (+ SiLU) over the channel concatenation of up to two channels-last fp16 tensors
  * src0 [N,S,C0], src1 [N,S,C1] (or NULL) -> out [N,S,C0+C1] fp16: the norm in front of every conv of
@@ -80,6 +88,12 @@ DDPM_API int ddpm_gn_silu(const void* src0, int C0, const void* src1, int C1, co
 DDPM_API int ddpm_gn_apply(const void* src0, int C0, const float* st0, int parts0, const void* src1, int C1,
                            const float* st1, int parts1, const float* gamma, const float* beta, void* out, int N, int S,
                            int groups, float eps, int silu, void* stream);
+
+/* Producer statistics -> per-(image, channel) GroupNorm (scale, shift) table ab [N][C0+C1][2] fp32 for
+ * ddpm_conv_args.gn_scale_shift: scale = gamma * rstd, shift = beta - mean * scale. */
+DDPM_API int ddpm_gn_finalize(int C0, const float* st0, int parts0, int C1, const float* st1, int parts1,
+                              const float* gamma, const float* beta, float* ab, int N, int S, int groups, float eps,
+                              void* stream);
 
 /* fp32 conv weight [Cout][Cin][3^dims] -> fp16 sub-pixel phase weights [2^dims * Cout][2^dims * Cin] for upsample2. */
 DDPM_API int ddpm_pack_upconv_weight(const float* w, int Cout, int Cin, int spatial_dims, void* dst, void* stream);

@@ -17,8 +17,11 @@ def _to_ncx(y):  # channels-last -> [N,C,*sp] fp32
     return y.permute(*perm).float()
 
 
-def _run_case(sd, n, sp, segs, cout, stride=1, use_bias=True, use_cadd=False, use_res=False, seed=0, impl=0):
-    """segs: list of (channels, ksize). Returns (rel_l2, max_abs_err/max_ref)."""
+def _run_case(sd, n, sp, segs, cout, stride=1, use_bias=True, use_cadd=False, use_res=False, seed=0, impl=0, gn=False,
+              stats=False):
+    """segs: list of (channels, ksize). Returns (rel_l2, max_abs_err/max_ref).
+    gn (impl 3): the 3x3 segments are consumed as silu(x * scale[n, c] + shift[n, c]) rounded to fp16, applied on the fly.
+    stats (impl 3): also check the epilogue's GroupNorm partial statistics."""
     from ddpm_ood_b200 import ops
 
     torch.backends.cudnn.allow_tf32 = False
@@ -31,6 +34,7 @@ def _run_case(sd, n, sp, segs, cout, stride=1, use_bias=True, use_cadd=False, us
     wp = torch.zeros(cout, ktot, dtype=torch.float16, device=dev)
     koff = 0
     ref = None
+    abs_ = []
     for c, k in segs:
         x = torch.randn((n, c) + tuple(sp), generator=g, device=dev)
         w = torch.randn((cout, c) + (k,) * sd, generator=g, device=dev) * (1.0 / (c * k ** sd) ** 0.5)
@@ -38,7 +42,14 @@ def _run_case(sd, n, sp, segs, cout, stride=1, use_bias=True, use_cadd=False, us
         ops.pack_conv_weight(w.contiguous(), wp, koff)
         koff += c * k ** sd
         xs.append(x16)
-        r = conv(_to_ncx(x16), w.half().float(), stride=stride, padding=k // 2)
+        xin = _to_ncx(x16)
+        if gn and k == 3:
+            ab = torch.stack([0.5 + torch.rand((n, c), generator=g, device=dev),
+                              torch.randn((n, c), generator=g, device=dev)], dim=-1)
+            abs_.append(ab)
+            bshape = (n, c) + (1,) * sd
+            xin = F.silu(xin * ab[..., 0].view(bshape) + ab[..., 1].view(bshape)).half().float()
+        r = conv(xin, w.half().float(), stride=stride, padding=k // 2)
         ref = r if ref is None else ref + r
     bias = torch.randn(cout, generator=g, device=dev) if use_bias else None
     cadd = torch.randn(n, cout, generator=g, device=dev) if use_cadd else None
@@ -51,9 +62,18 @@ def _run_case(sd, n, sp, segs, cout, stride=1, use_bias=True, use_cadd=False, us
         res = torch.randn(ref.shape, generator=g, device=dev)
         res16 = _nhwc(res)
         ref = ref + _to_ncx(res16)
+    st = None
+    if stats:
+        st = torch.full((n, ops.conv_halo_stats_parts(sp[0], sp[1]), cout // 4, 2), float("nan"), device=dev)
     out = ops.conv_forward(xs, [k for _, k in segs], wp, cout, stride=stride, bias=bias, chan_add=cadd,
-                           residual=res16, impl=impl)
+                           residual=res16, impl=impl, stats_out=st,
+                           gn_scale_shift=torch.cat(abs_, dim=1).contiguous() if abs_ else None)
     torch.cuda.synchronize()
+    if st is not None:
+        assert torch.isfinite(st).all()
+        o = out.float().reshape(n, -1, cout // 4, 4)
+        assert torch.allclose(st.sum(1)[..., 0], o.sum(dim=(1, 3)), rtol=1e-5, atol=1e-2)
+        assert torch.allclose(st.sum(1)[..., 1], (o * o).sum(dim=(1, 3)), rtol=1e-5, atol=1e-2)
     got = _to_ncx(out)
     assert got.shape == ref.shape, (got.shape, ref.shape)
     err = (got - ref)
@@ -101,8 +121,59 @@ def test_conv_case(name, impl):
     assert mx < 3e-3, (name, rel, mx)
 
 
+# Halo-tile kernel (impl 3): the haloed input of an 8 x 16 pixel tile is staged once per 64 channels and the 9 taps are
+# shifted UMMA-descriptor views of it; optional on-the-fly GroupNorm scale/shift + SiLU of the 3x3 segments' input.
+HALO_CASES = {
+    "halo_32px_128to128": dict(sd=2, n=4, sp=(32, 32), segs=[(128, 3)], cout=128),
+    "halo_16px_128to256_bias_temb_res": dict(sd=2, n=4, sp=(16, 16), segs=[(128, 3)], cout=256, use_cadd=True,
+                                             use_res=True),
+    "halo_conv2_plus_1x1_skip_concat": dict(sd=2, n=4, sp=(16, 16), segs=[(256, 3), (256, 1), (128, 1)], cout=256),
+    "halo_concat_3x3_inputs": dict(sd=2, n=3, sp=(32, 32), segs=[(256, 3), (128, 3)], cout=256, use_cadd=True),
+    "halo_28px_ragged_tiles": dict(sd=2, n=3, sp=(28, 28), segs=[(128, 3)], cout=128, use_res=True),
+    "halo_64px_384to128": dict(sd=2, n=2, sp=(64, 64), segs=[(384, 3)], cout=128),
+    "halo_odd_tile_count_16px_256": dict(sd=2, n=5, sp=(16, 24), segs=[(256, 3)], cout=256),
+    "halo_many_tiles_persistent_128": dict(sd=2, n=85, sp=(32, 32), segs=[(128, 3)], cout=128, use_res=True),
+    "halo_many_tiles_persistent_256": dict(sd=2, n=170, sp=(16, 16), segs=[(256, 3), (128, 1)], cout=256,
+                                           use_cadd=True),
+    "halo_512_out_channels": dict(sd=2, n=2, sp=(16, 16), segs=[(128, 3)], cout=512),
+}
+
+
+@pytest.mark.parametrize("gn", [False, True], ids=["raw", "gn_silu_on_the_fly"])
+@pytest.mark.parametrize("name", list(HALO_CASES))
+def test_conv_halo_case(name, gn):
+    rel, mx = _run_case(**HALO_CASES[name], impl=3, gn=gn, stats=True)
+    assert rel < 6e-4, (name, rel, mx)
+    assert mx < 3e-3, (name, rel, mx)
+
+
+def test_conv_halo_matches_im2col_kernel_bitwise():
+    """Same operands, same K order inside a 64-channel chunk per tap but a different tap/chunk interleave: fp32
+    accumulation order differs, so compare within one fp16 ulp; and the fused GroupNorm path against gn_apply + conv."""
+    from ddpm_ood_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n, c, cout, hw = 6, 256, 256, 16
+    x16 = _nhwc(torch.randn((n, c, hw, hw), generator=g, device="cuda"))
+    w = torch.randn((cout, c, 3, 3), generator=g, device="cuda") / (c * 9) ** 0.5
+    wp = torch.zeros(cout, c * 9, dtype=torch.float16, device="cuda")
+    ops.pack_conv_weight(w.contiguous(), wp, 0)
+    gamma = torch.randn(c, generator=g, device="cuda")
+    beta = torch.randn(c, generator=g, device="cuda")
+    # producer statistics of x16 as a conv epilogue would leave them (one part per image here)
+    xq = x16.float().reshape(n, -1, c // 4, 4)
+    st = torch.stack([xq.sum(dim=(1, 3)), (xq * xq).sum(dim=(1, 3))], dim=-1).reshape(n, 1, c // 4, 2).contiguous()
+    z = ops.gn_apply(x16, st, None, None, gamma, beta, 32, 1e-6, silu=True)
+    a = ops.conv_forward([z], [3], wp, cout, impl=0)
+    ab = ops.gn_finalize(st, None, gamma, beta, hw * hw, 32, 1e-6)
+    b = ops.conv_forward([x16], [3], wp, cout, impl=3, gn_scale_shift=ab)
+    torch.cuda.synchronize()
+    d = (a.float() - b.float()).abs()
+    assert (d <= 2.0 ** -10 * a.float().abs().clamp_min(1.0)).all(), d.max().item()
+
+
 if __name__ == "__main__":
-    for name, kw in CASES.items():
+    for name, kw in list(CASES.items()) + [(k, dict(v, impl=3, gn=True, stats=True)) for k, v in HALO_CASES.items()]:
         try:
             rel, mx = _run_case(**kw)
             print(f"{name:40s} rel_l2={rel:.3e} max={mx:.3e}", flush=True)
