@@ -159,15 +159,17 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint
                                 packed[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
                             }
                             uint4* d4 = reinterpret_cast<uint4*>(p.out + pix * static_cast<size_t>(p.Cout) + col0);
+                            if (!(p.dbg & 16)) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                                for (int j = 0; j < 4; ++j)
+                                    d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                            }
                         }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) packed[j] = 0u;
                     }
-                    if (p.stats_out) {
+                    if (p.stats_out && !(p.dbg & 8)) {
                         // per-lane quad sums of the ROUNDED values (what GroupNorm will read back), then a
                         // transpose-reduce over the warp's 32 pixels: 16 shuffles instead of 80.
                         float sv[16];

@@ -66,6 +66,7 @@ struct ConvGemmParams {
     // to output pixel 2*x + p. num_phases == 1: ordinary conv.
     int num_phases;
     int phase3d;
+    int dbg;  // timing experiments only: 8 skip the statistics, 16 skip the output stores (results wrong when set)
 };
 
 // Host side: filled by conv_prepare(), launched by conv_launch().
@@ -109,6 +110,9 @@ struct ConvProblem {
     // statistics come in 2^dims * conv_stats_parts(low-res extents) parts.
     int upsample2;
     int impl;  // 0: pick; 1: single-CTA kernel only (A/B tests of the CTA-pair kernel)
+    // halo kernel only: the 3x3 segments are channel slices of ONE conv weight [Cout][3x3 taps][C_total] (K ordered tap,
+    // then channel over the concatenation) instead of one K block per segment - a conv over torch.cat(inputs, dim=1)
+    int concat3x3;
 };
 
 // Number of GroupNorm-statistics parts per image the epilogue emits for an OUTPUT of this geometry (0: the tile box

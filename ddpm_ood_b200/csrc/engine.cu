@@ -168,6 +168,8 @@ int UNet::init() {
     if (const char* e = getenv("DDPM_UPCONV_PHASES")) upconv_phases_ = atoi(e) != 0;  // A/B switch for tests
     if (const char* e = getenv("DDPM_ATTN_TC")) use_attn_tc_ = atoi(e) != 0;  // A/B switch for tests
     if (const char* e = getenv("DDPM_FUSE_GN")) fuse_gn_stats_ = fuse_gn_stats_ && atoi(e) != 0;  // A/B switch for tests
+    if (const char* e = getenv("DDPM_CONV_HALO")) use_halo_ = atoi(e) != 0;  // A/B switch for tests
+    use_halo_ = use_halo_ && fuse_gn_stats_ && c.spatial_dims == 2;
     in_gemm_ = (c.in_channels % 64 == 0);
     out_gemm_ = (c.out_channels % 128 == 0);
     if (!in_gemm_ && c.in_channels > 8) { set_error("unet: in_channels=%d unsupported (<=8 or multiple of 64)", c.in_channels); return 2; }
@@ -501,7 +503,79 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             q.bias = bias; q.residual = residual; q.out = out;
             gemm(q, -1);
         };
+        // ResnetBlock on the halo-tile kernel: both GroupNorm+SiLU layers are applied inside the consuming conv (the
+        // normalised tensors never exist), each preceded by a tiny statistics -> scale/shift kernel.
+        auto halo_ok = [&](const Act& h, const Act* skip) {
+            if (!use_halo_ || h.parts <= 0 || (skip && skip->parts <= 0)) return false;
+            ConvProblem q{};
+            q.spatial_dims = sd; q.N = N; q.D = h.D; q.H = h.H; q.W = h.W; q.stride = 1; q.n_seg = 1;
+            q.seg[0] = {nullptr, h.C, 3};
+            q.Cout = 128; q.mode = EPI_STORE;
+            return conv_halo_supported(q);
+        };
+        auto finalize_op = [&](const Act& a, const Act* b, const float* g, const float* bt, float* ab) {
+            Op op{};
+            op.type = Op::GN_FINALIZE;
+            op.st0 = a.stats; op.parts0 = a.parts; op.C0 = a.C;
+            op.st1 = b ? b->stats : nullptr; op.parts1 = b ? b->parts : 0; op.C1 = b ? b->C : 0;
+            op.gamma = g; op.beta = bt; op.ab = ab; op.S = static_cast<int>(a.S());
+            op.bytes = static_cast<double>(N) * (a.parts * a.C + (b ? b->parts * b->C : 0)) * 2.0;
+            plan.ops.push_back(op);
+        };
+        auto halo_conv = [&](ConvProblem q, const float* ab, int ab_channels, int temb_off) {
+            Op op{};
+            op.type = Op::CONV_HALO;
+            op.uses_temb = temb_off >= 0;
+            op.temb_off = temb_off;
+            op.flops = conv_flops(q);
+            if (!dry) {
+                int r = conv_halo_prepare(q, ab, ab_channels, sms, &op.halo);
+                if (r && !rc) rc = r;
+            }
+            plan.ops.push_back(op);
+        };
+        auto resblock_halo = [&](const ResW& r, const Act& h, const Act* skip) -> Act {
+            const int cin = r.c0 + r.c1;
+            if (measure) {
+                const size_t ch = static_cast<size_t>(N) * h.S() * r.cout;
+                if (ch > max_h) max_h = ch;
+                return shape_act(r.cout, h.D, h.H, h.W);
+            }
+            const int parts = conv_halo_stats_parts(h.H, h.W);
+            float* ab1 = lay.take<float>(static_cast<size_t>(N) * cin * 2);
+            float* ab2 = lay.take<float>(static_cast<size_t>(N) * r.cout * 2);
+            finalize_op(h, skip, r.g1, r.b1, ab1);
+            Act h1{hB, r.cout, h.D, h.H, h.W, take_stats(r.cout, parts), parts};
+            ConvProblem q{};
+            q.spatial_dims = sd; q.N = N; q.D = h.D; q.H = h.H; q.W = h.W; q.stride = 1;
+            q.n_seg = 1;
+            q.seg[0] = {h.p, h.C, 3};
+            if (skip) q.seg[q.n_seg++] = {skip->p, skip->C, 3};
+            q.concat3x3 = 1;  // conv1's weight is one [cout][9][cin] matrix over cat(h, skip)
+            q.weights = r.w1; q.w_rows = r.cout; q.Cout = r.cout; q.mode = EPI_STORE;
+            q.bias = r.bias1; q.chan_add = plan.temb_all ? plan.temb_all + r.temb_off : nullptr; q.chan_add_stride = P_;
+            q.out = hB; q.stats_out = h1.stats;
+            halo_conv(q, ab1, cin, r.temb_off);
+            finalize_op(h1, nullptr, r.g2, r.b2, ab2);
+            Act out{lay.take<__half>(static_cast<size_t>(N) * h.S() * r.cout), r.cout, h.D, h.H, h.W,
+                    take_stats(r.cout, parts), parts};
+            ConvProblem q2{};
+            q2.spatial_dims = sd; q2.N = N; q2.D = h.D; q2.H = h.H; q2.W = h.W; q2.stride = 1;
+            q2.n_seg = 1;
+            q2.seg[0] = {hB, r.cout, 3};
+            if (r.skip_conv) {
+                q2.seg[q2.n_seg++] = {h.p, h.C, 1};
+                if (skip) q2.seg[q2.n_seg++] = {skip->p, skip->C, 1};
+            } else {
+                q2.residual = h.p;
+            }
+            q2.weights = r.w2; q2.w_rows = r.cout; q2.Cout = r.cout; q2.mode = EPI_STORE;
+            q2.bias = r.bias2_total; q2.out = out.p; q2.stats_out = out.stats;
+            halo_conv(q2, ab2, r.cout, -1);
+            return out;
+        };
         auto resblock = [&](const ResW& r, const Act& h, const Act* skip) -> Act {
+            if (halo_ok(h, skip)) return resblock_halo(r, h, skip);
             const int cin = r.c0 + r.c1;
             if (measure) {
                 const size_t ch = static_cast<size_t>(N) * h.S() * r.cout;
@@ -781,6 +855,17 @@ int UNet::forward(const float* x, const long long* timesteps, int t_uniform, flo
                 }
                 rc = conv_launch(op.conv, stream);
                 break;
+            case Op::GN_FINALIZE:
+                rc = gn_finalize(op.C0, op.st0, op.parts0, op.C1, op.st1, op.parts1, op.gamma, op.beta, op.ab, N, op.S,
+                                 c.norm_num_groups, c.norm_eps, stream);
+                break;
+            case Op::CONV_HALO:
+                if (op.uses_temb) {
+                    op.halo.p.g.chan_add = temb_base + op.temb_off;
+                    op.halo.p.g.chan_add_stride = temb_stride;
+                }
+                rc = conv_halo_launch(op.halo, stream);
+                break;
             case Op::ATTN:
                 rc = op.attn_tc ? attention_tc_launch(op.attn, stream)
                                 : attention_core(op.src0, op.dst, N, op.T, op.C, op.heads, op.scale, stream);
@@ -833,7 +918,9 @@ void UNet::harvest(Plan& plan) {
     for (size_t i = 0; i < n; ++i) {
         const Op& op = plan.ops[i];
         cudaEventElapsedTime(&ms, plan.events[1 + i], plan.events[2 + i]);
-        const int t = static_cast<int>(op.type);
+        // the appended op types report under their families: GroupNorm (2) and tensor-core conv (3)
+        const int t = op.type == Op::GN_FINALIZE ? static_cast<int>(Op::GN)
+                                                 : (op.type == Op::CONV_HALO ? static_cast<int>(Op::GEMM) : static_cast<int>(op.type));
         prof_.ms[t] += ms;
         prof_.flops[t] += op.flops;
         prof_.bytes[t] += op.bytes;

@@ -13,6 +13,7 @@
 
 #include "attention.cuh"
 #include "conv_gemm.cuh"
+#include "conv_halo.cuh"
 #include "kernels.cuh"
 
 namespace ddpm {
@@ -70,7 +71,10 @@ struct ParamSlot {
 };
 
 struct Op {
-    enum Type { CONV_IN_SMALL, CONV_IN_GEMM, GN, GEMM, ATTN, UPSAMPLE, CONV_OUT_SMALL, CONV_OUT_GEMM } type;
+    // GN_FINALIZE / CONV_HALO (appended so the profile indices of the older types stay put): GroupNorm statistics ->
+    // per-(image, channel) scale/shift table, consumed by the halo-tile conv that normalises its input on the fly
+    enum Type { CONV_IN_SMALL, CONV_IN_GEMM, GN, GEMM, ATTN, UPSAMPLE, CONV_OUT_SMALL, CONV_OUT_GEMM, GN_FINALIZE,
+                CONV_HALO } type;
     // GN
     const __half *src0, *src1;
     int C0, C1;
@@ -81,8 +85,10 @@ struct Op {
     __half* dst;
     int S;
     bool silu;
+    float* ab;  // GN_FINALIZE: destination table [N][C0 + C1][2]
     // GEMM
     ConvLaunch conv;
+    ConvHaloLaunch halo;  // CONV_HALO
     bool uses_temb;
     int temb_off;
     // ATTN
@@ -175,6 +181,7 @@ class UNet {
     bool use_attn_tc_ = true;
     bool upconv_phases_ = true;  // nearest-x2 + conv as sub-pixel 2x2 convs (4/9 of the MACs, no upsampled tensor)
     bool fuse_gn_stats_ = true;  // GroupNorm statistics from the producers' epilogues (cpg % 4 == 0 required)
+    bool use_halo_ = true;       // halo-tile conv kernel with GroupNorm+SiLU applied on the fly (2-D, images >= 16 x 8)
     // arenas
     size_t f32_count_ = 0, f16_count_ = 0, f32_used_ = 0, f16_used_ = 0;
     float* f32_arena_ = nullptr;

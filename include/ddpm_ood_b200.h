@@ -72,6 +72,8 @@ typedef struct ddpm_conv_args {
                                 3x3 segments' inputs are normalised on the fly, z = silu(x * scale + shift) -> fp16,
                                 i.e. the conv consumes GroupNorm+SiLU of its raw input without that tensor existing */
     int gn_channels;         /* total channels of the 3x3 segments */
+    int concat3x3;           /* impl 3: the 3x3 segments are channel slices of ONE conv weight [Cout][9][C_total] (a conv
+                                over the channel concatenation of the inputs) instead of one K block per segment */
 } ddpm_conv_args;
 DDPM_API int ddpm_conv_forward(const ddpm_conv_args* args, void* stream);
 /* Parts per image that ddpm_conv_forward emits for an output of this geometry (0: unsupported, use ddpm_gn_silu). */

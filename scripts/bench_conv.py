@@ -32,11 +32,12 @@ def main():
     ap.add_argument("--impls", default="0,3")
     ap.add_argument("--gn", action="store_true")
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--shapes", type=int, default=len(SHAPES), help="only the first n shapes")
     args = ap.parse_args()
     dev = "cuda"
     n = args.batch
     g = torch.Generator(device=dev).manual_seed(0)
-    for name, hw, segs, cout in SHAPES:
+    for name, hw, segs, cout in SHAPES[:args.shapes]:
         ktot = sum(c * k * k for c, k in segs)
         wp = (torch.randn(cout, ktot, generator=g, device=dev) / ktot ** 0.5).half()
         bias = torch.randn(cout, generator=g, device=dev)

@@ -147,6 +147,36 @@ def test_conv_halo_case(name, gn):
     assert mx < 3e-3, (name, rel, mx)
 
 
+@pytest.mark.parametrize("gn", [False, True], ids=["raw", "gn_silu_on_the_fly"])
+def test_conv_halo_concat_inputs_one_weight(gn):
+    """conv3x3(cat(a, b)) + 1x1 skip conv over a third tensor with ONE torch-layout weight for the 3x3 part (K ordered
+    tap, then channel over the concatenation) - ResnetBlock.conv1 of the UNet's up path."""
+    from ddpm_ood_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(11)
+    n, ca, cb, cs, cout, hw = 5, 256, 128, 128, 256, 16
+    xa = _nhwc(torch.randn((n, ca, hw, hw), generator=g, device="cuda"))
+    xb = _nhwc(torch.randn((n, cb, hw, hw), generator=g, device="cuda"))
+    xs = _nhwc(torch.randn((n, cs, hw, hw), generator=g, device="cuda"))
+    w = torch.randn((cout, ca + cb, 3, 3), generator=g, device="cuda") / ((ca + cb) * 9) ** 0.5
+    ws = torch.randn((cout, cs, 1, 1), generator=g, device="cuda") / cs ** 0.5
+    wp = torch.zeros(cout, (ca + cb) * 9 + cs, dtype=torch.float16, device="cuda")
+    ops.pack_conv_weight(w.contiguous(), wp, 0)
+    ops.pack_conv_weight(ws.contiguous(), wp, (ca + cb) * 9)
+    xin = torch.cat([_to_ncx(xa), _to_ncx(xb)], dim=1)
+    ab = None
+    if gn:
+        ab = torch.stack([0.5 + torch.rand((n, ca + cb), generator=g, device="cuda"),
+                          torch.randn((n, ca + cb), generator=g, device="cuda")], dim=-1).contiguous()
+        xin = F.silu(xin * ab[..., 0].view(n, -1, 1, 1) + ab[..., 1].view(n, -1, 1, 1)).half().float()
+    ref = F.conv2d(xin, w.half().float(), padding=1) + F.conv2d(_to_ncx(xs), ws.half().float())
+    out = ops.conv_forward([xa, xb, xs], [3, 3, 1], wp, cout, impl=3, gn_scale_shift=ab, concat3x3=True)
+    torch.cuda.synchronize()
+    got = _to_ncx(out)
+    rel = ((got - ref).norm() / ref.norm()).item()
+    assert rel < 6e-4, rel
+
+
 def test_conv_halo_matches_im2col_kernel_bitwise():
     """Same operands, same K order inside a 64-channel chunk per tap but a different tap/chunk interleave: fp32
     accumulation order differs, so compare within one fp16 ulp; and the fused GroupNorm path against gn_apply + conv."""
