@@ -41,6 +41,7 @@ class ConvArgs(C.Structure):
         ("stats_out", C.c_void_p),
         ("gn_scale_shift", C.c_void_p),
         ("gn_channels", C.c_int),
+        ("gn_no_act", C.c_int),
         ("concat3x3", C.c_int),
     ]
 

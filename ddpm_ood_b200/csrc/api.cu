@@ -117,6 +117,7 @@ int ddpm_conv_forward(const ddpm_conv_args* a, void* stream) {
     q.upsample2 = a->upsample2;
     q.impl = a->impl;
     q.concat3x3 = a->concat3x3;
+    q.gn_silu = a->gn_no_act ? 0 : 1;
     if (a->impl == 3) {
         ddpm::ConvHaloLaunch hl;
         int rc = ddpm::conv_halo_prepare(q, a->gn_scale_shift, a->gn_channels, ddpm::num_sms(), &hl);

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "conv_gemm.cuh"  // set_error, get_encode
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace ddpm {
@@ -44,6 +45,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const __grid_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ptx::pdl_trigger();
     const int head = blockIdx.y;
     const int tok0 = blockIdx.x * 128;                               // first query row of this CTA
     const int key0 = NKB == 1 ? tok0 : (tok0 / (NKB * 128)) * (NKB * 128);  // first key row
@@ -63,6 +65,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const __grid_
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::pdl_wait();
     const uint32_t tmem_s = tmem_base;        // S: NKB * 128 fp32 columns
     const uint32_t tmem_o = tmem_base + 256;  // O: 256 fp32 columns
 
@@ -235,11 +238,11 @@ int attention_tc_launch(const AttnTcLaunch& l, cudaStream_t stream) {
         attr_set = true;
     }
     dim3 grid(l.grid_x, l.heads);
+    cudaError_t e;
     if (l.T == 256)
-        attention_tc_kernel<2><<<grid, kThreads, kSmem, stream>>>(l);
+        e = launch_pdl(attention_tc_kernel<2>, grid, dim3(kThreads), kSmem, stream, l);
     else
-        attention_tc_kernel<1><<<grid, kThreads, kSmem, stream>>>(l);
-    cudaError_t e = cudaGetLastError();
+        e = launch_pdl(attention_tc_kernel<1>, grid, dim3(kThreads), kSmem, stream, l);
     if (e != cudaSuccess) { set_error("attention_tc: launch failed: %s", cudaGetErrorString(e)); return 5; }
     return 0;
 }

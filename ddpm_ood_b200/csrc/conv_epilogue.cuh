@@ -21,10 +21,15 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint
             const int td = t % p.tiles_d; t /= p.tiles_d;
             const int tn = t;
             int r = row;
-            const int w = tw * p.bw + r % p.bw; r /= p.bw;
-            const int h = th * p.bh + r % p.bh; r /= p.bh;
+            int w = tw * p.bw + r % p.bw; r /= p.bw;
+            int h = th * p.bh + r % p.bh; r /= p.bh;
             const int d = td * p.bd + r % p.bd; r /= p.bd;
-            const int n = tn * p.bn + r;
+            int n = tn * p.bn + r;
+            if (p.pair_rows) {  // conv_halo pair tiles: row = h * 16 + n' * 8 + w of images 2 * tile + n'
+                w = row & 7;
+                h = row >> 4;
+                n = m_tile * 2 + ((row >> 3) & 1);
+            }
             const bool valid = (w < p.W) && (h < p.H) && (d < p.D) && (n < p.N);
             size_t pix;
             if (p.num_phases > 1) {  // sub-pixel scatter into the doubled output grid
@@ -93,7 +98,11 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint
                 const float* cadd = p.chan_add ? p.chan_add + static_cast<size_t>(valid ? n : 0) * p.chan_add_stride : nullptr;
                 // GroupNorm partial statistics: all 32 rows of this warp lie in one image (host guarantees it)
                 float* st_base = nullptr;
-                if (p.stats_out) {
+                if (p.stats_out && p.pair_rows) {
+                    // lanes 0-7 / 16-23 hold image 0, lanes 8-15 / 24-31 image 1; part = this warp
+                    const int n_l = m_tile * 2 + ((lane >> 3) & 1);
+                    if (n_l < p.N) st_base = p.stats_out + (static_cast<size_t>(n_l) * p.stats_parts + q) * (p.Cout >> 1);
+                } else if (p.stats_out) {
                     const int R = p.bw * p.bh * p.bd;  // pixels of one image inside the tile box (multiple of 32)
                     const int n_w = tn * p.bn + (q * 32) / R;
                     if (n_w < p.N) {
@@ -180,6 +189,30 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint
                             sv[qd] = (a.x + a.y) + (b.x + b.y);
                             sv[8 + qd] = (a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y);
                         }
+                        if (p.pair_rows) {
+                            // two images per warp: add the two rows of each image (lane ^ 16), then transpose-reduce
+                            // inside the 8-lane groups: 16 + 14 shuffles; lanes 0-15 end with two values each
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) sv[i] += __shfl_xor_sync(0xffffffffu, sv[i], 16);
+#pragma unroll
+                            for (int half_n = 8, off = 4; half_n >= 2; half_n >>= 1, off >>= 1) {
+                                const bool hi = (lane & off) != 0;
+#pragma unroll
+                                for (int i = 0; i < half_n; ++i) {
+                                    const float send = hi ? sv[i] : sv[i + half_n];
+                                    const float keep = hi ? sv[i + half_n] : sv[i];
+                                    sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                                }
+                            }
+                            // value index = b2 b1 b0 j: b2 -> sum / sum of squares, (b1 b0 j) -> quad
+                            if (st_base && lane < 16) {
+#pragma unroll
+                                for (int j = 0; j < 2; ++j) {
+                                    const int quad = (col0 >> 2) + (((lane & 3) << 1) | j);
+                                    st_base[quad * 2 + ((lane >> 2) & 1)] = sv[j];
+                                }
+                            }
+                        } else {
 #pragma unroll
                         for (int half_n = 8, off = 16; half_n >= 1; half_n >>= 1, off >>= 1) {
                             const bool hi = (lane & off) != 0;
@@ -195,6 +228,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint
                         if (st_base && (lane & 1) == 0) {
                             const int quad = (col0 >> 2) + ((lane >> 1) & 7);
                             st_base[quad * 2 + (lane >> 4)] = sv[0];
+                        }
                         }
                     }
                 }

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include "conv_epilogue.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace ddpm {
@@ -53,6 +54,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    ptx::pdl_trigger();
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.n_seg; ++s) ptx::prefetch_tmap(&p.tmA[s]);
@@ -74,6 +76,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::pdl_wait();
 
     const int gpp = (p.num_m_tiles + MT - 1) / MT;  // a work item = MT consecutive M tiles (of one phase) x one N tile
     const int total_tiles = gpp * p.num_phases * p.num_n_tiles;
@@ -232,6 +235,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();  // 0 = leader
+    ptx::pdl_trigger();
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.n_seg; ++s) ptx::prefetch_tmap(&p.tmA[s]);
@@ -254,6 +258,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     ptx::cluster_sync_all();  // the peer's barriers must exist before anything is signalled across the pair
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::pdl_wait();
 
     // work item = 2*MT consecutive M tiles (MT per CTA) of one sub-pixel phase x one N tile
     const int gpp = (p.num_m_tiles + 2 * MT - 1) / (2 * MT);
@@ -574,20 +579,20 @@ int conv_launch(const ConvLaunch& l, cudaStream_t stream) {
         }
         g_attr_set = true;
     }
+    cudaError_t e;
     if (l.cta_pair) {
         if (l.block_n == 256)
-            conv_gemm_2cta_kernel<256, 1><<<l.grid, 256, Cfg2<256, 1>::kSmemBytes, stream>>>(l.p);
+            e = launch_pdl(conv_gemm_2cta_kernel<256, 1>, dim3(l.grid), dim3(256), Cfg2<256, 1>::kSmemBytes, stream, l.p);
         else if (l.m_tiles_per_cta == 2)
-            conv_gemm_2cta_kernel<128, 2><<<l.grid, 256, Cfg2<128, 2>::kSmemBytes, stream>>>(l.p);
+            e = launch_pdl(conv_gemm_2cta_kernel<128, 2>, dim3(l.grid), dim3(256), Cfg2<128, 2>::kSmemBytes, stream, l.p);
         else
-            conv_gemm_2cta_kernel<128, 1><<<l.grid, 256, Cfg2<128, 1>::kSmemBytes, stream>>>(l.p);
+            e = launch_pdl(conv_gemm_2cta_kernel<128, 1>, dim3(l.grid), dim3(256), Cfg2<128, 1>::kSmemBytes, stream, l.p);
     } else if (l.block_n == 256)
-        conv_gemm_kernel<256, 1><<<l.grid, 256, Cfg<256, 1>::kSmemBytes, stream>>>(l.p);
+        e = launch_pdl(conv_gemm_kernel<256, 1>, dim3(l.grid), dim3(256), Cfg<256, 1>::kSmemBytes, stream, l.p);
     else if (l.m_tiles_per_cta == 2)
-        conv_gemm_kernel<128, 2><<<l.grid, 256, Cfg<128, 2>::kSmemBytes, stream>>>(l.p);
+        e = launch_pdl(conv_gemm_kernel<128, 2>, dim3(l.grid), dim3(256), Cfg<128, 2>::kSmemBytes, stream, l.p);
     else
-        conv_gemm_kernel<128, 1><<<l.grid, 256, Cfg<128, 1>::kSmemBytes, stream>>>(l.p);
-    cudaError_t e = cudaGetLastError();
+        e = launch_pdl(conv_gemm_kernel<128, 1>, dim3(l.grid), dim3(256), Cfg<128, 1>::kSmemBytes, stream, l.p);
     if (e != cudaSuccess) { set_error("conv: launch failed: %s", cudaGetErrorString(e)); return 5; }
     return 0;
 }

@@ -66,6 +66,7 @@ struct ConvGemmParams {
     // to output pixel 2*x + p. num_phases == 1: ordinary conv.
     int num_phases;
     int phase3d;
+    int pair_rows;  // conv_halo pair tiles: accumulator row m = h * 16 + n' * 8 + w of images 2 * tile + n' (<= 8 x 8)
     int dbg;  // timing experiments only: 8 skip the statistics, 16 skip the output stores (results wrong when set)
 };
 
@@ -113,6 +114,7 @@ struct ConvProblem {
     // halo kernel only: the 3x3 segments are channel slices of ONE conv weight [Cout][3x3 taps][C_total] (K ordered tap,
     // then channel over the concatenation) instead of one K block per segment - a conv over torch.cat(inputs, dim=1)
     int concat3x3;
+    int gn_silu;  // halo kernel with a scale/shift table: 1 = GroupNorm + SiLU, 0 = GroupNorm only
 };
 
 // Number of GroupNorm-statistics parts per image the epilogue emits for an OUTPUT of this geometry (0: the tile box

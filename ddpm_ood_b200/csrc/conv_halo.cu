@@ -5,15 +5,24 @@
 #include <string.h>
 
 #include "conv_epilogue.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace ddpm {
 
 namespace {
 
-constexpr int kTileW = 8, kTileH = 16;              // output pixels of one M tile (one image region)
-constexpr int kHaloRows = (kTileW + 2) * (kTileH + 2);  // 180 input pixels around it
-constexpr int kATileBytes = 23 * 1024;              // 180 rows x 128 B = 23040, padded to the 1024-B swizzle period
+// Two tile geometries, both 128 output pixels whose A rows are 16 groups of 8 consecutive pixels (one image row piece)
+// at a CONSTANT shared-memory stride - what a UMMA descriptor can express:
+//  * region tiles (images taller than 8 rows): 8 (w) x 16 (h) pixels of ONE image; haloed input 10 x 18 = 180 rows,
+//    row = h' * 10 + w';
+//  * pair tiles (images up to 8 x 8): TWO whole images, rows interleaved by image: A row m = h * 16 + n' * 8 + w and
+//    haloed input row = (h' * 2 + n') * 10 + w' (TMA box over dims (C, W, N, H)): 200 rows. Interleaving is what keeps
+//    the group stride constant (10 rows) across the image boundary.
+constexpr int kTileW = 8, kTileH = 16;
+constexpr int kHaloRowsRegion = (kTileW + 2) * (kTileH + 2);  // 180
+constexpr int kHaloRowsPair = 2 * 10 * 10;                    // 200
+constexpr int kATileBytes = 25 * 1024;              // 200 rows x 128 B, a multiple of the 1024-B swizzle period
 constexpr int kAStages = 3;
 constexpr int kMaxGnChannels = 512;  // 3x3-segment channels a (scale, shift) row may hold
 // Warp roles. The single-lane roles sit at the HIGHEST warp ids: the SM's warp arbiter prefers high warp ids
@@ -32,7 +41,7 @@ struct HCfg {
     static constexpr int kBStages = 8;
     static constexpr int kAccCols = MT * BN;
     static constexpr int kTmemCols = 2 * kAccCols;
-    static constexpr int kAbBytes = MT * kMaxGnChannels * 8;  // per-item (scale, shift) rows of the MT tiles' images
+    static constexpr int kAbBytes = 2 * kMaxGnChannels * 8;  // per-item (scale, shift) rows of the (up to 2) images
     static constexpr int kSmemBytes =
         kAStages * kAStageBytes + kBStages * kBHalfBytes + kAbBytes + 1024 /*align*/ + 512 /*barriers*/;
     static_assert(kTmemCols <= 512, "TMEM");
@@ -79,6 +88,16 @@ __device__ __forceinline__ float silu_affine(float x, float a, float b, float a2
     return y * rcp_approx(d);
 }
 
+// GroupNorm without activation (the AttentionBlock norm): z = x * a + b
+__device__ __forceinline__ void affine_chunk(uint4& raw, const float (&ga)[8], const float (&gb)[8]) {
+    __half2* h2 = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h2[e]);
+        h2[e] = __floats2half2_rn(fmaf(f.x, ga[2 * e], gb[2 * e]), fmaf(f.y, ga[2 * e + 1], gb[2 * e + 1]));
+    }
+}
+
 // 8 channels of one haloed-tile pixel (one 16-byte chunk), in registers
 __device__ __forceinline__ void transform_chunk(uint4& raw, const float (&ga)[8], const float (&gb)[8],
                                                 const float (&ga2)[8], const float (&gb2)[8]) {
@@ -93,16 +112,38 @@ __device__ __forceinline__ void transform_chunk(uint4& raw, const float (&ga)[8]
 
 }  // namespace
 
-template <int BN, int MT>
+// Rows a transform thread visits. Region tiles: row = (tid >> 3) + 32 i. Pair tiles: threads 0-127 own image 0,
+// 128-255 image 1; pixel k = ((tid & 127) >> 3) + 16 i of the (haloed) image sits in row ((k / wbox) * 2 + image) * wbox
+// + k % wbox. Returns the tile row and the pixel's coordinates inside the (haloed) box.
+template <bool PAIR>
+__device__ __forceinline__ void xform_row(int tid, int i, bool halo, int& row, int& hh, int& ww, bool& ok) {
+    if (PAIR) {
+        const int wbox = halo ? 10 : 8;
+        const int k = ((tid & 127) >> 3) + 16 * i;
+        hh = k / wbox;
+        ww = k - hh * wbox;
+        row = (hh * 2 + (tid >> 7)) * wbox + ww;
+        ok = k < wbox * wbox;
+    } else {
+        const int wbox = halo ? kTileW + 2 : kTileW;
+        row = (tid >> 3) + 32 * i;
+        hh = row / wbox;
+        ww = row - hh * wbox;
+        ok = row < (halo ? kHaloRowsRegion : kTileW * kTileH);
+    }
+}
+
+template <int BN, int MT, bool PAIR>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     conv_halo_kernel(const __grid_constant__ ConvHaloParams hp) {
+    static_assert(!PAIR || MT == 1, "pair tiles: one M tile per CTA");
     using C = HCfg<BN, MT>;
     const ConvGemmParams& p = hp.g;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;                                   // [kAStages][MT][23 KB]
     uint8_t* smem_b = smem + kAStages * C::kAStageBytes;      // [kBStages][BN/2 rows x 128 B]
-    float2* s_ab = reinterpret_cast<float2*>(smem_b + C::kBStages * C::kBHalfBytes);  // [MT][kMaxGnChannels]
+    float2* s_ab = reinterpret_cast<float2*>(smem_b + C::kBStages * C::kBHalfBytes);  // [2][kMaxGnChannels]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + C::kBStages * C::kBHalfBytes + C::kAbBytes);
     uint64_t* a_full = bars;                      // per CTA: TMA -> transform warps
     uint64_t* a_ready = a_full + kAStages;        // leader's copy: transform warps of both CTAs -> MMA
@@ -116,6 +157,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
+    ptx::pdl_trigger();
 
     if (warp == kWarpA && lane == 0) {
         for (int s = 0; s < p.n_seg; ++s) ptx::prefetch_tmap(&p.tmA[s]);
@@ -143,6 +185,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     ptx::cluster_sync_all();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::pdl_wait();  // everything above overlapped the previous kernel's tail
 
     // work item = 2*MT consecutive M tiles (MT per CTA) x one N tile; N tiles of the same pixels run on neighbouring
     // clusters at the same time (the second read of the input hits L2).
@@ -161,25 +204,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 const int t = (m_group * 2 + static_cast<int>(rank)) * MT + mt;  // past-the-end tiles read zeros
-                const int n = t / tiles_per_img;
-                const int r = t - n * tiles_per_img;
-                const int th = r / p.tiles_w;
-                w0[mt] = (r - th * p.tiles_w) * kTileW;
-                h0[mt] = th * kTileH;
-                n0[mt] = n;
+                if (PAIR) {
+                    w0[mt] = 0; h0[mt] = 0; n0[mt] = 2 * t;
+                } else {
+                    const int n = t / tiles_per_img;
+                    const int r = t - n * tiles_per_img;
+                    const int th = r / p.tiles_w;
+                    w0[mt] = (r - th * p.tiles_w) * kTileW;
+                    h0[mt] = th * kTileH;
+                    n0[mt] = n;
+                }
             }
             for (int seg = 0; seg < p.n_seg; ++seg) {
                 const int halo = hp.seg_taps[seg] == 9 ? 1 : 0;
-                const uint32_t bytes = (halo ? kHaloRows : kTileW * kTileH) * 128u;
+                const uint32_t bytes = (halo ? (PAIR ? kHaloRowsPair : kHaloRowsRegion) : kTileW * kTileH) * 128u;
                 const CUtensorMap* ma = seg == 0 ? &p.tmA[0] : (seg == 1 ? &p.tmA[1] : &p.tmA[2]);
                 for (int chunk = 0; chunk < p.seg_chunks[seg]; ++chunk) {
                     ptx::mbar_wait(&a_empty[sa], pa ^ 1);
                     if (ptx::elect_one()) {
                         ptx::mbar_arrive_expect_tx(&a_full[sa], MT * bytes);
 #pragma unroll
-                        for (int mt = 0; mt < MT; ++mt)
-                            ptx::tma_load_5d(smem_a + sa * C::kAStageBytes + mt * kATileBytes, ma, &a_full[sa],
-                                             chunk * kBlockK, w0[mt] - halo, h0[mt] - halo, 0, n0[mt]);
+                        for (int mt = 0; mt < MT; ++mt) {
+                            uint8_t* dst = smem_a + sa * C::kAStageBytes + mt * kATileBytes;
+                            if (PAIR)  // tensor map dims (C, W, N, H, 1)
+                                ptx::tma_load_5d(dst, ma, &a_full[sa], chunk * kBlockK, -halo, n0[mt], -halo, 0);
+                            else               // tensor map dims (C, W, H, 1, N)
+                                ptx::tma_load_5d(dst, ma, &a_full[sa], chunk * kBlockK, w0[mt] - halo, h0[mt] - halo, 0,
+                                                 n0[mt]);
+                        }
                     }
                     __syncwarp();
                     if (++sa == kAStages) { sa = 0; pa ^= 1; }
@@ -232,7 +284,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                         const uint32_t a_base = ptx::smem_u32(smem_a + sa * C::kAStageBytes);
                         for (int tap = 0; tap < taps; ++tap) {
                             // tap (dh, dw): rows (h + 1 + dh) * pitch + (w + 1 + dw) of the haloed tile
-                            const uint32_t row0 = taps == 9 ? (tap / 3) * pitch + (tap % 3) : 0;
+                            const uint32_t row0 = taps == 9 ? (tap / 3) * (PAIR ? 2 * pitch : pitch) + (tap % 3) : 0;
                             const uint64_t da0 = desc_hi | ((a_base + row0 * 128) >> 4);
                             const uint64_t db0 = ptx::make_desc_k128(ptx::smem_u32(smem_b + sb * C::kBHalfBytes));
                             ptx::mbar_wait(&b_full[sb], pb);
@@ -262,74 +314,86 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             }
         }
     } else if (warp >= kXformWarp0 && warp < kXformWarp0 + kXformWarps) {
-        // ================================================================= transform: GroupNorm scale/shift + SiLU, in place
-        // thread -> 8 channels (one 16-byte chunk of every row it visits) x rows (tid >> 3) + 32 i; the 8 lanes of a row
-        // cover its 128 bytes (a permutation of the swizzled chunks): conflict-free.
+        // ================================================================= transform: GroupNorm scale/shift (+ SiLU), in place
+        // thread -> 8 channels (one 16-byte chunk of every row it visits, see xform_row); the 8 lanes that share a row
+        // cover its 128 bytes (a permutation of the swizzled chunks): conflict-free. Scale/shift slot: region tiles mt,
+        // pair tiles the thread's image.
         const int tid = threadIdx.x - kXformWarp0 * 32;
         const int cg = tid & 7;
-        const int r_first = tid >> 3;
-        constexpr int kRowStep = kXformWarps * 4;
-        constexpr int kRowIters = (kHaloRows + kRowStep - 1) / kRowStep;  // 6
+        constexpr int kRowIters = PAIR ? 7 : 6;
         constexpr float kNegLog2e = -1.4426950408889634f;
         const bool any_gn = hp.ab != nullptr && !(hp.dbg & 1);
         const uint32_t smem_a_u32 = ptx::smem_u32(smem_a);
-        // byte offset of this thread's chunk in row r_first + 32 i (the swizzle XOR depends on the row only)
-        uint32_t row_off[kRowIters];
-#pragma unroll
-        for (int i = 0; i < kRowIters; ++i) {
-            const int row = r_first + i * kRowStep;
-            row_off[i] = row * 128 + ((cg ^ (row & 7)) << 4);
-        }
+        const int slot_of_thread = PAIR ? (tid >> 7) : 0;
         int sa = 0;
         uint32_t pa = 0;
         for (int item = cluster_id; item < total_items; item += num_clusters) {
             const int m_group = item / p.num_n_tiles;
-            uint32_t valid_mask[MT];  // bit i: row r_first + 32 i is a pixel inside the image (padding must stay zero)
+            // validity of this thread's rows of a HALOED tile (zero padding must stay zero), per M tile
+            uint32_t mask_halo[MT];
+            int tn[MT], th0[MT], tw0[MT];
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 const int t = (m_group * 2 + static_cast<int>(rank)) * MT + mt;
-                const int n = t / tiles_per_img;
-                const int r = t - n * tiles_per_img;
-                const int th = r / p.tiles_w;
-                const int w0 = (r - th * p.tiles_w) * kTileW - 1;
-                const int h0 = th * kTileH - 1;
+                if (PAIR) {
+                    tn[mt] = 2 * t + (tid >> 7); th0[mt] = 0; tw0[mt] = 0;
+                } else {
+                    const int n = t / tiles_per_img;
+                    const int r = t - n * tiles_per_img;
+                    const int th = r / p.tiles_w;
+                    tn[mt] = n; th0[mt] = th * kTileH; tw0[mt] = (r - th * p.tiles_w) * kTileW;
+                }
                 uint32_t m = 0;
-                if (n < p.N) {
+                if (tn[mt] < p.N) {
 #pragma unroll
                     for (int i = 0; i < kRowIters; ++i) {
-                        const int row = r_first + i * kRowStep;
-                        const int hh = row / (kTileW + 2);
-                        const int ww = row - hh * (kTileW + 2);
-                        const int gh = h0 + hh, gw = w0 + ww;
-                        if (row < kHaloRows && gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) m |= 1u << i;
+                        int row, hh, ww;
+                        bool ok;
+                        xform_row<PAIR>(tid, i, true, row, hh, ww, ok);
+                        const int gh = th0[mt] + hh - 1, gw = tw0[mt] + ww - 1;
+                        if (ok && gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) m |= 1u << i;
                     }
                 }
-                valid_mask[mt] = m;
+                mask_halo[mt] = m;
             }
             if (any_gn) {
                 // (scale, shift) rows of this item's images -> shared memory (read once per item, not once per stage)
                 asm volatile("bar.sync 1, %0;" ::"n"(kXformWarps * 32) : "memory");  // previous item's readers are done
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    const int n = ((m_group * 2 + static_cast<int>(rank)) * MT + mt) / tiles_per_img;
+                for (int slot = 0; slot < 2; ++slot) {
+                    int n;
+                    if (PAIR) n = 2 * ((m_group * 2 + static_cast<int>(rank)) * MT) + slot;
+                    else n = slot < MT ? ((m_group * 2 + static_cast<int>(rank)) * MT + slot) / tiles_per_img : p.N;
                     if (n < p.N) {
                         const float2* src = hp.ab + static_cast<size_t>(n) * hp.ab_C;
-                        for (int c = tid; c < hp.ab_C; c += kXformWarps * 32) s_ab[mt * kMaxGnChannels + c] = __ldg(src + c);
+                        for (int c = tid; c < hp.ab_C; c += kXformWarps * 32) s_ab[slot * kMaxGnChannels + c] = __ldg(src + c);
                     }
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kXformWarps * 32) : "memory");
             }
             for (int seg = 0; seg < p.n_seg; ++seg) {
-                const bool gn = hp.seg_gn[seg] != 0 && !(hp.dbg & 1);
+                const int gn = (hp.dbg & 1) ? 0 : hp.seg_gn[seg];
+                const bool halo = hp.seg_taps[seg] == 9;
                 for (int chunk = 0; chunk < p.seg_chunks[seg]; ++chunk) {
                     if (gn) {
                         const uint32_t ab_chunk = ptx::smem_u32(s_ab + hp.seg_ab_off[seg] + chunk * kBlockK + cg * 8);
 #pragma unroll
                         for (int mt = 0; mt < MT; ++mt) {
+                            uint32_t off[kRowIters];
+                            uint32_t m = halo ? mask_halo[mt] : 0u;
+#pragma unroll
+                            for (int i = 0; i < kRowIters; ++i) {
+                                int row, hh, ww;
+                                bool ok;
+                                xform_row<PAIR>(tid, i, halo, row, hh, ww, ok);
+                                off[i] = row * 128 + ((cg ^ (row & 7)) << 4);
+                                if (!halo && ok && tn[mt] < p.N && th0[mt] + hh < p.H && tw0[mt] + ww < p.W) m |= 1u << i;
+                            }
+                            const int slot = PAIR ? slot_of_thread : mt;
                             float ga[8], gb[8], ga2[8], gb2[8];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const uint4 v = lds128(ab_chunk + (mt * kMaxGnChannels * 8 + j * 16));
+                                const uint4 v = lds128(ab_chunk + (slot * kMaxGnChannels * 8 + j * 16));
                                 ga[2 * j] = __uint_as_float(v.x); gb[2 * j] = __uint_as_float(v.y);
                                 ga[2 * j + 1] = __uint_as_float(v.z); gb[2 * j + 1] = __uint_as_float(v.w);
                             }
@@ -337,17 +401,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                             for (int j = 0; j < 8; ++j) { ga2[j] = ga[j] * kNegLog2e; gb2[j] = gb[j] * kNegLog2e; }
                             if (mt == 0) ptx::mbar_wait(&a_full[sa], pa);
                             const uint32_t tile = smem_a_u32 + sa * C::kAStageBytes + mt * kATileBytes;
-                            const uint32_t m = valid_mask[mt];
-                            // all loads first (6 rows in flight), then the math, then the stores
+                            // all loads first (6-7 rows in flight), then the math, then the stores
                             uint4 raw[kRowIters];
 #pragma unroll
                             for (int i = 0; i < kRowIters; ++i)
-                                if (m & (1u << i)) raw[i] = lds128(tile + row_off[i]);
+                                if (m & (1u << i)) raw[i] = lds128(tile + off[i]);
 #pragma unroll
                             for (int i = 0; i < kRowIters; ++i) {
                                 if (m & (1u << i)) {
-                                    transform_chunk(raw[i], ga, gb, ga2, gb2);
-                                    sts128(tile + row_off[i], raw[i]);
+                                    if (gn == 1) transform_chunk(raw[i], ga, gb, ga2, gb2);
+                                    else affine_chunk(raw[i], ga, gb);
+                                    sts128(tile + off[i], raw[i]);
                                 }
                             }
                         }
@@ -394,20 +458,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+static bool pair_tiles(const ConvProblem& q) { return q.H <= 8 && q.W <= 8; }
+
 bool conv_halo_supported(const ConvProblem& q) {
     if (q.spatial_dims != 2 || q.D != 1 || q.stride != 1 || q.upsample2 || q.mode != EPI_STORE || q.b_rows_per_mtile)
         return false;
-    if (q.n_seg < 1 || q.n_seg > kMaxSeg || q.seg[0].ksize != 3) return false;
+    if (q.n_seg < 1 || q.n_seg > kMaxSeg) return false;
     for (int s = 0; s < q.n_seg; ++s) {
         if (q.seg[s].channels % kBlockK != 0) return false;
         if (q.seg[s].ksize != 3 && q.seg[s].ksize != 1) return false;
     }
     if (q.Cout % 128 != 0) return false;
-    // a tile is an 8 x 16 region of ONE image: images shorter than 16 rows waste the tensor pipe on padding
-    return q.H >= kTileH && q.W >= kTileW;
+    // images up to 8 x 8: a tile is two whole images (one M tile per CTA: 256-wide N tiles only);
+    // larger images: a tile is an 8 x 16 region of one image
+    if (pair_tiles(q)) return q.Cout % 256 == 0;
+    return true;
 }
 
 int conv_halo_stats_parts(int H, int W) {
+    if (H <= 8 && W <= 8) return 4;
     return ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH) * 4;
 }
 
@@ -418,14 +487,17 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab, int gn_ab_channe
     memset(out, 0, sizeof(*out));
     ConvHaloParams& hp = out->p;
     ConvGemmParams& p = hp.g;
+    const bool pair = pair_tiles(q);
+    hp.pair_mode = pair ? 1 : 0;
+    p.pair_rows = pair ? 1 : 0;
     p.N = q.N; p.D = 1; p.H = q.H; p.W = q.W;
     p.stride = 1;
     p.bw = kTileW; p.bh = kTileH; p.bd = 1; p.bn = 1;
-    p.tiles_w = (q.W + kTileW - 1) / kTileW;
-    p.tiles_h = (q.H + kTileH - 1) / kTileH;
+    p.tiles_w = pair ? 1 : (q.W + kTileW - 1) / kTileW;
+    p.tiles_h = pair ? 1 : (q.H + kTileH - 1) / kTileH;
     p.tiles_d = 1;
-    p.tiles_n = q.N;
-    p.num_m_tiles = p.tiles_w * p.tiles_h * q.N;
+    p.tiles_n = pair ? (q.N + 1) / 2 : q.N;
+    p.num_m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     const int BN = (q.Cout % 256 == 0) ? 256 : 128;
     out->block_n = BN;
     out->m_tiles_per_cta = BN == 256 ? 1 : 2;
@@ -441,7 +513,7 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab, int gn_ab_channe
     p.stats_out = q.stats_out;
     p.stats_parts = q.stats_out ? conv_halo_stats_parts(q.H, q.W) : 0;
     p.n_seg = q.n_seg;
-    int kcol = 0, ab_off = 0, kb = 0;
+    int kcol = 0, ab_off = 0, kb = 0, c3_off = 0;
     int total3 = 0;  // channels of all 3x3 segments
     for (int s = 0; s < q.n_seg; ++s) total3 += q.seg[s].ksize == 3 ? q.seg[s].channels : 0;
     if (q.concat3x3) {
@@ -449,6 +521,9 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab, int gn_ab_channe
             if (q.seg[s].ksize == 3 && q.seg[s - 1].ksize != 3) { set_error("conv_halo: concat3x3 needs the 3x3 segments first"); return 2; }
         }
     }
+    // which segments are normalised on the fly: the 3x3 ones, or a leading 1x1 segment of a conv without 3x3 segments
+    // (the AttentionBlock norm in front of the q/k/v Linear)
+    const bool gn_on_1x1 = gn_ab && total3 == 0;
     for (int s = 0; s < q.n_seg; ++s) {
         const ConvSegment& g = q.seg[s];
         const int taps = g.ksize == 3 ? 9 : 1;
@@ -460,25 +535,32 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab, int gn_ab_channe
         hp.seg_taps[s] = taps;
         if (q.concat3x3 && taps == 9) {
             hp.seg_cin[s] = total3;     // tap stride along K
-            hp.seg_kcol0[s] = ab_off;   // channel offset inside the concatenation
+            hp.seg_kcol0[s] = c3_off;   // channel offset inside the concatenation
             kcol = 9 * total3;          // 1x1 segments follow the whole 3x3 block
         } else {
             hp.seg_cin[s] = g.channels;
             hp.seg_kcol0[s] = kcol;
             kcol += taps * g.channels;
         }
-        hp.seg_gn[s] = (gn_ab && taps == 9) ? 1 : 0;
+        const bool normalised = gn_ab && (taps == 9 || (gn_on_1x1 && s == 0));
+        hp.seg_gn[s] = normalised ? (q.gn_silu ? 1 : 2) : 0;
         hp.seg_ab_off[s] = ab_off;
-        if (taps == 9) ab_off += g.channels;
-        cuuint64_t gdim[5] = {static_cast<cuuint64_t>(g.channels), static_cast<cuuint64_t>(q.W),
-                              static_cast<cuuint64_t>(q.H), 1, static_cast<cuuint64_t>(q.N)};
-        cuuint64_t gstr[4];
-        gstr[0] = static_cast<cuuint64_t>(g.channels) * 2;
-        gstr[1] = gstr[0] * q.W;
-        gstr[2] = gstr[1] * q.H;
-        gstr[3] = gstr[2];
+        if (normalised) ab_off += g.channels;
+        if (taps == 9) c3_off += g.channels;
         const cuuint32_t halo = taps == 9 ? 2 : 0;
-        cuuint32_t box[5] = {kBlockK, kTileW + halo, kTileH + halo, 1, 1};
+        const cuuint64_t row_bytes = static_cast<cuuint64_t>(g.channels) * 2;
+        cuuint64_t gdim[5], gstr[4];
+        cuuint32_t box[5];
+        if (pair) {  // (C, W, N, H, 1): the box interleaves the rows of two images
+            gdim[0] = g.channels; gdim[1] = q.W; gdim[2] = q.N; gdim[3] = q.H; gdim[4] = 1;
+            gstr[0] = row_bytes; gstr[1] = row_bytes * q.W * q.H; gstr[2] = row_bytes * q.W;
+            gstr[3] = row_bytes * q.W * q.H * q.N;
+            box[0] = kBlockK; box[1] = 8 + halo; box[2] = 2; box[3] = 8 + halo; box[4] = 1;
+        } else {     // (C, W, H, 1, N)
+            gdim[0] = g.channels; gdim[1] = q.W; gdim[2] = q.H; gdim[3] = 1; gdim[4] = q.N;
+            gstr[0] = row_bytes; gstr[1] = row_bytes * q.W; gstr[2] = row_bytes * q.W * q.H; gstr[3] = gstr[2];
+            box[0] = kBlockK; box[1] = kTileW + halo; box[2] = kTileH + halo; box[3] = 1; box[4] = 1;
+        }
         cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         CUresult r = encode(&p.tmA[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(g.ptr), gdim, gstr, box,
                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -487,7 +569,7 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab, int gn_ab_channe
     }
     p.num_kb = kb;
     if (gn_ab && ab_off != gn_ab_channels) {
-        set_error("conv_halo: scale/shift table has %d channels, the 3x3 segments %d", gn_ab_channels, ab_off);
+        set_error("conv_halo: scale/shift table has %d channels, the normalised segments %d", gn_ab_channels, ab_off);
         return 2;
     }
     if (gn_ab && gn_ab_channels > kMaxGnChannels) {
@@ -521,21 +603,28 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab, int gn_ab_channe
 int conv_halo_launch(const ConvHaloLaunch& l, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e1 = cudaFuncSetAttribute(conv_halo_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e1 = cudaFuncSetAttribute(conv_halo_kernel<256, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               HCfg<256, 1>::kSmemBytes);
-        cudaError_t e2 = cudaFuncSetAttribute(conv_halo_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e2 = cudaFuncSetAttribute(conv_halo_kernel<128, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               HCfg<128, 2>::kSmemBytes);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) {
-            set_error("conv_halo: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-            return 4;
+        cudaError_t e3 = cudaFuncSetAttribute(conv_halo_kernel<256, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              HCfg<256, 1>::kSmemBytes);
+        const cudaError_t es[3] = {e1, e2, e3};
+        for (cudaError_t e : es) {
+            if (e != cudaSuccess) {
+                set_error("conv_halo: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+                return 4;
+            }
         }
         attr_set = true;
     }
-    if (l.block_n == 256)
-        conv_halo_kernel<256, 1><<<l.grid, kThreads, HCfg<256, 1>::kSmemBytes, stream>>>(l.p);
+    cudaError_t e;
+    if (l.p.pair_mode)
+        e = launch_pdl(conv_halo_kernel<256, 1, true>, dim3(l.grid), dim3(kThreads), HCfg<256, 1>::kSmemBytes, stream, l.p);
+    else if (l.block_n == 256)
+        e = launch_pdl(conv_halo_kernel<256, 1, false>, dim3(l.grid), dim3(kThreads), HCfg<256, 1>::kSmemBytes, stream, l.p);
     else
-        conv_halo_kernel<128, 2><<<l.grid, kThreads, HCfg<128, 2>::kSmemBytes, stream>>>(l.p);
-    cudaError_t e = cudaGetLastError();
+        e = launch_pdl(conv_halo_kernel<128, 2, false>, dim3(l.grid), dim3(kThreads), HCfg<128, 2>::kSmemBytes, stream, l.p);
     if (e != cudaSuccess) { set_error("conv_halo: launch failed: %s", cudaGetErrorString(e)); return 5; }
     return 0;
 }

@@ -30,10 +30,11 @@ struct ConvHaloParams {
     int seg_taps[kMaxSeg];    // 9 or 1
     int seg_cin[kMaxSeg];     // channels of the segment (tap stride along K)
     int seg_kcol0[kMaxSeg];   // first K column of the segment in the weight matrix
-    int seg_gn[kMaxSeg];      // 1: apply silu(x * a + b) to this segment's input tile
+    int seg_gn[kMaxSeg];      // 1: apply silu(x * a + b) to this segment's input tile, 2: x * a + b (no activation)
     int seg_ab_off[kMaxSeg];  // channel offset of the segment in the scale/shift table
     const float2* ab;         // [N][ab_C] (scale, shift) per image and input channel, or null
     int ab_C;
+    int pair_mode;            // 1: tiles are two whole images of up to 8 x 8 pixels (rows interleaved by image)
     int dbg;                  // timing experiments only (env DDPM_HALO_DBG): 1 skip transform math, 2 skip epilogue
                               // body, 4 skip the MMAs; results are wrong when non-zero
 };
@@ -45,7 +46,7 @@ struct ConvHaloLaunch {
     int grid;
 };
 
-// stride-1 2-D problems whose first segment is 3x3, store epilogue, images at least 16 x 8 pixels
+// stride-1 2-D problems of 3x3 / 1x1 segments, store epilogue; images of up to 8 x 8 pixels need Cout % 256 == 0
 bool conv_halo_supported(const ConvProblem& q);
 // GroupNorm-statistics parts per image emitted by this kernel's epilogue for an H x W output
 int conv_halo_stats_parts(int H, int W);

@@ -505,12 +505,13 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
         };
         // ResnetBlock on the halo-tile kernel: both GroupNorm+SiLU layers are applied inside the consuming conv (the
         // normalised tensors never exist), each preceded by a tiny statistics -> scale/shift kernel.
-        auto halo_ok = [&](const Act& h, const Act* skip) {
+        auto halo_ok = [&](const Act& h, const Act* skip, int cout) {
             if (!use_halo_ || h.parts <= 0 || (skip && skip->parts <= 0)) return false;
+            if (h.C + (skip ? skip->C : 0) > 512) return false;  // scale/shift rows the kernel stages in shared memory
             ConvProblem q{};
             q.spatial_dims = sd; q.N = N; q.D = h.D; q.H = h.H; q.W = h.W; q.stride = 1; q.n_seg = 1;
             q.seg[0] = {nullptr, h.C, 3};
-            q.Cout = 128; q.mode = EPI_STORE;
+            q.Cout = cout; q.mode = EPI_STORE;
             return conv_halo_supported(q);
         };
         auto finalize_op = [&](const Act& a, const Act* b, const float* g, const float* bt, float* ab) {
@@ -552,6 +553,7 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             q.seg[0] = {h.p, h.C, 3};
             if (skip) q.seg[q.n_seg++] = {skip->p, skip->C, 3};
             q.concat3x3 = 1;  // conv1's weight is one [cout][9][cin] matrix over cat(h, skip)
+            q.gn_silu = 1;
             q.weights = r.w1; q.w_rows = r.cout; q.Cout = r.cout; q.mode = EPI_STORE;
             q.bias = r.bias1; q.chan_add = plan.temb_all ? plan.temb_all + r.temb_off : nullptr; q.chan_add_stride = P_;
             q.out = hB; q.stats_out = h1.stats;
@@ -571,11 +573,12 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             }
             q2.weights = r.w2; q2.w_rows = r.cout; q2.Cout = r.cout; q2.mode = EPI_STORE;
             q2.bias = r.bias2_total; q2.out = out.p; q2.stats_out = out.stats;
+            q2.gn_silu = 1;
             halo_conv(q2, ab2, r.cout, -1);
             return out;
         };
         auto resblock = [&](const ResW& r, const Act& h, const Act* skip) -> Act {
-            if (halo_ok(h, skip)) return resblock_halo(r, h, skip);
+            if (halo_ok(h, skip, r.cout)) return resblock_halo(r, h, skip);
             const int cin = r.c0 + r.c1;
             if (measure) {
                 const size_t ch = static_cast<size_t>(N) * h.S() * r.cout;
@@ -604,8 +607,24 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
                 const size_t ch = static_cast<size_t>(rows) * a.C;
                 if (ch > max_h) max_h = ch;
             }
-            gn(h, nullptr, a.g, a.b, zA, false);
-            linear(zA, rows, a.C, a.wqkv, a.bqkv, 3 * a.C, nullptr, qkv);
+            // (measured slower than gn_apply + the im2col GEMM for the 3-N-tile q/k/v projection: off unless asked for)
+            static const bool fuse_attn_norm = getenv("DDPM_ATTN_NORM_FUSE") && atoi(getenv("DDPM_ATTN_NORM_FUSE")) != 0;
+            if (!measure && fuse_attn_norm && halo_ok(h, nullptr, 3 * a.C)) {
+                // AttentionBlock norm (no activation) applied inside the q/k/v projection's operand staging
+                float* ab = lay.take<float>(static_cast<size_t>(N) * a.C * 2);
+                finalize_op(h, nullptr, a.g, a.b, ab);
+                ConvProblem q{};
+                q.spatial_dims = sd; q.N = N; q.D = h.D; q.H = h.H; q.W = h.W; q.stride = 1;
+                q.n_seg = 1;
+                q.seg[0] = {h.p, a.C, 1};
+                q.weights = a.wqkv; q.w_rows = 3 * a.C; q.Cout = 3 * a.C; q.mode = EPI_STORE;
+                q.bias = a.bqkv; q.out = qkv;
+                q.gn_silu = 0;
+                halo_conv(q, ab, a.C, -1);
+            } else {
+                gn(h, nullptr, a.g, a.b, zA, false);
+                linear(zA, rows, a.C, a.wqkv, a.bqkv, 3 * a.C, nullptr, qkv);
+            }
             if (!measure) {
                 Op op{};
                 op.type = Op::ATTN;

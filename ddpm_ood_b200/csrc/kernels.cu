@@ -4,12 +4,22 @@
 #include <math.h>
 
 #include "conv_gemm.cuh"  // set_error
+#include "launch.cuh"
+#include "ptx.cuh"
 
 namespace ddpm {
 
 #define DDPM_CHECK_LAUNCH(name)                                                      \
     do {                                                                             \
         cudaError_t e__ = cudaGetLastError();                                        \
+        if (e__ != cudaSuccess) {                                                    \
+            set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));       \
+            return 5;                                                                \
+        }                                                                            \
+    } while (0)
+#define DDPM_CHECK_PDL(name, call)                                                   \
+    do {                                                                             \
+        cudaError_t e__ = (call);                                                    \
         if (e__ != cudaSuccess) {                                                    \
             set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));       \
             return 5;                                                                \
@@ -214,6 +224,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
     const int C = C0 + C1;
     const int n = blockIdx.y;
     const int tid = threadIdx.x;
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
     gn_scale_shift_from_parts(n, C0, st0, parts0, C1, st1, parts1, gamma, beta, S, cpg, eps, s_qs, s_qq, s_sub, s_a, s_b);
     // apply: a thread keeps one 8-channel vector (scale/shift in registers) and walks pixels, 4 loads in flight
     const int V = C >> 3;              // uint4 vectors per pixel
@@ -267,9 +279,8 @@ int gn_apply(const __half* src0, int C0, const float* st0, int parts0, const __h
     while (chunk > 32 && static_cast<long long>(N) * ((S + chunk - 1) / chunk) < 2 * 148 && chunk % 2 == 0) chunk >>= 1;
     while (chunk > 256) chunk = (chunk + 1) >> 1;
     dim3 grid((S + chunk - 1) / chunk, N);
-    gn_apply_kernel<<<grid, 256, 0, stream>>>(src0, C0, st0, parts0, src1, C1, st1, parts1, gamma, beta, out, S,
-                                              C / groups, eps, do_silu ? 1 : 0, chunk);
-    DDPM_CHECK_LAUNCH("gn_apply");
+    DDPM_CHECK_PDL("gn_apply", launch_pdl(gn_apply_kernel, grid, dim3(256), 0, stream, src0, C0, st0, parts0, src1, C1, st1,
+                                       parts1, gamma, beta, out, S, C / groups, eps, do_silu ? 1 : 0, chunk));
     return 0;
 }
 
@@ -284,6 +295,8 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(int C0, const float* _
     __shared__ float2 s_sub[256];
     const int C = C0 + C1;
     const int n = blockIdx.x;
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
     gn_scale_shift_from_parts(n, C0, st0, parts0, C1, st1, parts1, gamma, beta, S, cpg, eps, s_qs, s_qq, s_sub, s_a, s_b);
     for (int c = threadIdx.x; c < C; c += blockDim.x) ab[static_cast<size_t>(n) * C + c] = make_float2(s_a[c], s_b[c]);
 }
@@ -295,9 +308,8 @@ int gn_finalize(int C0, const float* st0, int parts0, int C1, const float* st1, 
         set_error("gn_finalize: C=%d+%d groups=%d unsupported", C0, C1, groups);
         return 2;
     }
-    gn_finalize_kernel<<<N, 256, 0, stream>>>(C0, st0, parts0, C1, st1, parts1, gamma, beta,
-                                              reinterpret_cast<float2*>(ab), S, C / groups, eps);
-    DDPM_CHECK_LAUNCH("gn_finalize");
+    DDPM_CHECK_PDL("gn_finalize", launch_pdl(gn_finalize_kernel, dim3(N), dim3(256), 0, stream, C0, st0, parts0, C1, st1, parts1,
+                                          gamma, beta, reinterpret_cast<float2*>(ab), S, C / groups, eps));
     return 0;
 }
 
@@ -615,6 +627,8 @@ __global__ void __launch_bounds__(256) conv_in_reg_kernel(const float* __restric
     float bias[CPT];
 #pragma unroll
     for (int j = 0; j < CPT; ++j) bias[j] = b[g * CPT + j];
+    ptx::pdl_trigger();
+    ptx::pdl_wait();  // the weights above do not depend on the previous kernel; x (the sample) does
     const int HW = H * W;
     const int S = D * HW;
     // One block iteration = one (image, part of kConvInPart pixels): statistics partials stay image-local.
@@ -693,9 +707,8 @@ static int launch_conv_in_reg(const float* x, const float* w, const float* b, __
     const int parts = conv_in_stats_parts(D, H, W);
     long long blocks = static_cast<long long>(N) * parts;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    conv_in_reg_kernel<CIN, KD, CPT><<<static_cast<int>(blocks), 256, 0, stream>>>(x, w, b, out, N, D, H, W, Cout,
-                                                                                   stats_out, parts);
-    DDPM_CHECK_LAUNCH("conv_in_reg");
+    DDPM_CHECK_PDL("conv_in_reg", launch_pdl(conv_in_reg_kernel<CIN, KD, CPT>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0,
+                                          stream, x, w, b, out, N, D, H, W, Cout, stats_out, parts));
     return 0;
 }
 
@@ -902,6 +915,8 @@ __global__ void __launch_bounds__(256) gn_apply_taps_kernel(const __half* __rest
     __shared__ float s_a[C], s_b[C];
     const int n = blockIdx.y;
     const int tid = threadIdx.x;
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
     {
         __shared__ float2 s_sub[256];
         constexpr int Q = C / 4;
@@ -1010,13 +1025,14 @@ int gn_apply_taps(const __half* src, int C, const float* st, int parts, const fl
     while (chunk > 256) chunk = (chunk + 1) >> 1;
     dim3 grid((S + chunk - 1) / chunk, N);
     const int cpg = C / groups;
+    cudaError_t e;
     if (C == 128 && Cout == 1)
-        gn_apply_taps_kernel<1, 8, 16><<<grid, 256, 0, stream>>>(src, st, parts, gamma, beta, w, d_out, S, cpg, eps, chunk);
+        e = launch_pdl(gn_apply_taps_kernel<1, 8, 16>, grid, dim3(256), 0, stream, src, st, parts, gamma, beta, w, d_out, S, cpg, eps, chunk);
     else if (C == 128 && Cout == 3)
-        gn_apply_taps_kernel<3, 4, 32><<<grid, 256, 0, stream>>>(src, st, parts, gamma, beta, w, d_out, S, cpg, eps, chunk);
+        e = launch_pdl(gn_apply_taps_kernel<3, 4, 32>, grid, dim3(256), 0, stream, src, st, parts, gamma, beta, w, d_out, S, cpg, eps, chunk);
     else
-        gn_apply_taps_kernel<1, 8, 32><<<grid, 256, 0, stream>>>(src, st, parts, gamma, beta, w, d_out, S, cpg, eps, chunk);
-    DDPM_CHECK_LAUNCH("gn_apply_taps");
+        e = launch_pdl(gn_apply_taps_kernel<1, 8, 32>, grid, dim3(256), 0, stream, src, st, parts, gamma, beta, w, d_out, S, cpg, eps, chunk);
+    DDPM_CHECK_PDL("gn_apply_taps", e);
     return 0;
 }
 
@@ -1027,6 +1043,8 @@ __global__ void __launch_bounds__(256) conv_out_gather_kernel(const float* __res
     const int S = H * W;
     const int NV = 9 * Cout;
     const long long numel = static_cast<long long>(N) * Cout * S;
+    ptx::pdl_trigger();
+    ptx::pdl_wait();
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < numel;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int sp = static_cast<int>(idx % S);
@@ -1052,9 +1070,8 @@ int conv_out_gather(const float* d, const float* b, float* eps_out, int N, int H
     if (blocks > 148 * 16) blocks = 148 * 16;
     PlmsStep st{};
     if (plms) st = *plms;
-    conv_out_gather_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(d, b, eps_out, N, H, W, Cout, plms ? 1 : 0, st,
-                                                                         ring, stash, sample);
-    DDPM_CHECK_LAUNCH("conv_out_gather");
+    DDPM_CHECK_PDL("conv_out_gather", launch_pdl(conv_out_gather_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream,
+                                              d, b, eps_out, N, H, W, Cout, plms ? 1 : 0, st, ring, stash, sample));
     return 0;
 }
 

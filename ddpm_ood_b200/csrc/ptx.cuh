@@ -61,6 +61,13 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Kernels of the UNet chain are launched with cudaLaunchAttributeProgrammaticStreamSerialization (launch.cuh): a grid
+// may start (barrier init, TMEM allocation, descriptor prefetch) while its predecessor drains, and blocks here until the
+// predecessor has completed and its writes are visible. Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -52,6 +52,7 @@ def conv_forward(
     impl: int = 0,
     gn_scale_shift: Optional[torch.Tensor] = None,
     concat3x3: bool = False,
+    gn_no_act: bool = False,
 ) -> torch.Tensor:
     """segs: fp16 channels-last tensors [N, (D,) H, W, C]; weights: packed fp16 [rows, Ktot].
     impl 3 = halo-tile kernel; gn_scale_shift (fp32 [N, C3x3, 2], impl 3 only) normalises the 3x3 segments on the fly."""
@@ -96,6 +97,7 @@ def conv_forward(
     a.gn_scale_shift = _ptr(gn_scale_shift)
     a.gn_channels = 0 if gn_scale_shift is None else gn_scale_shift.shape[1]
     a.concat3x3 = int(concat3x3)
+    a.gn_no_act = int(gn_no_act)
     check(lib().ddpm_conv_forward(C.byref(a), current_stream_ptr()), "ddpm_conv_forward")
     return out
 

@@ -61,9 +61,9 @@ typedef struct ddpm_conv_args {
                                 low-resolution input (N,D,H,W = low-res extents, one segment with ksize 2, weights from
                                 ddpm_pack_upconv_weight); the Upsample block of DiffusionModelUNet. 4/9 (8/27) of the MACs. */
     int impl;                /* 0: im2col-tile kernels, variant picked (CTA pairs whenever two 128-pixel tiles exist);
-                                1: single-CTA im2col kernel only; 3: halo-tile kernel (stride-1 2-D 3x3 convs on images of
-                                at least 16 x 8 pixels: the input is staged once per 64 channels as a haloed tile and the
-                                9 taps read shifted views of it) */
+                                1: single-CTA im2col kernel only; 3: halo-tile kernel (stride-1 2-D 3x3 / 1x1 convs: the
+                                input is staged once per 64 channels as a haloed tile - an 8 x 16 region of an image, or
+                                two whole images of up to 8 x 8 pixels - and the 9 taps read shifted views of it) */
     float* stats_out;        /* mode 0, optional: GroupNorm partial statistics of the fp16-rounded output,
                                 [N][ddpm_conv_stats_parts()][Cout/4][2] fp32 = (sum, sum of squares) per 4-channel quad
                                 and 32-pixel part of an image; consumed by ddpm_gn_apply() / ddpm_gn_finalize();
@@ -72,6 +72,8 @@ typedef struct ddpm_conv_args {
                                 3x3 segments' inputs are normalised on the fly, z = silu(x * scale + shift) -> fp16,
                                 i.e. the conv consumes GroupNorm+SiLU of its raw input without that tensor existing */
     int gn_channels;         /* total channels of the 3x3 segments */
+    int gn_no_act;           /* 1: gn_scale_shift without the SiLU (AttentionBlock norm); with no 3x3 segment the table
+                                applies to the first (1x1) segment */
     int concat3x3;           /* impl 3: the 3x3 segments are channel slices of ONE conv weight [Cout][9][C_total] (a conv
                                 over the channel concatenation of the inputs) instead of one K block per segment */
 } ddpm_conv_args;

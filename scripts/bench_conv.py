@@ -23,6 +23,8 @@ SHAPES = [
     ("up1.res1.conv2+sk 16px 256(+384)", 16, [(256, 3), (256, 1), (128, 1)], 256),
     ("mid.res.conv1      8px 256->256", 8, [(256, 3)], 256),
     ("up0.res0.conv1     8px 512->256", 8, [(256, 3), (256, 3)], 256),
+    ("up0.res0.conv2+sk  8px 256(+512)", 8, [(256, 3), (256, 1), (256, 1)], 256),
+    ("attn.qkv 1x1       8px 256->768", 8, [(256, 1)], 768),
 ]
 
 
@@ -33,11 +35,12 @@ def main():
     ap.add_argument("--gn", action="store_true")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--shapes", type=int, default=len(SHAPES), help="only the first n shapes")
+    ap.add_argument("--first", type=int, default=0, help="skip the first n shapes")
     args = ap.parse_args()
     dev = "cuda"
     n = args.batch
     g = torch.Generator(device=dev).manual_seed(0)
-    for name, hw, segs, cout in SHAPES[:args.shapes]:
+    for name, hw, segs, cout in SHAPES[args.first:args.shapes]:
         ktot = sum(c * k * k for c, k in segs)
         wp = (torch.randn(cout, ktot, generator=g, device=dev) / ktot ** 0.5).half()
         bias = torch.randn(cout, generator=g, device=dev)
@@ -50,9 +53,6 @@ def main():
         flops = 2.0 * n * hw * hw * cout * ktot
         row = f"{name:36s} {flops / 1e9:7.1f} GF "
         for impl in [int(v) for v in args.impls.split(",")]:
-            if impl == 3 and hw < 16:
-                row += " | impl3     n/a          "
-                continue
             st = None
             if impl == 3:
                 st = torch.empty((n, ops.conv_halo_stats_parts(hw, hw), cout // 4, 2), device=dev)
@@ -61,7 +61,7 @@ def main():
                 st = torch.empty((n, parts, cout // 4, 2), device=dev) if parts else None
             kw = dict(bias=bias, impl=impl, stats_out=st)
             if impl == 3 and args.gn:
-                kw["gn_scale_shift"] = ab
+                kw["gn_scale_shift"] = ab if c3 else torch.cat([ab, torch.stack([torch.ones((n, segs[0][0]), device=dev), torch.zeros((n, segs[0][0]), device=dev)], dim=-1)], dim=1).contiguous()
             for i in range(3):
                 ops.conv_forward(xs[i % nbuf], [k for _, k in segs], wp, cout, out=outs[i % nbuf], **kw)
             torch.cuda.synchronize()

@@ -136,6 +136,13 @@ HALO_CASES = {
     "halo_many_tiles_persistent_256": dict(sd=2, n=170, sp=(16, 16), segs=[(256, 3), (128, 1)], cout=256,
                                            use_cadd=True),
     "halo_512_out_channels": dict(sd=2, n=2, sp=(16, 16), segs=[(128, 3)], cout=512),
+    # images of up to 8 x 8 pixels: a tile is TWO whole images with their rows interleaved in shared memory
+    "halo_pair_8px_256to256_odd_n": dict(sd=2, n=5, sp=(8, 8), segs=[(256, 3)], cout=256, use_cadd=True, use_res=True),
+    "halo_pair_8px_concat_plus_skip": dict(sd=2, n=6, sp=(8, 8), segs=[(256, 3), (256, 1), (256, 1)], cout=256),
+    "halo_pair_7px": dict(sd=2, n=4, sp=(7, 7), segs=[(256, 3)], cout=256, use_res=True),
+    "halo_pair_4px_512out": dict(sd=2, n=9, sp=(4, 4), segs=[(128, 3), (128, 3)], cout=512),
+    "halo_pair_many_items": dict(sd=2, n=333, sp=(8, 8), segs=[(256, 3)], cout=256, use_cadd=True),
+    "halo_14px_one_partial_tile_row": dict(sd=2, n=3, sp=(14, 14), segs=[(256, 3)], cout=256),
 }
 
 
@@ -171,6 +178,29 @@ def test_conv_halo_concat_inputs_one_weight(gn):
         xin = F.silu(xin * ab[..., 0].view(n, -1, 1, 1) + ab[..., 1].view(n, -1, 1, 1)).half().float()
     ref = F.conv2d(xin, w.half().float(), padding=1) + F.conv2d(_to_ncx(xs), ws.half().float())
     out = ops.conv_forward([xa, xb, xs], [3, 3, 1], wp, cout, impl=3, gn_scale_shift=ab, concat3x3=True)
+    torch.cuda.synchronize()
+    got = _to_ncx(out)
+    rel = ((got - ref).norm() / ref.norm()).item()
+    assert rel < 6e-4, rel
+
+
+@pytest.mark.parametrize("hw", [8, 16])
+def test_conv_halo_norm_without_activation_on_1x1(hw):
+    """AttentionBlock: GroupNorm (no SiLU) applied to the input of the q/k/v projection (a 1x1 conv, N = 768)."""
+    from ddpm_ood_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(13)
+    n, c, cout = 7, 256, 768
+    x16 = _nhwc(torch.randn((n, c, hw, hw), generator=g, device="cuda"))
+    w = torch.randn((cout, c, 1, 1), generator=g, device="cuda") / c ** 0.5
+    bias = torch.randn(cout, generator=g, device="cuda")
+    wp = torch.zeros(cout, c, dtype=torch.float16, device="cuda")
+    ops.pack_conv_weight(w.contiguous(), wp, 0)
+    ab = torch.stack([0.5 + torch.rand((n, c), generator=g, device="cuda"),
+                      torch.randn((n, c), generator=g, device="cuda")], dim=-1).contiguous()
+    xin = (_to_ncx(x16) * ab[..., 0].view(n, c, 1, 1) + ab[..., 1].view(n, c, 1, 1)).half().float()
+    ref = F.conv2d(xin, w.half().float(), bias=bias)
+    out = ops.conv_forward([x16], [1], wp, cout, bias=bias, impl=3, gn_scale_shift=ab, gn_no_act=True)
     torch.cuda.synchronize()
     got = _to_ncx(out)
     rel = ((got - ref).norm() / ref.norm()).item()
