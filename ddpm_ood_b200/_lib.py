@@ -41,6 +41,9 @@ class ConvArgs(C.Structure):
         ("stats_out", C.c_void_p),
         ("gn_scale_shift", C.c_void_p),
         ("gn_channels", C.c_int),
+        ("gn_st0", C.c_void_p), ("gn_parts0", C.c_int), ("gn_c0", C.c_int),
+        ("gn_st1", C.c_void_p), ("gn_parts1", C.c_int), ("gn_c1", C.c_int),
+        ("gn_gamma", C.c_void_p), ("gn_beta", C.c_void_p), ("gn_groups", C.c_int), ("gn_eps", C.c_float),
         ("gn_no_act", C.c_int),
         ("concat3x3", C.c_int),
     ]

@@ -120,7 +120,16 @@ int ddpm_conv_forward(const ddpm_conv_args* a, void* stream) {
     q.gn_silu = a->gn_no_act ? 0 : 1;
     if (a->impl == 3) {
         ddpm::ConvHaloLaunch hl;
-        int rc = ddpm::conv_halo_prepare(q, a->gn_scale_shift, a->gn_channels, ddpm::num_sms(), &hl);
+        ddpm::HaloGnSource src{};
+        const bool from_stats = a->gn_st0 != nullptr;
+        if (from_stats) {
+            src.st0 = a->gn_st0; src.parts0 = a->gn_parts0; src.C0 = a->gn_c0;
+            src.st1 = a->gn_st1; src.parts1 = a->gn_parts1; src.C1 = a->gn_st1 ? a->gn_c1 : 0;
+            src.gamma = a->gn_gamma; src.beta = a->gn_beta;
+            src.S = a->D * a->H * a->W; src.groups = a->gn_groups; src.eps = a->gn_eps;
+        }
+        int rc = ddpm::conv_halo_prepare(q, a->gn_scale_shift, a->gn_channels, ddpm::num_sms(), &hl,
+                                         from_stats ? &src : nullptr);
         if (rc) return rc;
         return ddpm::conv_halo_launch(hl, static_cast<cudaStream_t>(stream));
     }

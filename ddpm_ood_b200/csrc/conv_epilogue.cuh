@@ -10,9 +10,12 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)
 
 // Epilogue of one 128-pixel x BN-channel accumulator tile; executed by the 4 epilogue warps (q = TMEM lane quarter),
 // one output pixel (row) per thread. t_addr: TMEM address of the tile for this warp's lanes. sub: sub-pixel phase.
+// s_add (optional): the per-column addend (bias + this row's image's chan_add) staged in shared memory, [slot][BN] fp32
+// with slot = 0 for region tiles / the row's image (0, 1) for pair tiles; replaces the global bias / chan_add loads
+// (with ~230 KB of shared memory in use the L1 cache is gone and each of those loads is an L2 round trip).
 template <int BN>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint32_t t_addr, int m_tile, int n_tile,
-                                                   int sub, int q, int lane) {
+                                                   int sub, int q, int lane, const float* s_add = nullptr) {
             const int row = q * 32 + lane;
 
             int t = m_tile;
@@ -121,14 +124,23 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint
                         float f[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                        if (p.bias) {
+                        if (s_add) {
+                            const float4* sa4 = reinterpret_cast<const float4*>(
+                                s_add + (p.pair_rows ? ((row >> 3) & 1) * BN : 0) + c * 32);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = sa4[j >> 2];
+                                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                            }
+                        }
+                        if (!s_add && p.bias) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
                                 f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
                             }
                         }
-                        if (cadd) {
+                        if (!s_add && cadd) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(cadd + col0 + j));

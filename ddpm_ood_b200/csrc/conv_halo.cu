@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "conv_epilogue.cuh"
+#include "gn_stats.cuh"
 #include "launch.cuh"
 #include "ptx.cuh"
 
@@ -38,12 +39,15 @@ template <int BN, int MT>
 struct HCfg {
     static constexpr int kAStageBytes = MT * kATileBytes;
     static constexpr int kBHalfBytes = (BN / 2) * kBlockK * 2;  // this CTA's half of a weight tile
-    static constexpr int kBStages = 8;
+    static constexpr int kBStages = MT == 2 ? 7 : 8;
+    static constexpr int kAddBytes = 2 * BN * 4 * (MT == 2 ? 1 : 2);  // epilogue addend rows: [MT or 2 images][BN] fp32
     static constexpr int kAccCols = MT * BN;
     static constexpr int kTmemCols = 2 * kAccCols;
     static constexpr int kAbBytes = 2 * kMaxGnChannels * 8;  // per-item (scale, shift) rows of the (up to 2) images
+    static constexpr int kGnScratchBytes = (kMaxGnChannels / 4) * 8 + 256 * 8;  // statistics reduction scratch
     static constexpr int kSmemBytes =
-        kAStages * kAStageBytes + kBStages * kBHalfBytes + kAbBytes + 1024 /*align*/ + 512 /*barriers*/;
+        kAStages * kAStageBytes + kBStages * kBHalfBytes + kAbBytes + kGnScratchBytes + kAddBytes + 1024 /*align*/ +
+        512 /*barriers*/;
     static_assert(kTmemCols <= 512, "TMEM");
     static_assert(kSmemBytes <= 227 * 1024, "shared memory");
 };
@@ -144,7 +148,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     uint8_t* smem_a = smem;                                   // [kAStages][MT][23 KB]
     uint8_t* smem_b = smem + kAStages * C::kAStageBytes;      // [kBStages][BN/2 rows x 128 B]
     float2* s_ab = reinterpret_cast<float2*>(smem_b + C::kBStages * C::kBHalfBytes);  // [2][kMaxGnChannels]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + C::kBStages * C::kBHalfBytes + C::kAbBytes);
+    float* s_gn = reinterpret_cast<float*>(smem_b + C::kBStages * C::kBHalfBytes + C::kAbBytes);  // s_qs | s_qq | s_sub
+    float* s_add = s_gn + C::kGnScratchBytes / 4;  // [MT (region) | 2 images (pair)][BN]: bias + chan_add per column
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + C::kBStages * C::kBHalfBytes + C::kAbBytes + C::kGnScratchBytes +
+                                                 C::kAddBytes);
     uint64_t* a_full = bars;                      // per CTA: TMA -> transform warps
     uint64_t* a_ready = a_full + kAStages;        // leader's copy: transform warps of both CTAs -> MMA
     uint64_t* a_empty = a_ready + kAStages;       // per CTA: MMA (multicast commit) -> A producer
@@ -322,7 +329,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         const int cg = tid & 7;
         constexpr int kRowIters = PAIR ? 7 : 6;
         constexpr float kNegLog2e = -1.4426950408889634f;
-        const bool any_gn = hp.ab != nullptr && !(hp.dbg & 1);
+        const bool any_gn = (hp.ab != nullptr || hp.gn_from_stats) && !(hp.dbg & 1);
         const uint32_t smem_a_u32 = ptx::smem_u32(smem_a);
         const int slot_of_thread = PAIR ? (tid >> 7) : 0;
         int sa = 0;
@@ -357,19 +364,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 mask_halo[mt] = m;
             }
             if (any_gn) {
-                // (scale, shift) rows of this item's images -> shared memory (read once per item, not once per stage)
-                asm volatile("bar.sync 1, %0;" ::"n"(kXformWarps * 32) : "memory");  // previous item's readers are done
+                // (scale, shift) rows of this item's images -> shared memory, once per item: either copied from the
+                // precomputed table or derived here from the producers' partial statistics (same code as gn_finalize)
+                auto xsync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kXformWarps * 32) : "memory"); };
+                xsync();  // previous item's readers are done
 #pragma unroll
                 for (int slot = 0; slot < 2; ++slot) {
                     int n;
                     if (PAIR) n = 2 * ((m_group * 2 + static_cast<int>(rank)) * MT) + slot;
                     else n = slot < MT ? ((m_group * 2 + static_cast<int>(rank)) * MT + slot) / tiles_per_img : p.N;
-                    if (n < p.N) {
+                    if (n >= p.N) continue;  // uniform across the transform warps
+                    if (!PAIR && slot == 1 && n == ((m_group * 2 + static_cast<int>(rank)) * MT) / tiles_per_img) {
+                        // both tiles lie in the same image: copy slot 0 instead of reducing the statistics twice
+                        xsync();
+                        for (int c = tid; c < hp.ab_C; c += kXformWarps * 32) s_ab[kMaxGnChannels + c] = s_ab[c];
+                        continue;
+                    }
+                    float2* dst = s_ab + slot * kMaxGnChannels;
+                    if (hp.gn_from_stats) {
+                        const HaloGnSource& g = hp.gn;
+                        gn_scale_shift_from_parts(tid, n, g.C0, g.st0, g.parts0, g.C1, g.st1, g.parts1, g.gamma, g.beta, g.S,
+                                                  (g.C0 + g.C1) / g.groups, g.eps, s_gn, s_gn + kMaxGnChannels / 4,
+                                                  reinterpret_cast<float2*>(s_gn + kMaxGnChannels / 2), xsync,
+                                                  [&](int c, float a, float b) { dst[c] = make_float2(a, b); });
+                    } else {
                         const float2* src = hp.ab + static_cast<size_t>(n) * hp.ab_C;
-                        for (int c = tid; c < hp.ab_C; c += kXformWarps * 32) s_ab[slot * kMaxGnChannels + c] = __ldg(src + c);
+                        for (int c = tid; c < hp.ab_C; c += kXformWarps * 32) dst[c] = __ldg(src + c);
                     }
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(kXformWarps * 32) : "memory");
+                xsync();
             }
             for (int seg = 0; seg < p.n_seg; ++seg) {
                 const int gn = (hp.dbg & 1) ? 0 : hp.seg_gn[seg];
@@ -433,13 +456,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         for (int item = cluster_id; item < total_items; item += num_clusters) {
             const int m_group = item / p.num_n_tiles;
             const int n_tile = item - m_group * p.num_n_tiles;
+            // stage the per-column addends (bias + timestep-embedding row of the tile's image) while the MMAs run
+            {
+                const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..127
+                constexpr int kSlots = PAIR ? 2 : MT;
+                asm volatile("bar.sync 2, 128;" ::: "memory");  // the previous item's readers are done
+#pragma unroll
+                for (int slot = 0; slot < kSlots; ++slot) {
+                    const int t = (m_group * 2 + static_cast<int>(rank)) * MT + (PAIR ? 0 : slot);
+                    int n = PAIR ? 2 * t + slot : t / tiles_per_img;
+                    if (n >= p.N) n = 0;
+                    for (int i = et; i < BN; i += 128) {
+                        float v = p.bias ? __ldg(p.bias + n_tile * BN + i) : 0.f;
+                        if (p.chan_add) v += __ldg(p.chan_add + static_cast<size_t>(n) * p.chan_add_stride + n_tile * BN + i);
+                        s_add[slot * BN + i] = v;
+                    }
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+            }
             ptx::mbar_wait(&tfull_bar[as], pt);
             ptx::tc_fence_after();
             if (!(hp.dbg & 2)) {
 #pragma unroll 1
                 for (int mt = 0; mt < MT; ++mt)
                     conv_epilogue_tile<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * C::kAccCols + mt * BN,
-                                           (m_group * 2 + static_cast<int>(rank)) * MT + mt, n_tile, 0, q, lane);
+                                           (m_group * 2 + static_cast<int>(rank)) * MT + mt, n_tile, 0, q, lane,
+                                           s_add + (PAIR ? 0 : mt * BN));
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -480,13 +522,25 @@ int conv_halo_stats_parts(int H, int W) {
     return ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH) * 4;
 }
 
-int conv_halo_prepare(const ConvProblem& q, const float* gn_ab, int gn_ab_channels, int num_sms, ConvHaloLaunch* out) {
+int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_channels, int num_sms, ConvHaloLaunch* out,
+                      const HaloGnSource* gn_src) {
     PFN_encodeTiled encode = get_encode();
     if (!encode) return 1;
     if (!conv_halo_supported(q)) { set_error("conv_halo: problem not supported by the halo-tile kernel"); return 2; }
     memset(out, 0, sizeof(*out));
     ConvHaloParams& hp = out->p;
     ConvGemmParams& p = hp.g;
+    // `gn_ab` below only says "some segments are normalised"; with gn_src the table is built inside the kernel
+    const float* gn_ab = gn_src ? reinterpret_cast<const float*>(gn_src) : gn_ab_in;
+    if (gn_src) {
+        gn_ab_channels = gn_src->C0 + gn_src->C1;
+        const int C = gn_ab_channels;
+        if (gn_src->groups <= 0 || C % gn_src->groups != 0 || (C / gn_src->groups) % 4 != 0 || gn_src->C0 % 8 != 0 ||
+            gn_src->C1 % 8 != 0) {
+            set_error("conv_halo: GroupNorm over %d+%d channels in %d groups unsupported", gn_src->C0, gn_src->C1, gn_src->groups);
+            return 2;
+        }
+    }
     const bool pair = pair_tiles(q);
     hp.pair_mode = pair ? 1 : 0;
     p.pair_rows = pair ? 1 : 0;
@@ -576,8 +630,10 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab, int gn_ab_channe
         set_error("conv_halo: %d normalised input channels exceed the %d the kernel stages", gn_ab_channels, kMaxGnChannels);
         return 2;
     }
-    hp.ab = reinterpret_cast<const float2*>(gn_ab);
+    hp.ab = gn_src ? nullptr : reinterpret_cast<const float2*>(gn_ab_in);
     hp.ab_C = gn_ab_channels;
+    hp.gn_from_stats = gn_src ? 1 : 0;
+    if (gn_src) hp.gn = *gn_src;
     {
         const char* e = getenv("DDPM_HALO_DBG");
         hp.dbg = e ? atoi(e) : 0;

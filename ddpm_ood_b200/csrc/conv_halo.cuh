@@ -25,6 +25,18 @@
 
 namespace ddpm {
 
+// GroupNorm of the conv's input computed from its producers' partial statistics (ConvGemmParams::stats_out layout) by
+// the kernel itself, per work item: replaces a separate statistics -> scale/shift launch. The normalised channels are
+// the concatenation of (up to) two tensors, in segment order.
+struct HaloGnSource {
+    const float* st0; int parts0; int C0;
+    const float* st1; int parts1; int C1;   // st1 null / C1 0: one tensor
+    const float* gamma; const float* beta;  // [C0 + C1]
+    int S;                                  // pixels per image
+    int groups;
+    float eps;
+};
+
 struct ConvHaloParams {
     ConvGemmParams g;         // geometry, K schedule, epilogue, tmA[seg] (haloed / plain boxes), tmB (half weight tile)
     int seg_taps[kMaxSeg];    // 9 or 1
@@ -33,6 +45,8 @@ struct ConvHaloParams {
     int seg_gn[kMaxSeg];      // 1: apply silu(x * a + b) to this segment's input tile, 2: x * a + b (no activation)
     int seg_ab_off[kMaxSeg];  // channel offset of the segment in the scale/shift table
     const float2* ab;         // [N][ab_C] (scale, shift) per image and input channel, or null
+    HaloGnSource gn;          // gn_from_stats: derive (scale, shift) from these statistics instead of reading `ab`
+    int gn_from_stats;
     int ab_C;
     int pair_mode;            // 1: tiles are two whole images of up to 8 x 8 pixels (rows interleaved by image)
     int dbg;                  // timing experiments only (env DDPM_HALO_DBG): 1 skip transform math, 2 skip epilogue
@@ -52,7 +66,9 @@ bool conv_halo_supported(const ConvProblem& q);
 int conv_halo_stats_parts(int H, int W);
 // gn_ab: null, or the (scale, shift) table [N][gn_ab_channels] applied to the 3x3 segments (channels concatenated in
 // segment order)
-int conv_halo_prepare(const ConvProblem& q, const float* gn_ab, int gn_ab_channels, int num_sms, ConvHaloLaunch* out);
+// gn_src (optional, instead of gn_ab): compute the table inside the kernel from producer statistics.
+int conv_halo_prepare(const ConvProblem& q, const float* gn_ab, int gn_ab_channels, int num_sms, ConvHaloLaunch* out,
+                      const HaloGnSource* gn_src = nullptr);
 int conv_halo_launch(const ConvHaloLaunch& l, cudaStream_t stream);
 
 }  // namespace ddpm

@@ -169,6 +169,7 @@ int UNet::init() {
     if (const char* e = getenv("DDPM_ATTN_TC")) use_attn_tc_ = atoi(e) != 0;  // A/B switch for tests
     if (const char* e = getenv("DDPM_FUSE_GN")) fuse_gn_stats_ = fuse_gn_stats_ && atoi(e) != 0;  // A/B switch for tests
     if (const char* e = getenv("DDPM_CONV_HALO")) use_halo_ = atoi(e) != 0;  // A/B switch for tests
+    if (const char* e = getenv("DDPM_HALO_GN_IN_KERNEL")) halo_gn_in_kernel_ = atoi(e) != 0;  // A/B switch for tests
     use_halo_ = use_halo_ && fuse_gn_stats_ && c.spatial_dims == 2;
     in_gemm_ = (c.in_channels % 64 == 0);
     out_gemm_ = (c.out_channels % 128 == 0);
@@ -523,14 +524,21 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             op.bytes = static_cast<double>(N) * (a.parts * a.C + (b ? b->parts * b->C : 0)) * 2.0;
             plan.ops.push_back(op);
         };
-        auto halo_conv = [&](ConvProblem q, const float* ab, int ab_channels, int temb_off) {
+        auto gn_source = [&](const Act& a, const Act* b, const float* g, const float* bt) {
+            HaloGnSource src{};
+            src.st0 = a.stats; src.parts0 = a.parts; src.C0 = a.C;
+            src.st1 = b ? b->stats : nullptr; src.parts1 = b ? b->parts : 0; src.C1 = b ? b->C : 0;
+            src.gamma = g; src.beta = bt; src.S = static_cast<int>(a.S()); src.groups = c.norm_num_groups; src.eps = c.norm_eps;
+            return src;
+        };
+        auto halo_conv = [&](ConvProblem q, const float* ab, int ab_channels, int temb_off, const HaloGnSource* src = nullptr) {
             Op op{};
             op.type = Op::CONV_HALO;
             op.uses_temb = temb_off >= 0;
             op.temb_off = temb_off;
             op.flops = conv_flops(q);
             if (!dry) {
-                int r = conv_halo_prepare(q, ab, ab_channels, sms, &op.halo);
+                int r = conv_halo_prepare(q, ab, ab_channels, sms, &op.halo, src);
                 if (r && !rc) rc = r;
             }
             plan.ops.push_back(op);
@@ -543,9 +551,10 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
                 return shape_act(r.cout, h.D, h.H, h.W);
             }
             const int parts = conv_halo_stats_parts(h.H, h.W);
-            float* ab1 = lay.take<float>(static_cast<size_t>(N) * cin * 2);
-            float* ab2 = lay.take<float>(static_cast<size_t>(N) * r.cout * 2);
-            finalize_op(h, skip, r.g1, r.b1, ab1);
+            // GroupNorm statistics are finalised inside the consuming kernel (halo_gn_in_kernel_) or by a tiny launch
+            float* ab1 = halo_gn_in_kernel_ ? nullptr : lay.take<float>(static_cast<size_t>(N) * cin * 2);
+            float* ab2 = halo_gn_in_kernel_ ? nullptr : lay.take<float>(static_cast<size_t>(N) * r.cout * 2);
+            if (!halo_gn_in_kernel_) finalize_op(h, skip, r.g1, r.b1, ab1);
             Act h1{hB, r.cout, h.D, h.H, h.W, take_stats(r.cout, parts), parts};
             ConvProblem q{};
             q.spatial_dims = sd; q.N = N; q.D = h.D; q.H = h.H; q.W = h.W; q.stride = 1;
@@ -557,8 +566,9 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             q.weights = r.w1; q.w_rows = r.cout; q.Cout = r.cout; q.mode = EPI_STORE;
             q.bias = r.bias1; q.chan_add = plan.temb_all ? plan.temb_all + r.temb_off : nullptr; q.chan_add_stride = P_;
             q.out = hB; q.stats_out = h1.stats;
-            halo_conv(q, ab1, cin, r.temb_off);
-            finalize_op(h1, nullptr, r.g2, r.b2, ab2);
+            const HaloGnSource src1 = gn_source(h, skip, r.g1, r.b1);
+            halo_conv(q, ab1, cin, r.temb_off, halo_gn_in_kernel_ ? &src1 : nullptr);
+            if (!halo_gn_in_kernel_) finalize_op(h1, nullptr, r.g2, r.b2, ab2);
             Act out{lay.take<__half>(static_cast<size_t>(N) * h.S() * r.cout), r.cout, h.D, h.H, h.W,
                     take_stats(r.cout, parts), parts};
             ConvProblem q2{};
@@ -574,7 +584,8 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             q2.weights = r.w2; q2.w_rows = r.cout; q2.Cout = r.cout; q2.mode = EPI_STORE;
             q2.bias = r.bias2_total; q2.out = out.p; q2.stats_out = out.stats;
             q2.gn_silu = 1;
-            halo_conv(q2, ab2, r.cout, -1);
+            const HaloGnSource src2 = gn_source(h1, nullptr, r.g2, r.b2);
+            halo_conv(q2, ab2, r.cout, -1, halo_gn_in_kernel_ ? &src2 : nullptr);
             return out;
         };
         auto resblock = [&](const ResW& r, const Act& h, const Act* skip) -> Act {

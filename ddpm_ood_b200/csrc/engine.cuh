@@ -181,6 +181,7 @@ class UNet {
     bool use_attn_tc_ = true;
     bool upconv_phases_ = true;  // nearest-x2 + conv as sub-pixel 2x2 convs (4/9 of the MACs, no upsampled tensor)
     bool fuse_gn_stats_ = true;  // GroupNorm statistics from the producers' epilogues (cpg % 4 == 0 required)
+    bool halo_gn_in_kernel_ = true;  // the halo conv derives scale/shift from producer statistics itself (no gn_finalize)
     bool use_halo_ = true;       // halo-tile conv kernel with GroupNorm+SiLU applied on the fly (2-D, images >= 16 x 8)
     // arenas
     size_t f32_count_ = 0, f16_count_ = 0, f32_used_ = 0, f16_used_ = 0;

@@ -4,6 +4,7 @@
 #include <math.h>
 
 #include "conv_gemm.cuh"  // set_error
+#include "gn_stats.cuh"
 #include "launch.cuh"
 #include "ptx.cuh"
 
@@ -156,61 +157,6 @@ int gn_silu(const __half* src0, int C0, const __half* src1, int C1, const float*
 // derives per-channel scale/shift and streams its pixel chunk once: one fp16 read + one fp16 write per element.
 constexpr int kGnApplyMaxC = 2048;
 
-// Per-channel scale/shift of image n from the producers' partial statistics, into shared memory (s_a, s_b): the
-// common front half of gn_apply_kernel and gn_finalize_kernel (identical summation order -> identical bits).
-__device__ __forceinline__ void gn_scale_shift_from_parts(int n, int C0, const float* __restrict__ st0, int parts0,
-                                                          int C1, const float* __restrict__ st1, int parts1,
-                                                          const float* __restrict__ gamma,
-                                                          const float* __restrict__ beta, int S, int cpg, float eps,
-                                                          float* s_qs, float* s_qq, float2* s_sub, float* s_a,
-                                                          float* s_b) {
-    const int C = C0 + C1;
-    const int Q = C >> 2, Q0 = C0 >> 2, Q1 = C1 >> 2;
-    const int tid = threadIdx.x;
-    {
-        // fixed-order two-level sum of the partials: J threads per quad take parts j, j+J, ... (independent loads),
-        // then one thread per quad adds the J sub-sums.
-        const int J = Q <= 256 ? 256 / Q : 1;
-        for (int base = 0; base < Q; base += 256) {
-            const int qd = base + tid % (Q < 256 ? Q : 256);
-            const int j = tid / (Q < 256 ? Q : 256);
-            float a = 0.f, b = 0.f;
-            if (qd < Q && j < J) {
-                const float2* p;
-                int parts, Qs;
-                if (qd < Q0) { p = reinterpret_cast<const float2*>(st0) + static_cast<size_t>(n) * parts0 * Q0 + qd; parts = parts0; Qs = Q0; }
-                else { p = reinterpret_cast<const float2*>(st1) + static_cast<size_t>(n) * parts1 * Q1 + (qd - Q0); parts = parts1; Qs = Q1; }
-#pragma unroll 4
-                for (int i = j; i < parts; i += J) { const float2 v = __ldg(p + static_cast<size_t>(i) * Qs); a += v.x; b += v.y; }
-            }
-            s_sub[tid] = make_float2(a, b);
-            __syncthreads();
-            if (tid < 256 && base + tid < Q && tid < (Q < 256 ? Q : 256)) {
-                float sa = 0.f, sb = 0.f;
-                for (int jj = 0; jj < J; ++jj) { const float2 v = s_sub[jj * (Q < 256 ? Q : 256) + tid]; sa += v.x; sb += v.y; }
-                s_qs[base + tid] = sa;
-                s_qq[base + tid] = sb;
-            }
-            __syncthreads();
-        }
-    }
-    __syncthreads();
-    const float inv_n = 1.0f / (static_cast<float>(cpg) * static_cast<float>(S));
-    for (int c = tid; c < C; c += blockDim.x) {
-        const int q0 = (c / cpg) * (cpg >> 2);
-        float sum = 0.f, sq = 0.f;
-        for (int i = 0; i < (cpg >> 2); ++i) { sum += s_qs[q0 + i]; sq += s_qq[q0 + i]; }
-        const float mean = sum * inv_n;
-        float var = sq * inv_n - mean * mean;
-        var = var < 0.f ? 0.f : var;
-        const float rstd = rsqrtf(var + eps);
-        const float a = gamma[c] * rstd;
-        s_a[c] = a;
-        s_b[c] = beta[c] - mean * a;
-    }
-    __syncthreads();
-}
-
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ src0, int C0,
                                                        const float* __restrict__ st0, int parts0,
                                                        const __half* __restrict__ src1, int C1,
@@ -226,7 +172,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
     const int tid = threadIdx.x;
     ptx::pdl_trigger();
     ptx::pdl_wait();
-    gn_scale_shift_from_parts(n, C0, st0, parts0, C1, st1, parts1, gamma, beta, S, cpg, eps, s_qs, s_qq, s_sub, s_a, s_b);
+    gn_scale_shift_from_parts(
+        tid, n, C0, st0, parts0, C1, st1, parts1, gamma, beta, S, cpg, eps, s_qs, s_qq, s_sub, [] { __syncthreads(); },
+        [&](int c, float a, float b) { s_a[c] = a; s_b[c] = b; });
     // apply: a thread keeps one 8-channel vector (scale/shift in registers) and walks pixels, 4 loads in flight
     const int V = C >> 3;              // uint4 vectors per pixel
     const int ppi = blockDim.x / V;    // pixels per block iteration (threads beyond ppi*V idle in this phase)
@@ -291,14 +239,14 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(int C0, const float* _
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           float2* __restrict__ ab, int S, int cpg, float eps) {
     __shared__ float s_qs[kGnApplyMaxC / 4], s_qq[kGnApplyMaxC / 4];
-    __shared__ float s_a[kGnApplyMaxC], s_b[kGnApplyMaxC];
     __shared__ float2 s_sub[256];
     const int C = C0 + C1;
     const int n = blockIdx.x;
     ptx::pdl_trigger();
     ptx::pdl_wait();
-    gn_scale_shift_from_parts(n, C0, st0, parts0, C1, st1, parts1, gamma, beta, S, cpg, eps, s_qs, s_qq, s_sub, s_a, s_b);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) ab[static_cast<size_t>(n) * C + c] = make_float2(s_a[c], s_b[c]);
+    gn_scale_shift_from_parts(
+        static_cast<int>(threadIdx.x), n, C0, st0, parts0, C1, st1, parts1, gamma, beta, S, cpg, eps, s_qs, s_qq, s_sub,
+        [] { __syncthreads(); }, [&](int c, float a, float b) { ab[static_cast<size_t>(n) * C + c] = make_float2(a, b); });
 }
 
 int gn_finalize(int C0, const float* st0, int parts0, int C1, const float* st1, int parts1, const float* gamma,

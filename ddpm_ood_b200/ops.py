@@ -53,6 +53,10 @@ def conv_forward(
     gn_scale_shift: Optional[torch.Tensor] = None,
     concat3x3: bool = False,
     gn_no_act: bool = False,
+    gn_stats: Optional[Sequence[torch.Tensor]] = None,
+    gn_affine: Optional[Sequence[torch.Tensor]] = None,
+    gn_groups: int = 32,
+    gn_eps: float = 1e-6,
 ) -> torch.Tensor:
     """segs: fp16 channels-last tensors [N, (D,) H, W, C]; weights: packed fp16 [rows, Ktot].
     impl 3 = halo-tile kernel; gn_scale_shift (fp32 [N, C3x3, 2], impl 3 only) normalises the 3x3 segments on the fly."""
@@ -98,6 +102,12 @@ def conv_forward(
     a.gn_channels = 0 if gn_scale_shift is None else gn_scale_shift.shape[1]
     a.concat3x3 = int(concat3x3)
     a.gn_no_act = int(gn_no_act)
+    if gn_stats is not None:  # statistics [N, parts, C/4, 2] of one or two tensors + (gamma, beta): table built in-kernel
+        a.gn_st0, a.gn_parts0, a.gn_c0 = gn_stats[0].data_ptr(), gn_stats[0].shape[1], gn_stats[0].shape[2] * 4
+        if len(gn_stats) > 1:
+            a.gn_st1, a.gn_parts1, a.gn_c1 = gn_stats[1].data_ptr(), gn_stats[1].shape[1], gn_stats[1].shape[2] * 4
+        a.gn_gamma, a.gn_beta = gn_affine[0].data_ptr(), gn_affine[1].data_ptr()
+        a.gn_groups, a.gn_eps = gn_groups, gn_eps
     check(lib().ddpm_conv_forward(C.byref(a), current_stream_ptr()), "ddpm_conv_forward")
     return out
 

@@ -72,6 +72,12 @@ typedef struct ddpm_conv_args {
                                 3x3 segments' inputs are normalised on the fly, z = silu(x * scale + shift) -> fp16,
                                 i.e. the conv consumes GroupNorm+SiLU of its raw input without that tensor existing */
     int gn_channels;         /* total channels of the 3x3 segments */
+    /* impl 3, instead of gn_scale_shift: the kernel derives the table itself, per work item, from the statistics its
+       input tensors' producers left (stats_out layout) - no ddpm_gn_finalize launch. The normalised channels are the
+       concatenation (segment order) of one or two tensors. */
+    const float* gn_st0; int gn_parts0; int gn_c0;
+    const float* gn_st1; int gn_parts1; int gn_c1;
+    const float* gn_gamma; const float* gn_beta; int gn_groups; float gn_eps;
     int gn_no_act;           /* 1: gn_scale_shift without the SiLU (AttentionBlock norm); with no 3x3 segment the table
                                 applies to the first (1x1) segment */
     int concat3x3;           /* impl 3: the 3x3 segments are channel slices of ONE conv weight [Cout][9][C_total] (a conv

@@ -207,6 +207,41 @@ def test_conv_halo_norm_without_activation_on_1x1(hw):
     assert rel < 6e-4, rel
 
 
+@pytest.mark.parametrize("hw", [8, 16, 32])
+def test_conv_halo_scale_shift_from_statistics_in_kernel(hw):
+    """The kernel's own statistics -> scale/shift step (per work item, in the transform warps) runs the same reduction
+    as ddpm_gn_finalize: identical bits to the table path, for one tensor and for a channel concatenation of two."""
+    from ddpm_ood_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(17)
+    n, ca, cb, cout = 5, 256, 128, 256
+    xa = _nhwc(torch.randn((n, ca, hw, hw), generator=g, device="cuda"))
+    xb = _nhwc(torch.randn((n, cb, hw, hw), generator=g, device="cuda"))
+    w = torch.randn((cout, ca + cb, 3, 3), generator=g, device="cuda") / ((ca + cb) * 9) ** 0.5
+    wp = torch.zeros(cout, (ca + cb) * 9, dtype=torch.float16, device="cuda")
+    ops.pack_conv_weight(w.contiguous(), wp, 0)
+    gamma = torch.randn(ca + cb, generator=g, device="cuda")
+    beta = torch.randn(ca + cb, generator=g, device="cuda")
+
+    def stats_of(x, parts):  # what a producer epilogue leaves: per-part partial sums (here: pixel slices)
+        q = x.float().reshape(n, parts, -1, x.shape[-1] // 4, 4)
+        return torch.stack([q.sum(dim=(2, 4)), (q * q).sum(dim=(2, 4))], dim=-1).contiguous()
+
+    sta, stb = stats_of(xa, 4), stats_of(xb, 8)
+    ab = ops.gn_finalize(sta, stb, gamma, beta, hw * hw, 32, 1e-6)
+    want = ops.conv_forward([xa, xb], [3, 3], wp, cout, impl=3, gn_scale_shift=ab, concat3x3=True)
+    got = ops.conv_forward([xa, xb], [3, 3], wp, cout, impl=3, concat3x3=True, gn_stats=[sta, stb],
+                           gn_affine=[gamma, beta], gn_groups=32, gn_eps=1e-6)
+    torch.cuda.synchronize()
+    assert torch.equal(want, got)
+    # and against torch's GroupNorm + SiLU + conv on the same fp16 inputs
+    xin = torch.cat([_to_ncx(xa), _to_ncx(xb)], dim=1)
+    z = F.silu(F.group_norm(xin, 32, gamma, beta, eps=1e-6)).half().float()
+    ref = F.conv2d(z, w.half().float(), padding=1)
+    rel = ((_to_ncx(got) - ref).norm() / ref.norm()).item()
+    assert rel < 1e-3, rel
+
+
 def test_conv_halo_matches_im2col_kernel_bitwise():
     """Same operands, same K order inside a 64-channel chunk per tap but a different tap/chunk interleave: fp32
     accumulation order differs, so compare within one fp16 ulp; and the fused GroupNorm path against gn_apply + conv."""
