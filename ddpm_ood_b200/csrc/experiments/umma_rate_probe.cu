@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int iters, int mode, long 
         const uint32_t a0 = ptx::smem_u32(smem) + ((mode & 1) ? 11 * 128 : 0);
         const uint32_t sbo = (mode & 1) ? 1280 : 1024;
         const uint32_t b0 = ptx::smem_u32(smem + 64 * 1024);
-        const int mt_n = (mode & 4) ? 4 : ((mode & 2) ? 2 : 1);
+        const int mt_n = (mode & 16) ? 3 : ((mode & 4) ? 4 : ((mode & 2) ? 2 : 1));
+        const uint32_t acc_stride = (mode & 8) ? 256 : N;
         const uint64_t da_base = make_desc(a0, sbo);
         const uint64_t db_base = make_desc(b0, 1024);
         t0 = clock64();
@@ -63,8 +64,8 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int iters, int mode, long 
                 for (int k = 0; k < 4; ++k) {
 #pragma unroll 4
                     for (int mt = 0; mt < mt_n; ++mt) {
-                        if (CG == 2) ptx::umma_f16_2cta(tmem + mt * N, da + 2 * k, db + 2 * k, idesc, 1);
-                        else ptx::umma_f16(tmem + mt * N, da + 2 * k, db + 2 * k, idesc, 1);
+                        if (CG == 2) ptx::umma_f16_2cta(tmem + mt * acc_stride, da + 2 * k, db + 2 * k, idesc, 1);
+                        else ptx::umma_f16(tmem + mt * acc_stride, da + 2 * k, db + 2 * k, idesc, 1);
                     }
                 }
             }
@@ -115,7 +116,7 @@ void run(const char* name, int mode, long long* dout) {
         CK(cudaDeviceSynchronize());
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         long long cyc; CK(cudaMemcpy(&cyc, dout, 8, cudaMemcpyDeviceToHost));
-        const int mt_n = (mode & 4) ? 4 : ((mode & 2) ? 2 : 1);
+        const int mt_n = (mode & 16) ? 3 : ((mode & 4) ? 4 : ((mode & 2) ? 2 : 1));
         const double mmas = 4.0 * iters * mt_n;
         const double macs_per_cta = 128.0 * N * 16;  // per CTA per MMA
         if (rep == 1)
@@ -127,17 +128,12 @@ void run(const char* name, int mode, long long* dout) {
 int main() {
     long long* dout;
     CK(cudaMalloc(&dout, 8));
-    const int modes[3] = {0, 2, 4};
-    for (int mi = 0; mi < 3; ++mi) {
+    const int modes[5] = {0, 2, 10, 16, 4};  // 1 acc; 2 accs; 2 accs 256 columns apart; 3 accs; 4 accs
+    for (int mi = 0; mi < 5; ++mi) {
         const int mode = modes[mi];
-        run<1, 64>("cta_group::1 M=128 N=64", mode, dout);
         run<1, 128>("cta_group::1 M=128 N=128", mode, dout);
-        if (mode != 4) run<1, 192>("cta_group::1 M=128 N=192", mode, dout);
-        if (mode != 4) run<1, 256>("cta_group::1 M=128 N=256", mode, dout);
-        run<2, 64>("cta_group::2 M=256 N=64", mode, dout);
         run<2, 128>("cta_group::2 M=256 N=128", mode, dout);
-        if (mode != 4) run<2, 192>("cta_group::2 M=256 N=192", mode, dout);
-        if (mode != 4) run<2, 256>("cta_group::2 M=256 N=256", mode, dout);
+        if (mode != 4 && mode != 16) run<2, 256>("cta_group::2 M=256 N=256", mode, dout);
     }
     return 0;
 }

@@ -1,8 +1,8 @@
 // LPIPS (AlexNet, v0.1, linear heads, spatial average) on the device, fp32 throughout.
 // Replaces `lpips.LPIPS.forward(in0, in1, normalize=...)` as called through the reference's wrapper
 // src/losses/perceptual_loss.py:125,181-183 from src/trainers/reconstruct.py:170-187.
-// The feature extractor is a few MFLOP per image (vs ~400 GFLOP for the reconstruction chain it scores), so plain
-// direct convolutions on CUDA cores are used; what matters is that the whole score stays on the device.
+// The feature extractor is a few MFLOP per image (vs ~400 GFLOP for the reconstruction chain it scores): shared-memory
+// tiled fp32 GEMM convolutions on CUDA cores (~0.5 ms per batch of 256 image pairs); the whole score stays on the device.
 #include "lpips.cuh"
 
 #include <string.h>
@@ -22,9 +22,8 @@ namespace ddpm {
 
 static const int kChn[5] = {64, 192, 384, 256, 256};
 static const int kCin[5] = {3, 64, 192, 384, 256};
+// kernel / stride / padding: 11/4/2, 5/1/2, 3/1/1 x3 (torchvision AlexNet features), template arguments of the conv kernel
 static const int kK[5] = {11, 5, 3, 3, 3};
-static const int kStride[5] = {4, 1, 1, 1, 1};
-static const int kPad[5] = {2, 2, 1, 1, 1};
 
 // in0/in1: [B, C, H, W] (C = 1 broadcasts to 3, like the reference's ScalingLayer does for grayscale); out: [2B,3,H,W]
 __global__ void lpips_scale_kernel(const float* __restrict__ in0, const float* __restrict__ in1, float* __restrict__ out,
@@ -45,56 +44,90 @@ __global__ void lpips_scale_kernel(const float* __restrict__ in0, const float* _
     }
 }
 
-// Direct convolution + bias + ReLU, NCHW fp32. One warp per (image, output channel, block of 32 output pixels): the
-// filter row is streamed once per warp (lanes split the Cin*k*k reduction for tiny maps, pixels for large maps).
+// Convolution + bias + ReLU as a shared-memory tiled fp32 GEMM (NCHW in, NCHW out):
+//   out[(n, p), co] = relu(bias[co] + sum_k patch[(n, p), k] * w[co, k]),   k = (ci, kh, kw)
+// A CTA owns a 64 (image, pixel) x 64 output-channel tile; the patch matrix is gathered on the fly (zero padding), the
+// filter rows are read once per 64 rows instead of once per (image, channel, pixel block). 16 x 16 threads, 4 x 4
+// outputs each, K in steps of 16. fp32 CUDA-core math on purpose: the reference computes LPIPS in fp32
+// (src/losses/perceptual_loss.py:107-108) and the score tolerance is 2e-4.
+// CENTER: a 3x3 / pad 1 conv over a 1x1 map only ever sees its centre tap (AlexNet's last three convs on 32x32 images):
+// the reduction runs over Cin with the centre weights, 1/9 of the work.
+template <int K, int STRIDE, int PAD, bool CENTER = false>
 __global__ void __launch_bounds__(256) lpips_conv_relu_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                               const float* __restrict__ bias, float* __restrict__ out,
-                                                              int NB, int Cin, int H, int W, int Cout, int Ho, int Wo,
-                                                              int K, int stride, int pad) {
-    const int lane = threadIdx.x & 31;
-    const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+                                                              int NB, int Cin, int H, int W, int Cout, int Ho, int Wo) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Ws[BK][BN + 4];
     const int npix = Ho * Wo;
-    const int pblocks = (npix + 31) / 32;
-    const long long total = static_cast<long long>(NB) * Cout * pblocks;
-    if (warp >= total) return;
-    const int pb = static_cast<int>(warp % pblocks);
-    const int co = static_cast<int>((warp / pblocks) % Cout);
-    const long long n = warp / (static_cast<long long>(pblocks) * Cout);
-    const float* wrow = w + static_cast<long long>(co) * Cin * K * K;
-    const float* img = in + n * Cin * H * W;
-    if (npix >= 16) {
-        // lane = output pixel
-        const int p = pb * 32 + lane;
-        if (p >= npix) return;
-        const int ho = p / Wo, wo = p % Wo;
-        float acc = bias[co];
-        for (int ci = 0; ci < Cin; ++ci) {
-            for (int kh = 0; kh < K; ++kh) {
-                const int hi = ho * stride + kh - pad;
-                if (hi < 0 || hi >= H) continue;
-                for (int kw = 0; kw < K; ++kw) {
-                    const int wi = wo * stride + kw - pad;
-                    if (wi < 0 || wi >= W) continue;
-                    acc += img[(ci * H + hi) * W + wi] * __ldg(wrow + (ci * K + kh) * K + kw);
-                }
-            }
-        }
-        out[(n * Cout + co) * npix + p] = fmaxf(acc, 0.f);
-    } else {
-        // tiny maps: lanes split the reduction, one pixel at a time
-        const int red = Cin * K * K;
-        for (int p = 0; p < npix; ++p) {
-            const int ho = p / Wo, wo = p % Wo;
-            float acc = 0.f;
-            for (int r = lane; r < red; r += 32) {
-                const int kw = r % K, kh = (r / K) % K, ci = r / (K * K);
-                const int hi = ho * stride + kh - pad, wi = wo * stride + kw - pad;
-                if (hi < 0 || hi >= H || wi < 0 || wi >= W) continue;
-                acc += img[(ci * H + hi) * W + wi] * __ldg(wrow + r);
-            }
+    const long long M = static_cast<long long>(NB) * npix;
+    const int red = CENTER ? Cin : Cin * K * K;
+    const long long m0 = static_cast<long long>(blockIdx.x) * BM;
+    const int n0 = blockIdx.y * BN;
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    // loader mapping: row/col = tid % 64, k = tid / 64 + 4 j
+    const int lrow = tid & 63, lk = tid >> 6;
+    const long long am = m0 + lrow;
+    const bool a_ok = am < M;
+    const long long an = a_ok ? am / npix : 0;
+    const int ap = a_ok ? static_cast<int>(am - an * npix) : 0;
+    const int aho = ap / Wo, awo = ap - aho * Wo;
+    const float* img = in + an * Cin * H * W;
+    const int wco = n0 + lrow;
+    const bool w_ok = wco < Cout;
+    const float* wrow = w + static_cast<long long>(w_ok ? wco : 0) * Cin * K * K;
+    float acc[4][4];
 #pragma unroll
-            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) out[(n * Cout + co) * npix + p] = fmaxf(acc + bias[co], 0.f);
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < red; k0 += BK) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int kk = lk + 4 * j;
+            const int k = k0 + kk;
+            float av = 0.f, wv = 0.f;
+            if (CENTER) {
+                if (k < red) {
+                    if (a_ok) av = __ldg(img + k);
+                    if (w_ok) wv = __ldg(wrow + k * (K * K) + (K * K) / 2);
+                }
+            } else if (k < red) {
+                const int ci = k / (K * K);
+                const int rem = k - ci * (K * K);
+                const int kh = rem / K, kw = rem - kh * K;
+                const int hi = aho * STRIDE + kh - PAD, wi = awo * STRIDE + kw - PAD;
+                if (a_ok && hi >= 0 && hi < H && wi >= 0 && wi < W) av = __ldg(img + (ci * H + hi) * W + wi);
+                if (w_ok) wv = __ldg(wrow + k);
+            }
+            As[kk][lrow] = av;
+            Ws[kk][lrow] = wv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+        const long long n = m / npix;
+        const int pp = static_cast<int>(m - n * npix);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int co = n0 + tx * 4 + j;
+            if (co < Cout) out[(n * Cout + co) * npix + pp] = fmaxf(acc[i][j] + __ldg(bias + co), 0.f);
         }
     }
 }
@@ -266,11 +299,20 @@ int Lpips::forward(const float* in0, const float* in1, float* out, int B, int C,
             LP_CHECK("lpips_maxpool");
             cur = pool; ch = oh; cw = ow;
         }
-        const int npix = h[k] * w[k];
-        const long long warps = static_cast<long long>(NB) * kChn[k] * ((npix + 31) / 32);
-        const long long blocks = (warps * 32 + 255) / 256;
-        lpips_conv_relu_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(cur, w_[k], b_[k], f[k], NB, kCin[k], ch, cw,
-                                                                                  kChn[k], h[k], w[k], kK[k], kStride[k], kPad[k]);
+        const long long M = static_cast<long long>(NB) * h[k] * w[k];
+        dim3 grid(static_cast<unsigned>((M + 63) / 64), static_cast<unsigned>((kChn[k] + 63) / 64));
+        if (k == 0)
+            lpips_conv_relu_kernel<11, 4, 2><<<grid, 256, 0, stream>>>(cur, w_[k], b_[k], f[k], NB, kCin[k], ch, cw, kChn[k],
+                                                                      h[k], w[k]);
+        else if (k == 1)
+            lpips_conv_relu_kernel<5, 1, 2><<<grid, 256, 0, stream>>>(cur, w_[k], b_[k], f[k], NB, kCin[k], ch, cw, kChn[k],
+                                                                     h[k], w[k]);
+        else if (ch == 1 && cw == 1)
+            lpips_conv_relu_kernel<3, 1, 1, true><<<grid, 256, 0, stream>>>(cur, w_[k], b_[k], f[k], NB, kCin[k], ch, cw,
+                                                                           kChn[k], h[k], w[k]);
+        else
+            lpips_conv_relu_kernel<3, 1, 1><<<grid, 256, 0, stream>>>(cur, w_[k], b_[k], f[k], NB, kCin[k], ch, cw, kChn[k],
+                                                                     h[k], w[k]);
         LP_CHECK("lpips_conv");
         cur = f[k]; ch = h[k]; cw = w[k];
     }
