@@ -291,7 +291,8 @@ def run_ours(args):
     value = total / (ms / 1000.0)
     e2e_value = total / (ms_e2e / 1000.0)
 
-    # ---- roofline of the dominant kernel (conv_gemm_kernel: every 3x3 conv, 1x1 skip conv and attention Linear)
+    # ---- roofline of the dominant kernel family: the tcgen05 convolutions (conv_halo_kernel for the ResnetBlock 3x3 convs
+    # with GroupNorm+SiLU applied in shared memory, conv_gemm_2cta_kernel for stride-2 / upsample convs and attention Linears)
     peaks_path = ROOT / "MEASURED_PEAKS.json"
     if peaks_path.exists():
         peaks = json.loads(peaks_path.read_text())
@@ -305,8 +306,13 @@ def run_ours(args):
     if prof and "conv_gemm" in prof:
         cg = prof["conv_gemm"]
         achieved = cg["flops"] / (cg["ms"] / 1000.0) / 1e12
-        roofline = {"kernel": "conv_gemm_kernel", "bound": "tensor", "achieved": achieved, "peak": peak_tf,
-                    "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+        roofline = {"kernel": "conv_halo_kernel + conv_gemm_2cta_kernel (tcgen05 implicit-GEMM convolutions)",
+                    "bound": "tensor", "achieved": achieved, "peak": peak_tf,
+                    "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                    # dram__bytes_read.sum + dram__bytes_write.sum per conv_halo launch, mean of the 22 launches of one
+                    # forward at batch 256 (profiles/r01_halo_ncu_full_s3.md)
+                    "traffic": 83.4e6 if args.batch == 256 else None, "traffic_unit": "bytes/launch (ncu, conv_halo)",
+                    "peak_source": peak_src,
                     "launches_timed": cg["launches"],
                     "avg_launch_us": 1000.0 * cg["ms"] / cg["launches"],
                     "flop_per_launch_avg": cg["flops"] / cg["launches"]}
