@@ -591,6 +591,7 @@ __global__ void __launch_bounds__(256) conv_in_reg_kernel(const float* __restric
 #pragma unroll
         for (int k = 0; k < CPT / 4; ++k) { qs[k] = 0.f; qq[k] = 0.f; }
         const float* xn = x + static_cast<size_t>(n) * CIN * S;
+#pragma unroll 4
         for (int r = p_begin + pl; r < p_end && pl < ppb; r += ppb) {
             const int dq = r / HW;
             const int r2 = r - dq * HW;
@@ -912,48 +913,63 @@ __global__ void __launch_bounds__(256) gn_apply_taps_kernel(const __half* __rest
     const int p_begin = blockIdx.x * chunk;
     const int p_end = min(S, p_begin + chunk);
     const __half* base = src + static_cast<size_t>(n) * S * C + g * CPT;
-    for (int p0 = p_begin; p0 < p_end; p0 += ppb) {  // uniform trip count: the shuffles need every lane
-        const int pp = p0 + pl;
-        const bool live = pp < p_end;
-        float z[CPT];
-        if (live) {
-            if constexpr (CPT == 8) {
-                unpack8(__ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(pp) * C)), z);
+    // 4 pixels per thread per trip, loads first (the kernel is latency-bound otherwise); uniform trip count: the
+    // shuffles need every lane
+    constexpr int U = 4;
+    for (int p0 = p_begin; p0 < p_end; p0 += U * ppb) {
+        uint4 raw8[U];
+        uint2 raw4[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int pp = p0 + u * ppb + pl;
+            if (pp < p_end) {
+                if constexpr (CPT == 8) raw8[u] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(pp) * C));
+                else raw4[u] = __ldg(reinterpret_cast<const uint2*>(base + static_cast<size_t>(pp) * C));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int pp = p0 + u * ppb + pl;
+            const bool live = pp < p_end;
+            float z[CPT];
+            if (live) {
+                if constexpr (CPT == 8) {
+                    unpack8(raw8[u], z);
+                } else {
+                    const __half2* h = reinterpret_cast<const __half2*>(&raw4[u]);
+                    const float2 t0 = __half22float2(h[0]), t1 = __half22float2(h[1]);
+                    z[0] = t0.x; z[1] = t0.y; z[2] = t1.x; z[3] = t1.y;
+                }
+#pragma unroll
+                for (int j = 0; j < CPT; ++j)  // fp16 rounding of the normalised value, like the materialised path
+                    z[j] = __half2float(__float2half_rn(silu_fast(fmaf(z[j], ga[j], gb[j]))));
             } else {
-                const uint2 raw = __ldg(reinterpret_cast<const uint2*>(base + static_cast<size_t>(pp) * C));
-                const __half2* h = reinterpret_cast<const __half2*>(&raw);
-                const float2 t0 = __half22float2(h[0]), t1 = __half22float2(h[1]);
-                z[0] = t0.x; z[1] = t0.y; z[2] = t1.x; z[3] = t1.y;
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) z[j] = 0.f;
             }
+            float v[G];
 #pragma unroll
-            for (int j = 0; j < CPT; ++j)  // fp16 rounding of the normalised value, like the materialised path
-                z[j] = __half2float(__float2half_rn(silu_fast(fmaf(z[j], ga[j], gb[j]))));
-        } else {
+            for (int k = 0; k < G; ++k) {
+                float acc = 0.f;
+                if (k < NV) {
 #pragma unroll
-            for (int j = 0; j < CPT; ++j) z[j] = 0.f;
-        }
-        float v[G];
-#pragma unroll
-        for (int k = 0; k < G; ++k) {
-            float acc = 0.f;
-            if (k < NV) {
-#pragma unroll
-                for (int j = 0; j < CPT; ++j) acc = fmaf(z[j], wr[k < NV ? k : 0][j], acc);
+                    for (int j = 0; j < CPT; ++j) acc = fmaf(z[j], wr[k < NV ? k : 0][j], acc);
+                }
+                v[k] = acc;
             }
-            v[k] = acc;
-        }
-        // transpose-reduce over the pixel's G lanes: lane g ends with the total of value g
+            // transpose-reduce over the pixel's G lanes: lane g ends with the total of value g
 #pragma unroll
-        for (int half_n = G / 2, off = G / 2; half_n >= 1; half_n >>= 1, off >>= 1) {
-            const bool hi = (g & off) != 0;
+            for (int half_n = G / 2, off = G / 2; half_n >= 1; half_n >>= 1, off >>= 1) {
+                const bool hi = (g & off) != 0;
 #pragma unroll
-            for (int i = 0; i < half_n; ++i) {
-                const float send = hi ? v[i] : v[i + half_n];
-                const float keep = hi ? v[i + half_n] : v[i];
-                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                for (int i = 0; i < half_n; ++i) {
+                    const float send = hi ? v[i] : v[i + half_n];
+                    const float keep = hi ? v[i + half_n] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
             }
+            if (live && g < NV) d_out[(static_cast<size_t>(n) * S + pp) * NV + g] = v[0];
         }
-        if (live && g < NV) d_out[(static_cast<size_t>(n) * S + pp) * NV + g] = v[0];
     }
 }
 

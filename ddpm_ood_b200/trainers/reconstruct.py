@@ -23,6 +23,20 @@ from ..reconstruction import BatchReconstructor, ReconConfig
 from .base import BaseTrainer
 
 
+def gather_scores(scores: torch.Tensor, names, device):
+    """The one collective of the path (reference: `dist.all_gather_object(results)`, trainers/reconstruct.py:238-242):
+    every rank contributes its [rows, 3] float64 (t, perceptual_difference, mse) tensor - equal row counts, because the
+    image partition is even_divisible - with ONE all-gather (NCCL over NVLink on GPUs, gloo in the CPU tests), plus the
+    file names as objects. Returns (all rows in rank order, all names in the same order) on every rank."""
+    world = dist.get_world_size()
+    local = scores.to(device).contiguous()
+    gathered = torch.empty((world * local.shape[0], local.shape[1]), dtype=local.dtype, device=device)
+    dist.all_gather_into_tensor(gathered, local)
+    all_names = [None] * world
+    dist.all_gather_object(all_names, list(names))
+    return gathered.cpu(), [n for sub in all_names for n in sub]
+
+
 class Reconstruct(BaseTrainer):
     def __init__(self, args):
         super().__init__(args)
@@ -92,14 +106,7 @@ class Reconstruct(BaseTrainer):
                 print(f"Took {t2-t1}s for a batch size of {B}")
         scores = torch.stack([torch.cat(ts), torch.cat(pds), torch.cat(mses)], dim=1) if ts else torch.zeros((0, 3), dtype=torch.float64)
         if dist.is_initialized():
-            world = dist.get_world_size()
-            local = scores.to(self.device)
-            gathered = torch.empty((world * local.shape[0], 3), dtype=local.dtype, device=self.device)
-            dist.all_gather_into_tensor(gathered, local)  # NCCL over NVLink; even_divisible partition => equal sizes
-            all_names = [None] * world
-            dist.all_gather_object(all_names, names)
-            names = [n for sub in all_names for n in sub]
-            scores = gathered.cpu()
+            scores, names = gather_scores(scores, names, self.device)
             local_rank = int(os.environ["LOCAL_RANK"])
             if local_rank != 0:
                 f = open(os.devnull, "w")
