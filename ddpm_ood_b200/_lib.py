@@ -100,6 +100,7 @@ class DdpmError(RuntimeError):
 SIGNATURES = {
     "ddpm_last_error": (C.c_char_p, []),
     "ddpm_abi_version": (C.c_int, []),
+    "ddpm_struct_sizes": (None, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ddpm_conv_forward": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "ddpm_conv_stats_parts": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "ddpm_conv_halo_stats_parts": (C.c_int, [C.c_int, C.c_int]),

@@ -85,7 +85,14 @@ int pack_upconv_weight(const float* w, int Cout, int Cin, int dims, __half* dst,
 extern "C" {
 
 const char* ddpm_last_error(void) { return ddpm::last_error(); }
-int ddpm_abi_version(void) { return 3; }
+int ddpm_abi_version(void) { return 4; }
+
+void ddpm_struct_sizes(int* conv_args, int* unet_config, int* plms_step, int* op_profile) {
+    if (conv_args) *conv_args = static_cast<int>(sizeof(ddpm_conv_args));
+    if (unet_config) *unet_config = static_cast<int>(sizeof(ddpm_unet_config));
+    if (plms_step) *plms_step = static_cast<int>(sizeof(ddpm_plms_step));
+    if (op_profile) *op_profile = static_cast<int>(sizeof(ddpm_op_profile));
+}
 
 int ddpm_conv_forward(const ddpm_conv_args* a, void* stream) {
     if (!a) { ddpm::set_error("ddpm_conv_forward: null args"); return 2; }

@@ -196,6 +196,9 @@ DDPM_API int ddpm_unet_run_chain(void* handle, int n_steps, const int* timesteps
                                  float* sample, float* ring, float* stash, int N, int D, int H, int W, void* workspace,
                                  long long workspace_bytes, void* stream);
 
+/* sizeof() of the structs above as this library was compiled (binding self-check: a ctypes mirror must agree). */
+DDPM_API void ddpm_struct_sizes(int* conv_args, int* unet_config, int* plms_step, int* op_profile);
+
 /* ------------------------------------------------------------------------------------------------ scoring
  * recon = clamp(x / b_scale, 0, 1) and mse[n] = mean((x0 - recon)^2): src/trainers/reconstruct.py:167-168,188-191. */
 DDPM_API int ddpm_clamp_mse(const float* x, const float* x0, float b_scale, float* recon, float* mse, int N,
