@@ -247,4 +247,145 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint
             }
 }
 
+// Store-mode epilogue of the halo-tile kernel (conv_halo.cu): same results as conv_epilogue_tile's EPI_STORE path with
+// the per-column addend staged in shared memory, restructured for latency - 16-column chunks with double-buffered
+// TMEM loads (chunk c + 1 is in flight while chunk c is converted, stored and reduced), half the live registers.
+// s_add: [slot][BN] fp32 (bias + chan_add), slot = 0 for region tiles / the row's image for pair tiles.
+template <int BN>
+__device__ __forceinline__ void conv_epilogue_tile16(const ConvGemmParams& p, uint32_t t_addr, int m_tile, int n_tile,
+                                                     int q, int lane, const float* s_add) {
+    const int row = q * 32 + lane;
+    int w, h, n;
+    int tile_sp = 0;
+    if (p.pair_rows) {  // row = h * 16 + n' * 8 + w of images 2 * tile + n'
+        w = row & 7;
+        h = row >> 4;
+        n = m_tile * 2 + ((row >> 3) & 1);
+    } else {            // 8 x 16 region of one image (bd == bn == 1)
+        int t = m_tile;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h; t /= p.tiles_h;
+        n = t;
+        w = tw * p.bw + row % p.bw;
+        h = th * p.bh + row / p.bw;
+        tile_sp = th * p.tiles_w + tw;
+    }
+    const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
+    const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
+    const int col_base = n_tile * BN;
+    const float* addend = s_add + (p.pair_rows ? ((row >> 3) & 1) * BN : 0);
+    float* st_base = nullptr;
+    if (p.stats_out && !(p.dbg & 8)) {
+        if (p.pair_rows) {
+            // lanes 0-7 / 16-23 hold image 0, lanes 8-15 / 24-31 image 1; part = this warp
+            const int n_l = m_tile * 2 + ((lane >> 3) & 1);
+            if (n_l < p.N) st_base = p.stats_out + (static_cast<size_t>(n_l) * p.stats_parts + q) * (p.Cout >> 1);
+        } else {
+            const int n_w = m_tile / (p.tiles_w * p.tiles_h);  // all 32 rows of a warp lie in one image
+            if (n_w < p.N) st_base = p.stats_out + (static_cast<size_t>(n_w) * p.stats_parts + tile_sp * 4 + q) * (p.Cout >> 1);
+        }
+    }
+    const bool want_stats = p.stats_out && !(p.dbg & 8);
+    __half* out_row = p.out + pix * static_cast<size_t>(p.Cout) + col_base;
+    const __half* res_row = p.residual ? p.residual + pix * static_cast<size_t>(p.Cout) + col_base : nullptr;
+
+    auto process = [&](const int c, const uint32_t (&v)[16]) {
+        uint32_t packed[8];
+        if (valid) {
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            const float4* sa4 = reinterpret_cast<const float4*>(addend + c * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 b4 = sa4[j];
+                f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+            }
+            if (res_row) {
+                const uint4* r4 = reinterpret_cast<const uint4*>(res_row + c * 16);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint4 rv = __ldg(r4 + j);
+                    const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 ff = __half22float2(h2[e]);
+                        f[8 * j + 2 * e] += ff.x;
+                        f[8 * j + 2 * e + 1] += ff.y;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                __half2 hh = __floats2half2_rn(f[j], f[j + 1]);
+                packed[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+            }
+            if (!(p.dbg & 16)) {
+                uint4* d4 = reinterpret_cast<uint4*>(out_row + c * 16);
+                d4[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                d4[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) packed[j] = 0u;
+        }
+        if (want_stats) {
+            // quad sums of the ROUNDED values (what GroupNorm reads back): sv[0..3] sums, sv[4..7] sums of squares
+            float sv[8];
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&packed[2 * qd]));
+                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&packed[2 * qd + 1]));
+                sv[qd] = (a.x + a.y) + (b.x + b.y);
+                sv[4 + qd] = (a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y);
+            }
+            const int quad0 = (col_base + c * 16) >> 2;
+            if (p.pair_rows) {
+                // two images per warp: add the two rows of each image (lane ^ 16), then transpose-reduce inside the
+                // 8-lane groups; lanes 0-15 end with one value: b2 -> sum / squares, b1 b0 -> quad, b3 -> image
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sv[i] += __shfl_xor_sync(0xffffffffu, sv[i], 16);
+#pragma unroll
+                for (int half_n = 4, off = 4; half_n >= 1; half_n >>= 1, off >>= 1) {
+                    const bool hi = (lane & off) != 0;
+#pragma unroll
+                    for (int i = 0; i < half_n; ++i) {
+                        const float send = hi ? sv[i] : sv[i + half_n];
+                        const float keep = hi ? sv[i + half_n] : sv[i];
+                        sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
+                }
+                if (st_base && lane < 16) st_base[(quad0 + (lane & 3)) * 2 + ((lane >> 2) & 1)] = sv[0];
+            } else {
+                // transpose-reduce over the warp's 32 pixels: b4 -> sum / squares, b3 b2 -> quad, then two butterflies
+#pragma unroll
+                for (int half_n = 4, off = 16; half_n >= 1; half_n >>= 1, off >>= 1) {
+                    const bool hi = (lane & off) != 0;
+#pragma unroll
+                    for (int i = 0; i < half_n; ++i) {
+                        const float send = hi ? sv[i] : sv[i + half_n];
+                        const float keep = hi ? sv[i + half_n] : sv[i];
+                        sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
+                }
+                sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 2);
+                sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
+                if (st_base && (lane & 3) == 0) st_base[(quad0 + ((lane >> 2) & 3)) * 2 + (lane >> 4)] = sv[0];
+            }
+        }
+    };
+
+    uint32_t va[16], vb[16];
+    ptx::tmem_ld_32x16(t_addr, va);
+#pragma unroll 1
+    for (int c = 0; c < BN / 16; c += 2) {
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x16(t_addr + (c + 1) * 16, vb);
+        process(c, va);
+        ptx::tmem_ld_wait();
+        if (c + 2 < BN / 16) ptx::tmem_ld_32x16(t_addr + (c + 2) * 16, va);
+        process(c + 1, vb);
+    }
+}
+
 }  // namespace ddpm

@@ -119,6 +119,11 @@ __device__ __forceinline__ void transform_chunk(uint4& raw, const float (&ga)[8]
 // Rows a transform thread visits. Region tiles: row = (tid >> 3) + 32 i. Pair tiles: threads 0-127 own image 0,
 // 128-255 image 1; pixel k = ((tid & 127) >> 3) + 16 i of the (haloed) image sits in row ((k / wbox) * 2 + image) * wbox
 // + k % wbox. Returns the tile row and the pixel's coordinates inside the (haloed) box.
+// Position of channel c's (scale, shift) pair in the shared-memory table: inside each 64-channel chunk the pairs are
+// stored [pair-of-channels j (4)][8-channel group cg (8)][2], so that the 8 lanes of a quarter warp (cg = 0..7) read 128
+// contiguous bytes (channel-major order made every such load a 4-way bank conflict).
+__device__ __forceinline__ int ab_slot(int c) { return (c & ~63) + ((c & 7) >> 1) * 16 + ((c & 63) >> 3) * 2 + (c & 1); }
+
 template <bool PAIR>
 __device__ __forceinline__ void xform_row(int tid, int i, bool halo, int& row, int& hh, int& ww, bool& ok) {
     if (PAIR) {
@@ -386,10 +391,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                         gn_scale_shift_from_parts(tid, n, g.C0, g.st0, g.parts0, g.C1, g.st1, g.parts1, g.gamma, g.beta, g.S,
                                                   (g.C0 + g.C1) / g.groups, g.eps, s_gn, s_gn + kMaxGnChannels / 4,
                                                   reinterpret_cast<float2*>(s_gn + kMaxGnChannels / 2), xsync,
-                                                  [&](int c, float a, float b) { dst[c] = make_float2(a, b); });
+                                                  [&](int c, float a, float b) { dst[ab_slot(c)] = make_float2(a, b); });
                     } else {
                         const float2* src = hp.ab + static_cast<size_t>(n) * hp.ab_C;
-                        for (int c = tid; c < hp.ab_C; c += kXformWarps * 32) dst[c] = __ldg(src + c);
+                        for (int c = tid; c < hp.ab_C; c += kXformWarps * 32) dst[ab_slot(c)] = __ldg(src + c);
                     }
                 }
                 xsync();
@@ -399,7 +404,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 const bool halo = hp.seg_taps[seg] == 9;
                 for (int chunk = 0; chunk < p.seg_chunks[seg]; ++chunk) {
                     if (gn) {
-                        const uint32_t ab_chunk = ptx::smem_u32(s_ab + hp.seg_ab_off[seg] + chunk * kBlockK + cg * 8);
+                        const uint32_t ab_chunk = ptx::smem_u32(s_ab + hp.seg_ab_off[seg] + chunk * kBlockK) + cg * 16;
 #pragma unroll
                         for (int mt = 0; mt < MT; ++mt) {
                             uint32_t off[kRowIters];
@@ -416,7 +421,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                             float ga[8], gb[8], ga2[8], gb2[8];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const uint4 v = lds128(ab_chunk + (slot * kMaxGnChannels * 8 + j * 16));
+                                const uint4 v = lds128(ab_chunk + (slot * kMaxGnChannels * 8 + j * 128));
                                 ga[2 * j] = __uint_as_float(v.x); gb[2 * j] = __uint_as_float(v.y);
                                 ga[2 * j + 1] = __uint_as_float(v.z); gb[2 * j + 1] = __uint_as_float(v.w);
                             }
@@ -479,9 +484,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             if (!(hp.dbg & 2)) {
 #pragma unroll 1
                 for (int mt = 0; mt < MT; ++mt)
-                    conv_epilogue_tile<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * C::kAccCols + mt * BN,
-                                           (m_group * 2 + static_cast<int>(rank)) * MT + mt, n_tile, 0, q, lane,
-                                           s_add + (PAIR ? 0 : mt * BN));
+                    conv_epilogue_tile16<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * C::kAccCols + mt * BN,
+                                             (m_group * 2 + static_cast<int>(rank)) * MT + mt, n_tile, q, lane,
+                                             s_add + (PAIR ? 0 : mt * BN));
             }
             ptx::tc_fence_before();
             __syncwarp();
