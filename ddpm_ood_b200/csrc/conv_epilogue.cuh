@@ -247,31 +247,44 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint
             }
 }
 
-// Store-mode epilogue of the halo-tile kernel (conv_halo.cu): same results as conv_epilogue_tile's EPI_STORE path with
+// Store-mode epilogue of the halo-tile kernel (conv_halo.cu) and of the CTA-pair im2col kernel: same results as conv_epilogue_tile's EPI_STORE path with
 // the per-column addend staged in shared memory, restructured for latency - 16-column chunks with double-buffered
 // TMEM loads (chunk c + 1 is in flight while chunk c is converted, stored and reduced), half the live registers.
 // s_add: [slot][BN] fp32 (bias + chan_add), slot = 0 for region tiles / the row's image for pair tiles.
 template <int BN>
 __device__ __forceinline__ void conv_epilogue_tile16(const ConvGemmParams& p, uint32_t t_addr, int m_tile, int n_tile,
-                                                     int q, int lane, const float* s_add) {
+                                                     int sub, int q, int lane, const float* s_add) {
     const int row = q * 32 + lane;
-    int w, h, n;
-    int tile_sp = 0;
-    if (p.pair_rows) {  // row = h * 16 + n' * 8 + w of images 2 * tile + n'
+    int w, h, d = 0, n;
+    int part = 0, n_w = 0;  // statistics part / image of this warp's 32 rows (region and im2col tiles)
+    if (p.pair_rows) {  // conv_halo pair tiles: row = h * 16 + n' * 8 + w of images 2 * tile + n'
         w = row & 7;
         h = row >> 4;
         n = m_tile * 2 + ((row >> 3) & 1);
-    } else {            // 8 x 16 region of one image (bd == bn == 1)
+    } else {            // tile box (bw, bh, bd, bn) of the tile grid (tiles_w, tiles_h, tiles_d, tiles_n)
         int t = m_tile;
         const int tw = t % p.tiles_w; t /= p.tiles_w;
         const int th = t % p.tiles_h; t /= p.tiles_h;
-        n = t;
-        w = tw * p.bw + row % p.bw;
-        h = th * p.bh + row / p.bw;
-        tile_sp = th * p.tiles_w + tw;
+        const int td = t % p.tiles_d; t /= p.tiles_d;
+        const int tn = t;
+        int r = row;
+        w = tw * p.bw + r % p.bw; r /= p.bw;
+        h = th * p.bh + r % p.bh; r /= p.bh;
+        d = td * p.bd + r % p.bd; r /= p.bd;
+        n = tn * p.bn + r;
+        const int R = p.bw * p.bh * p.bd;  // pixels of one image inside the tile box (a multiple of 32 with statistics)
+        n_w = tn * p.bn + (q * 32) / R;
+        part = sub * (p.stats_parts / p.num_phases) + ((td * p.tiles_h + th) * p.tiles_w + tw) * (R >> 5) + ((q * 32) % R) / 32;
     }
-    const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
-    const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
+    const bool valid = (w < p.W) && (h < p.H) && (d < p.D) && (n < p.N);
+    size_t pix;
+    if (p.num_phases > 1) {  // sub-pixel scatter into the doubled output grid
+        const int od = p.phase3d ? 2 * d + ((sub >> 2) & 1) : d;
+        const int Do = p.phase3d ? 2 * p.D : p.D;
+        pix = ((static_cast<size_t>(n) * Do + od) * (2 * p.H) + (2 * h + ((sub >> 1) & 1))) * (2 * p.W) + (2 * w + (sub & 1));
+    } else {
+        pix = ((static_cast<size_t>(n) * p.D + d) * p.H + h) * p.W + w;
+    }
     const int col_base = n_tile * BN;
     const float* addend = s_add + (p.pair_rows ? ((row >> 3) & 1) * BN : 0);
     float* st_base = nullptr;
@@ -280,9 +293,8 @@ __device__ __forceinline__ void conv_epilogue_tile16(const ConvGemmParams& p, ui
             // lanes 0-7 / 16-23 hold image 0, lanes 8-15 / 24-31 image 1; part = this warp
             const int n_l = m_tile * 2 + ((lane >> 3) & 1);
             if (n_l < p.N) st_base = p.stats_out + (static_cast<size_t>(n_l) * p.stats_parts + q) * (p.Cout >> 1);
-        } else {
-            const int n_w = m_tile / (p.tiles_w * p.tiles_h);  // all 32 rows of a warp lie in one image
-            if (n_w < p.N) st_base = p.stats_out + (static_cast<size_t>(n_w) * p.stats_parts + tile_sp * 4 + q) * (p.Cout >> 1);
+        } else if (n_w < p.N) {  // all 32 rows of a warp lie in one image (host guarantees it)
+            st_base = p.stats_out + (static_cast<size_t>(n_w) * p.stats_parts + part) * (p.Cout >> 1);
         }
     }
     const bool want_stats = p.stats_out && !(p.dbg & 8);

@@ -214,7 +214,7 @@ struct Cfg2 {
     static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
     static constexpr int kAccCols = MT * BN;
     static constexpr int kTmemCols = 2 * kAccCols;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + BN * 4 /*epilogue addend row*/;
 };
 
 template <int BN, int MT>
@@ -231,6 +231,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     uint64_t* tfull_bar = bars + 2 * C::kStages;  // per CTA: MMA (multicast commit) -> this CTA's epilogue
     uint64_t* tempty_bar = tfull_bar + 2;         // leader's copy: epilogue warps of both CTAs -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* s_add = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes + 256);  // [BN] bias of the item's N tile
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -359,12 +360,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
             const int n_tile = item - g * p.num_n_tiles;
             const int sub = g / gpp;
             const int m_group = g - sub * gpp;
+            // fast path (plain store epilogue without a per-image addend): bias row staged in shared memory, 16-column
+            // chunks with double-buffered TMEM loads (conv_epilogue_tile16)
+            const bool fast = p.mode == EPI_STORE && p.chan_add == nullptr;
+            if (fast) {
+                asm volatile("bar.sync 2, 128;" ::: "memory");  // the previous item's readers are done
+                for (int i = threadIdx.x - 128; i < BN; i += 128) s_add[i] = p.bias ? __ldg(p.bias + n_tile * BN + i) : 0.f;
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+            }
             ptx::mbar_wait(&tfull_bar[as], aparity);
             ptx::tc_fence_after();
 #pragma unroll 1
-            for (int mt = 0; mt < MT; ++mt)
-                conv_epilogue_tile<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * C::kAccCols + mt * BN,
-                                       (m_group * 2 + static_cast<int>(rank)) * MT + mt, n_tile, sub, q, lane);
+            for (int mt = 0; mt < MT; ++mt) {
+                const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * C::kAccCols + mt * BN;
+                const int m_tile = (m_group * 2 + static_cast<int>(rank)) * MT + mt;
+                if (fast) conv_epilogue_tile16<BN>(p, t_addr, m_tile, n_tile, sub, q, lane, s_add);
+                else conv_epilogue_tile<BN>(p, t_addr, m_tile, n_tile, sub, q, lane);
+            }
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_leader(&tempty_bar[as]);

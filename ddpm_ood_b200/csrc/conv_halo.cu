@@ -485,7 +485,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 #pragma unroll 1
                 for (int mt = 0; mt < MT; ++mt)
                     conv_epilogue_tile16<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * C::kAccCols + mt * BN,
-                                             (m_group * 2 + static_cast<int>(rank)) * MT + mt, n_tile, q, lane,
+                                             (m_group * 2 + static_cast<int>(rank)) * MT + mt, n_tile, 0, q, lane,
                                              s_add + (PAIR ? 0 : mt * BN));
             }
             ptx::tc_fence_before();
