@@ -3,6 +3,8 @@
 
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "attention.cuh"
@@ -138,7 +140,18 @@ int ddpm_conv_forward(const ddpm_conv_args* a, void* stream) {
         int rc = ddpm::conv_halo_prepare(q, a->gn_scale_shift, a->gn_channels, ddpm::num_sms(), &hl,
                                          from_stats ? &src : nullptr);
         if (rc) return rc;
-        return ddpm::conv_halo_launch(hl, static_cast<cudaStream_t>(stream));
+        rc = ddpm::conv_halo_launch(hl, static_cast<cudaStream_t>(stream));
+        if (!rc && hl.p.dbg_cycles && getenv("DDPM_HALO_CYCLES_PRINT")) {  // experiment only
+            long long h[4 * 74];
+            if (!ddpm::conv_halo_read_cycles(hl, h, 4 * 74)) {
+                double s[4] = {0, 0, 0, 0};
+                const int nc = hl.grid / 2;
+                for (int i = 0; i < nc; ++i) for (int k = 0; k < 4; ++k) s[k] += static_cast<double>(h[4 * i + k]);
+                fprintf(stderr, "halo cycles (mean over %d clusters): total %.0f  wait_tempty %.0f  wait_a_ready %.0f  wait_b_full %.0f\n",
+                        nc, s[0] / nc, s[1] / nc, s[2] / nc, s[3] / nc);
+            }
+        }
+        return rc;
     }
     if (a->gn_scale_shift) { ddpm::set_error("ddpm_conv_forward: gn_scale_shift needs impl 3"); return 2; }
     ddpm::ConvLaunch l;

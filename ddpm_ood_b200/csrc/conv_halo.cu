@@ -62,19 +62,6 @@ __device__ __forceinline__ uint64_t make_desc_k128_sbo(uint32_t smem_addr, uint3
     return d;
 }
 
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// One haloed-tile row chunk (8 channels of one pixel): z = silu(x * a + b) -> fp16, in place. a2/b2 = -log2(e) * (a, b),
-// so the exponent argument is one FFMA: silu(y) = y / (1 + 2^(x * a2 + b2)). Two MUFU ops per element (ex2, rcp).
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -82,14 +69,6 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 }
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
-// z = silu(x * a + b) with a2/b2 = -log2(e) * (a, b): the exponent argument is one FFMA,
-// silu(y) = y / (1 + 2^(x * a2 + b2)); ex2(+inf-ish) -> +inf -> rcp -> 0 -> y * 0 = -0 for very negative y.
-__device__ __forceinline__ float silu_affine(float x, float a, float b, float a2, float b2) {
-    const float y = fmaf(x, a, b);
-    const float d = 1.0f + ex2_approx(fmaf(x, a2, b2));
-    return y * rcp_approx(d);
 }
 
 // GroupNorm without activation (the AttentionBlock norm): z = x * a + b
@@ -102,23 +81,26 @@ __device__ __forceinline__ void affine_chunk(uint4& raw, const float (&ga)[8], c
     }
 }
 
-// 8 channels of one haloed-tile pixel (one 16-byte chunk), in registers
-__device__ __forceinline__ void transform_chunk(uint4& raw, const float (&ga)[8], const float (&gb)[8],
-                                                const float (&ga2)[8], const float (&gb2)[8]) {
+// GroupNorm + SiLU of 8 channels of one pixel (one 16-byte chunk), in registers. tanh form of SiLU:
+// silu(y) = h + h * tanh(h), h = y / 2 -> one MUFU op and two FFMAs per element (the exp / rcp form needs two MUFU ops
+// and five FP32 instructions, and the transform warps are instruction-issue bound). tanh.approx.f32 has a relative
+// error of 2^-11 - the size of the fp16 rounding applied right after; measured end-to-end parity is unchanged
+// (1.2e-4 vs the fp32 oracle over 98-step chains). ga/gb hold scale / 2 and shift / 2.
+__device__ __forceinline__ void transform_chunk(uint4& raw, const float (&ga)[8], const float (&gb)[8]) {
     __half2* h2 = reinterpret_cast<__half2*>(&raw);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const float2 f = __half22float2(h2[e]);
-        h2[e] = __floats2half2_rn(silu_affine(f.x, ga[2 * e], gb[2 * e], ga2[2 * e], gb2[2 * e]),
-                                  silu_affine(f.y, ga[2 * e + 1], gb[2 * e + 1], ga2[2 * e + 1], gb2[2 * e + 1]));
+        const float h0 = fmaf(f.x, ga[2 * e], gb[2 * e]), h1 = fmaf(f.y, ga[2 * e + 1], gb[2 * e + 1]);  // ga/gb hold a/2, b/2
+        float t0, t1;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+        h2[e] = __floats2half2_rn(fmaf(h0, t0, h0), fmaf(h1, t1, h1));
     }
 }
 
 }  // namespace
 
-// Rows a transform thread visits. Region tiles: row = (tid >> 3) + 32 i. Pair tiles: threads 0-127 own image 0,
-// 128-255 image 1; pixel k = ((tid & 127) >> 3) + 16 i of the (haloed) image sits in row ((k / wbox) * 2 + image) * wbox
-// + k % wbox. Returns the tile row and the pixel's coordinates inside the (haloed) box.
 // Position of channel c's (scale, shift) pair in the shared-memory table: inside each 64-channel chunk the pairs are
 // stored [pair-of-channels j (4)][8-channel group cg (8)][2], so that the 8 lanes of a quarter warp (cg = 0..7) read 128
 // contiguous bytes (channel-major order made every such load a 4-way bank conflict).
@@ -227,11 +209,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                     n0[mt] = n;
                 }
             }
-            for (int seg = 0; seg < p.n_seg; ++seg) {
+            for (int st = 0; st < hp.n_stages; ++st) {  // (segment, 64-channel chunk) in the host's schedule order
+                const int seg = hp.sched_seg[st], chunk = hp.sched_chunk[st];
                 const int halo = hp.seg_taps[seg] == 9 ? 1 : 0;
                 const uint32_t bytes = (halo ? (PAIR ? kHaloRowsPair : kHaloRowsRegion) : kTileW * kTileH) * 128u;
                 const CUtensorMap* ma = seg == 0 ? &p.tmA[0] : (seg == 1 ? &p.tmA[1] : &p.tmA[2]);
-                for (int chunk = 0; chunk < p.seg_chunks[seg]; ++chunk) {
+                {
                     ptx::mbar_wait(&a_empty[sa], pa ^ 1);
                     if (ptx::elect_one()) {
                         ptx::mbar_arrive_expect_tx(&a_full[sa], MT * bytes);
@@ -257,9 +240,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         for (int item = cluster_id; item < total_items; item += num_clusters) {
             const int n_tile = item % p.num_n_tiles;
             const int brow = n_tile * BN + static_cast<int>(rank) * (BN / 2);
-            for (int seg = 0; seg < p.n_seg; ++seg) {
+            for (int st = 0; st < hp.n_stages; ++st) {  // (segment, 64-channel chunk) in the host's schedule order
+                const int seg = hp.sched_seg[st], chunk = hp.sched_chunk[st];
                 const int taps = hp.seg_taps[seg];
-                for (int chunk = 0; chunk < p.seg_chunks[seg]; ++chunk) {
+                {
                     const int kc = hp.seg_kcol0[seg] + chunk * kBlockK;
                     for (int tap = 0; tap < taps; ++tap) {
                         ptx::mbar_wait(&b_empty[sb], pb ^ 1);
@@ -281,17 +265,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             constexpr uint32_t idesc = ptx::make_idesc_f16(2 * kBlockM, BN);
             int sa = 0, sb = 0, as = 0;
             uint32_t pa = 0, pb = 0, pt = 0;
+            long long cyc_t = 0, cyc_a = 0, cyc_b = 0;
+            const bool prof = hp.dbg_cycles != nullptr;
+            const long long t_begin = prof ? clock64() : 0;
             for (int item = cluster_id; item < total_items; item += num_clusters) {
+                long long t0 = prof ? clock64() : 0;
                 ptx::mbar_wait(&tempty_bar[as], pt ^ 1);
+                if (prof) cyc_t += clock64() - t0;
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * C::kAccCols;
                 uint32_t accumulate = 0;
-                for (int seg = 0; seg < p.n_seg; ++seg) {
+                for (int st = 0; st < hp.n_stages; ++st) {  // (segment, 64-channel chunk) in the host's schedule order
+                const int seg = hp.sched_seg[st];
                     const int taps = hp.seg_taps[seg];
                     const uint32_t pitch = taps == 9 ? (kTileW + 2) : kTileW;  // smem rows per image row
                     const uint64_t desc_hi = make_desc_k128_sbo(0, pitch * 128);
-                    for (int chunk = 0; chunk < p.seg_chunks[seg]; ++chunk) {
+                    {
+                        t0 = prof ? clock64() : 0;
                         ptx::mbar_wait(&a_ready[sa], pa);
+                        if (prof) cyc_a += clock64() - t0;
                         ptx::tc_fence_after();
                         const uint32_t a_base = ptx::smem_u32(smem_a + sa * C::kAStageBytes);
                         for (int tap = 0; tap < taps; ++tap) {
@@ -299,7 +291,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                             const uint32_t row0 = taps == 9 ? (tap / 3) * (PAIR ? 2 * pitch : pitch) + (tap % 3) : 0;
                             const uint64_t da0 = desc_hi | ((a_base + row0 * 128) >> 4);
                             const uint64_t db0 = ptx::make_desc_k128(ptx::smem_u32(smem_b + sb * C::kBHalfBytes));
+                            t0 = prof ? clock64() : 0;
                             ptx::mbar_wait(&b_full[sb], pb);
+                            if (prof) cyc_b += clock64() - t0;
                             ptx::tc_fence_after();
                             if (ptx::elect_one()) {
 #pragma unroll
@@ -324,6 +318,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 __syncwarp();
                 if (++as == 2) { as = 0; pt ^= 1; }
             }
+            if (prof && lane == 0) {
+                long long* o = hp.dbg_cycles + 4 * cluster_id;
+                o[0] = clock64() - t_begin; o[1] = cyc_t; o[2] = cyc_a; o[3] = cyc_b;
+            }
         }
     } else if (warp >= kXformWarp0 && warp < kXformWarp0 + kXformWarps) {
         // ================================================================= transform: GroupNorm scale/shift (+ SiLU), in place
@@ -333,7 +331,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         const int tid = threadIdx.x - kXformWarp0 * 32;
         const int cg = tid & 7;
         constexpr int kRowIters = PAIR ? 7 : 6;
-        constexpr float kNegLog2e = -1.4426950408889634f;
         const bool any_gn = (hp.ab != nullptr || hp.gn_from_stats) && !(hp.dbg & 1);
         const uint32_t smem_a_u32 = ptx::smem_u32(smem_a);
         const int slot_of_thread = PAIR ? (tid >> 7) : 0;
@@ -399,10 +396,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 }
                 xsync();
             }
-            for (int seg = 0; seg < p.n_seg; ++seg) {
+            for (int st = 0; st < hp.n_stages; ++st) {  // (segment, 64-channel chunk) in the host's schedule order
+                const int seg = hp.sched_seg[st], chunk = hp.sched_chunk[st];
                 const int gn = (hp.dbg & 1) ? 0 : hp.seg_gn[seg];
                 const bool halo = hp.seg_taps[seg] == 9;
-                for (int chunk = 0; chunk < p.seg_chunks[seg]; ++chunk) {
+                {
                     if (gn) {
                         const uint32_t ab_chunk = ptx::smem_u32(s_ab + hp.seg_ab_off[seg] + chunk * kBlockK) + cg * 16;
 #pragma unroll
@@ -418,15 +416,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                                 if (!halo && ok && tn[mt] < p.N && th0[mt] + hh < p.H && tw0[mt] + ww < p.W) m |= 1u << i;
                             }
                             const int slot = PAIR ? slot_of_thread : mt;
-                            float ga[8], gb[8], ga2[8], gb2[8];
+                            float ga[8], gb[8];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const uint4 v = lds128(ab_chunk + (slot * kMaxGnChannels * 8 + j * 128));
                                 ga[2 * j] = __uint_as_float(v.x); gb[2 * j] = __uint_as_float(v.y);
                                 ga[2 * j + 1] = __uint_as_float(v.z); gb[2 * j + 1] = __uint_as_float(v.w);
                             }
+                            if (gn == 1) {  // SiLU in tanh form works on y / 2
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) { ga2[j] = ga[j] * kNegLog2e; gb2[j] = gb[j] * kNegLog2e; }
+                                for (int j = 0; j < 8; ++j) { ga[j] *= 0.5f; gb[j] *= 0.5f; }
+                            }
                             if (mt == 0) ptx::mbar_wait(&a_full[sa], pa);
                             const uint32_t tile = smem_a_u32 + sa * C::kAStageBytes + mt * kATileBytes;
                             // all loads first (6-7 rows in flight), then the math, then the stores
@@ -437,7 +437,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 #pragma unroll
                             for (int i = 0; i < kRowIters; ++i) {
                                 if (m & (1u << i)) {
-                                    if (gn == 1) transform_chunk(raw[i], ga, gb, ga2, gb2);
+                                    if (gn == 1) transform_chunk(raw[i], ga, gb);
                                     else affine_chunk(raw[i], ga, gb);
                                     sts128(tile + off[i], raw[i]);
                                 }
@@ -627,6 +627,31 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_cha
         if (r != CUDA_SUCCESS) { set_error("conv_halo: cuTensorMapEncodeTiled(A seg %d) failed: %d", s, (int)r); return 3; }
     }
     p.num_kb = kb;
+    // K-loop order: 3x3 chunks ("heavy": 9 taps of MMAs per staged tile) and 1x1 chunks ("light": one tap) interleaved.
+    // Light stages are consumed faster than the 3-deep A ring can refill them (one TMA round trip per stage), so a run of
+    // them starves the MMA warp (measured: 42 % of the kernel waiting on a_ready with the 1x1 skip segments at the end);
+    // spreading them between the heavy chunks lets every refill hide behind 9 taps of work.
+    {
+        int heavy_seg[64], heavy_chunk[64], light_seg[64], light_chunk[64], nh = 0, nl = 0;
+        for (int s = 0; s < q.n_seg; ++s)
+            for (int c = 0; c < p.seg_chunks[s]; ++c) {
+                if (nh + nl >= kMaxStagesPerItem) { set_error("conv_halo: more than %d K stages per item", kMaxStagesPerItem); return 2; }
+                if (hp.seg_taps[s] == 9) { heavy_seg[nh] = s; heavy_chunk[nh++] = c; }
+                else { light_seg[nl] = s; light_chunk[nl++] = c; }
+            }
+        int n = 0, li = 0;
+        for (int h = 0; h < nh; ++h) {
+            hp.sched_seg[n] = static_cast<uint8_t>(heavy_seg[h]); hp.sched_chunk[n++] = static_cast<uint8_t>(heavy_chunk[h]);
+            const int take = (nl - li + (nh - h) - 1) / (nh - h);  // spread the remaining lights over the remaining heavies
+            for (int t = 0; t < take; ++t, ++li) {
+                hp.sched_seg[n] = static_cast<uint8_t>(light_seg[li]); hp.sched_chunk[n++] = static_cast<uint8_t>(light_chunk[li]);
+            }
+        }
+        for (; li < nl; ++li) {  // no heavy chunk at all (pure 1x1 conv)
+            hp.sched_seg[n] = static_cast<uint8_t>(light_seg[li]); hp.sched_chunk[n++] = static_cast<uint8_t>(light_chunk[li]);
+        }
+        hp.n_stages = n;
+    }
     if (gn_ab && ab_off != gn_ab_channels) {
         set_error("conv_halo: scale/shift table has %d channels, the normalised segments %d", gn_ab_channels, ab_off);
         return 2;
@@ -643,6 +668,11 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_cha
         const char* e = getenv("DDPM_HALO_DBG");
         hp.dbg = e ? atoi(e) : 0;
         p.dbg = hp.dbg;
+        static long long* cyc_buf = nullptr;  // experiment only: one buffer for the process, read back by the caller
+        if (getenv("DDPM_HALO_CYCLES")) {
+            if (!cyc_buf) cudaMalloc(&cyc_buf, 4 * 128 * sizeof(long long));
+            hp.dbg_cycles = cyc_buf;
+        }
     }
     {
         cuuint64_t gdim[2] = {static_cast<cuuint64_t>(kcol), static_cast<cuuint64_t>(q.w_rows)};
@@ -659,6 +689,13 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_cha
     const int clusters = items < num_sms / 2 ? items : num_sms / 2;
     out->grid = 2 * clusters;
     return 0;
+}
+
+// experiment only: copy the MMA-warp cycle counters of the last launch to the host (74 clusters x 4)
+int conv_halo_read_cycles(const ConvHaloLaunch& l, long long* host, int n) {
+    if (!l.p.dbg_cycles) return 1;
+    cudaDeviceSynchronize();
+    return cudaMemcpy(host, l.p.dbg_cycles, n * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
 }
 
 int conv_halo_launch(const ConvHaloLaunch& l, cudaStream_t stream) {

@@ -37,8 +37,12 @@ struct HaloGnSource {
     float eps;
 };
 
+constexpr int kMaxStagesPerItem = 48;  // (segment, 64-channel chunk) stages of one work item
+
 struct ConvHaloParams {
     ConvGemmParams g;         // geometry, K schedule, epilogue, tmA[seg] (haloed / plain boxes), tmB (half weight tile)
+    int n_stages;             // K-loop schedule: stage i stages chunk sched_chunk[i] of segment sched_seg[i]
+    uint8_t sched_seg[kMaxStagesPerItem], sched_chunk[kMaxStagesPerItem];
     int seg_taps[kMaxSeg];    // 9 or 1
     int seg_cin[kMaxSeg];     // channels of the segment (tap stride along K)
     int seg_kcol0[kMaxSeg];   // first K column of the segment in the weight matrix
@@ -49,6 +53,8 @@ struct ConvHaloParams {
     int gn_from_stats;
     int ab_C;
     int pair_mode;            // 1: tiles are two whole images of up to 8 x 8 pixels (rows interleaved by image)
+    long long* dbg_cycles;    // timing experiments only (env DDPM_HALO_CYCLES): per leader CTA [total, wait tempty,
+                              // wait a_ready, wait b_full] cycles of the MMA warp
     int dbg;                  // timing experiments only (env DDPM_HALO_DBG): 1 skip transform math, 2 skip epilogue
                               // body, 4 skip the MMAs; results are wrong when non-zero
 };
@@ -70,5 +76,6 @@ int conv_halo_stats_parts(int H, int W);
 int conv_halo_prepare(const ConvProblem& q, const float* gn_ab, int gn_ab_channels, int num_sms, ConvHaloLaunch* out,
                       const HaloGnSource* gn_src = nullptr);
 int conv_halo_launch(const ConvHaloLaunch& l, cudaStream_t stream);
+int conv_halo_read_cycles(const ConvHaloLaunch& l, long long* host, int n);  // experiment only (DDPM_HALO_CYCLES)
 
 }  // namespace ddpm

@@ -591,7 +591,6 @@ __global__ void __launch_bounds__(256) conv_in_reg_kernel(const float* __restric
 #pragma unroll
         for (int k = 0; k < CPT / 4; ++k) { qs[k] = 0.f; qq[k] = 0.f; }
         const float* xn = x + static_cast<size_t>(n) * CIN * S;
-#pragma unroll 4
         for (int r = p_begin + pl; r < p_end && pl < ppb; r += ppb) {
             const int dq = r / HW;
             const int r2 = r - dq * HW;
