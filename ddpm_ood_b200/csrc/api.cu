@@ -7,6 +7,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "attention.cuh"
 #include "conv_gemm.cuh"
 #include "conv_halo.cuh"
@@ -319,14 +321,10 @@ int ddpm_unet_run_chain(void* handle, int n_steps, const int* timesteps, const d
         return 2;
     }
     ddpm::UNet* u = static_cast<ddpm::UNet*>(handle);
-    for (int i = 0; i < n_steps; ++i) {
-        const ddpm::PlmsStep st = to_step(steps[i]);
-        int rc = u->forward(sample, nullptr, timesteps[i], nullptr, N, D, H, W, workspace,
-                            static_cast<size_t>(workspace_bytes), static_cast<cudaStream_t>(stream), &st, ring, stash,
-                            sample);
-        if (rc) return rc;
-    }
-    return 0;
+    std::vector<ddpm::PlmsStep> st(static_cast<size_t>(n_steps > 0 ? n_steps : 0));
+    for (int i = 0; i < n_steps; ++i) st[i] = to_step(steps[i]);
+    return u->run_chain(n_steps, timesteps, st.data(), sample, ring, stash, N, D, H, W, workspace,
+                        static_cast<size_t>(workspace_bytes), static_cast<cudaStream_t>(stream));
 }
 
 int ddpm_clamp_mse(const float* x, const float* x0, float b_scale, float* recon, float* mse, int N,
