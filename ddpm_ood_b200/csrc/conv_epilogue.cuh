@@ -292,7 +292,8 @@ __device__ __forceinline__ void conv_epilogue_tile16(const ConvGemmParams& p, ui
         if (p.pair_rows) {
             // lanes 0-7 / 16-23 hold image 0, lanes 8-15 / 24-31 image 1; part = this warp
             const int n_l = m_tile * 2 + ((lane >> 3) & 1);
-            if (n_l < p.N) st_base = p.stats_out + (static_cast<size_t>(n_l) * p.stats_parts + q) * (p.Cout >> 1);
+            if (n_l < p.N)
+                st_base = p.stats_out + (static_cast<size_t>(n_l) * p.stats_parts + sub * (p.stats_parts / p.num_phases) + q) * (p.Cout >> 1);
         } else if (n_w < p.N) {  // all 32 rows of a warp lie in one image (host guarantees it)
             st_base = p.stats_out + (static_cast<size_t>(n_w) * p.stats_parts + part) * (p.Cout >> 1);
         }

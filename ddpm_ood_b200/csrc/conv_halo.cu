@@ -184,7 +184,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     // work item = 2*MT consecutive M tiles (MT per CTA) x one N tile; N tiles of the same pixels run on neighbouring
     // clusters at the same time (the second read of the input hits L2).
     const int gpp = (p.num_m_tiles + 2 * MT - 1) / (2 * MT);
-    const int total_items = gpp * p.num_n_tiles;
+    // item = ((tile group, sub-pixel phase), N tile): the phases of an upsample conv re-stage the same haloed tile back to
+    // back (L2 hits)
+    const int total_items = gpp * p.num_phases * p.num_n_tiles;
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
     const int tiles_per_img = p.tiles_w * p.tiles_h;
 
@@ -193,7 +195,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         int sa = 0;
         uint32_t pa = 0;
         for (int item = cluster_id; item < total_items; item += num_clusters) {
-            const int m_group = item / p.num_n_tiles;
+            const int m_group = item / (p.num_n_tiles * p.num_phases);
             int w0[MT], h0[MT], n0[MT];
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
@@ -211,7 +213,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             }
             for (int st = 0; st < hp.n_stages; ++st) {  // (segment, 64-channel chunk) in the host's schedule order
                 const int seg = hp.sched_seg[st], chunk = hp.sched_chunk[st];
-                const int halo = hp.seg_taps[seg] == 9 ? 1 : 0;
+                const int halo = hp.seg_taps[seg] > 1 ? 1 : 0;
                 const uint32_t bytes = (halo ? (PAIR ? kHaloRowsPair : kHaloRowsRegion) : kTileW * kTileH) * 128u;
                 const CUtensorMap* ma = seg == 0 ? &p.tmA[0] : (seg == 1 ? &p.tmA[1] : &p.tmA[2]);
                 {
@@ -239,7 +241,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         uint32_t pb = 0;
         for (int item = cluster_id; item < total_items; item += num_clusters) {
             const int n_tile = item % p.num_n_tiles;
-            const int brow = n_tile * BN + static_cast<int>(rank) * (BN / 2);
+            const int phase = (item / p.num_n_tiles) % p.num_phases;
+            const int brow = phase * p.Cout + n_tile * BN + static_cast<int>(rank) * (BN / 2);
             for (int st = 0; st < hp.n_stages; ++st) {  // (segment, 64-channel chunk) in the host's schedule order
                 const int seg = hp.sched_seg[st], chunk = hp.sched_chunk[st];
                 const int taps = hp.seg_taps[seg];
@@ -269,6 +272,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             const bool prof = hp.dbg_cycles != nullptr;
             const long long t_begin = prof ? clock64() : 0;
             for (int item = cluster_id; item < total_items; item += num_clusters) {
+                const int phase = (item / p.num_n_tiles) % p.num_phases;
                 long long t0 = prof ? clock64() : 0;
                 ptx::mbar_wait(&tempty_bar[as], pt ^ 1);
                 if (prof) cyc_t += clock64() - t0;
@@ -278,7 +282,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 for (int st = 0; st < hp.n_stages; ++st) {  // (segment, 64-channel chunk) in the host's schedule order
                 const int seg = hp.sched_seg[st];
                     const int taps = hp.seg_taps[seg];
-                    const uint32_t pitch = taps == 9 ? (kTileW + 2) : kTileW;  // smem rows per image row
+                    const uint32_t pitch = taps > 1 ? (kTileW + 2) : kTileW;  // smem rows per image row
                     const uint64_t desc_hi = make_desc_k128_sbo(0, pitch * 128);
                     {
                         t0 = prof ? clock64() : 0;
@@ -288,7 +292,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                         const uint32_t a_base = ptx::smem_u32(smem_a + sa * C::kAStageBytes);
                         for (int tap = 0; tap < taps; ++tap) {
                             // tap (dh, dw): rows (h + 1 + dh) * pitch + (w + 1 + dw) of the haloed tile
-                            const uint32_t row0 = taps == 9 ? (tap / 3) * (PAIR ? 2 * pitch : pitch) + (tap % 3) : 0;
+                            // taps == 4: sub-pixel phase (ph, pw) of an upsample conv, tap (a, b) reads low-res pixel
+                            // (h + ph - 1 + a, w + pw - 1 + b): the same nine views, four per phase
+                            const uint32_t th_ = taps == 9 ? tap / 3 : (taps == 4 ? ((phase >> 1) & 1) + (tap >> 1) : 0);
+                            const uint32_t tw_ = taps == 9 ? tap % 3 : (taps == 4 ? (phase & 1) + (tap & 1) : 0);
+                            const uint32_t row0 = th_ * (PAIR ? 2 * pitch : pitch) + tw_;
                             const uint64_t da0 = desc_hi | ((a_base + row0 * 128) >> 4);
                             const uint64_t db0 = ptx::make_desc_k128(ptx::smem_u32(smem_b + sb * C::kBHalfBytes));
                             t0 = prof ? clock64() : 0;
@@ -337,7 +345,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         int sa = 0;
         uint32_t pa = 0;
         for (int item = cluster_id; item < total_items; item += num_clusters) {
-            const int m_group = item / p.num_n_tiles;
+            const int m_group = item / (p.num_n_tiles * p.num_phases);
             // validity of this thread's rows of a HALOED tile (zero padding must stay zero), per M tile
             uint32_t mask_halo[MT];
             int tn[MT], th0[MT], tw0[MT];
@@ -399,7 +407,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             for (int st = 0; st < hp.n_stages; ++st) {  // (segment, 64-channel chunk) in the host's schedule order
                 const int seg = hp.sched_seg[st], chunk = hp.sched_chunk[st];
                 const int gn = (hp.dbg & 1) ? 0 : hp.seg_gn[seg];
-                const bool halo = hp.seg_taps[seg] == 9;
+                const bool halo = hp.seg_taps[seg] > 1;
                 {
                     if (gn) {
                         const uint32_t ab_chunk = ptx::smem_u32(s_ab + hp.seg_ab_off[seg] + chunk * kBlockK) + cg * 16;
@@ -459,8 +467,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         int as = 0;
         uint32_t pt = 0;
         for (int item = cluster_id; item < total_items; item += num_clusters) {
-            const int m_group = item / p.num_n_tiles;
-            const int n_tile = item - m_group * p.num_n_tiles;
+            const int m_group = item / (p.num_n_tiles * p.num_phases);
+            const int n_tile = item % p.num_n_tiles;
+            const int phase = (item / p.num_n_tiles) % p.num_phases;
             // stage the per-column addends (bias + timestep-embedding row of the tile's image) while the MMAs run
             {
                 const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..127
@@ -485,7 +494,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 #pragma unroll 1
                 for (int mt = 0; mt < MT; ++mt)
                     conv_epilogue_tile16<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * C::kAccCols + mt * BN,
-                                             (m_group * 2 + static_cast<int>(rank)) * MT + mt, n_tile, 0, q, lane,
+                                             (m_group * 2 + static_cast<int>(rank)) * MT + mt, n_tile, phase, q, lane,
                                              s_add + (PAIR ? 0 : mt * BN));
             }
             ptx::tc_fence_before();
@@ -508,12 +517,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 static bool pair_tiles(const ConvProblem& q) { return q.H <= 8 && q.W <= 8; }
 
 bool conv_halo_supported(const ConvProblem& q) {
-    if (q.spatial_dims != 2 || q.D != 1 || q.stride != 1 || q.upsample2 || q.mode != EPI_STORE || q.b_rows_per_mtile)
-        return false;
+    if (q.spatial_dims != 2 || q.D != 1 || q.stride != 1 || q.mode != EPI_STORE || q.b_rows_per_mtile) return false;
     if (q.n_seg < 1 || q.n_seg > kMaxSeg) return false;
-    for (int s = 0; s < q.n_seg; ++s) {
-        if (q.seg[s].channels % kBlockK != 0) return false;
-        if (q.seg[s].ksize != 3 && q.seg[s].ksize != 1) return false;
+    if (q.upsample2) {  // nearest x2 + 3x3 conv as four sub-pixel 2x2 phases over the low-resolution tile
+        if (q.n_seg != 1 || q.seg[0].ksize != 2 || q.seg[0].channels % kBlockK != 0 || q.residual) return false;
+    } else {
+        for (int s = 0; s < q.n_seg; ++s) {
+            if (q.seg[s].channels % kBlockK != 0) return false;
+            if (q.seg[s].ksize != 3 && q.seg[s].ksize != 1) return false;
+        }
     }
     if (q.Cout % 128 != 0) return false;
     // images up to 8 x 8: a tile is two whole images (one M tile per CTA: 256-wide N tiles only);
@@ -568,9 +580,10 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_cha
     p.chan_add_stride = q.chan_add_stride;
     p.residual = static_cast<const __half*>(q.residual);
     p.out = static_cast<__half*>(q.out);
-    p.num_phases = 1;
+    p.num_phases = q.upsample2 ? 4 : 1;
+    p.phase3d = 0;
     p.stats_out = q.stats_out;
-    p.stats_parts = q.stats_out ? conv_halo_stats_parts(q.H, q.W) : 0;
+    p.stats_parts = q.stats_out ? conv_halo_stats_parts(q.H, q.W) * p.num_phases : 0;
     p.n_seg = q.n_seg;
     int kcol = 0, ab_off = 0, kb = 0, c3_off = 0;
     int total3 = 0;  // channels of all 3x3 segments
@@ -585,7 +598,7 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_cha
     const bool gn_on_1x1 = gn_ab && total3 == 0;
     for (int s = 0; s < q.n_seg; ++s) {
         const ConvSegment& g = q.seg[s];
-        const int taps = g.ksize == 3 ? 9 : 1;
+        const int taps = g.ksize == 3 ? 9 : (g.ksize == 2 ? 4 : 1);
         p.seg_chunks[s] = g.channels / kBlockK;
         p.seg_kw[s] = p.seg_kh[s] = g.ksize;
         p.seg_kd[s] = 1;
@@ -606,7 +619,7 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_cha
         hp.seg_ab_off[s] = ab_off;
         if (normalised) ab_off += g.channels;
         if (taps == 9) c3_off += g.channels;
-        const cuuint32_t halo = taps == 9 ? 2 : 0;
+        const cuuint32_t halo = taps > 1 ? 2 : 0;
         const cuuint64_t row_bytes = static_cast<cuuint64_t>(g.channels) * 2;
         cuuint64_t gdim[5], gstr[4];
         cuuint32_t box[5];
@@ -636,7 +649,7 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_cha
         for (int s = 0; s < q.n_seg; ++s)
             for (int c = 0; c < p.seg_chunks[s]; ++c) {
                 if (nh + nl >= kMaxStagesPerItem) { set_error("conv_halo: more than %d K stages per item", kMaxStagesPerItem); return 2; }
-                if (hp.seg_taps[s] == 9) { heavy_seg[nh] = s; heavy_chunk[nh++] = c; }
+                if (hp.seg_taps[s] > 1) { heavy_seg[nh] = s; heavy_chunk[nh++] = c; }
                 else { light_seg[nl] = s; light_chunk[nl++] = c; }
             }
         int n = 0, li = 0;
@@ -685,7 +698,7 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_cha
         if (r != CUDA_SUCCESS) { set_error("conv_halo: cuTensorMapEncodeTiled(B) failed: %d", (int)r); return 3; }
     }
     const int per_item = 2 * out->m_tiles_per_cta;
-    const int items = ((p.num_m_tiles + per_item - 1) / per_item) * p.num_n_tiles;
+    const int items = ((p.num_m_tiles + per_item - 1) / per_item) * p.num_n_tiles * p.num_phases;
     const int clusters = items < num_sms / 2 ? items : num_sms / 2;
     out->grid = 2 * clusters;
     return 0;
