@@ -251,9 +251,11 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint
 // the per-column addend staged in shared memory, restructured for latency - 16-column chunks with double-buffered
 // TMEM loads (chunk c + 1 is in flight while chunk c is converted, stored and reduced), half the live registers.
 // s_add: [slot][BN] fp32 (bias + chan_add), slot = 0 for region tiles / the row's image for pair tiles.
+// c_begin / c_end: range of 16-column chunks this warp handles (two warps per TMEM lane quarter can split a tile).
 template <int BN>
 __device__ __forceinline__ void conv_epilogue_tile16(const ConvGemmParams& p, uint32_t t_addr, int m_tile, int n_tile,
-                                                     int sub, int q, int lane, const float* s_add) {
+                                                     int sub, int q, int lane, const float* s_add, int c_begin = 0,
+                                                     int c_end = BN / 16) {
     const int row = q * 32 + lane;
     int w, h, d = 0, n;
     int part = 0, n_w = 0;  // statistics part / image of this warp's 32 rows (region and im2col tiles)
@@ -389,14 +391,14 @@ __device__ __forceinline__ void conv_epilogue_tile16(const ConvGemmParams& p, ui
     };
 
     uint32_t va[16], vb[16];
-    ptx::tmem_ld_32x16(t_addr, va);
+    ptx::tmem_ld_32x16(t_addr + c_begin * 16, va);
 #pragma unroll 1
-    for (int c = 0; c < BN / 16; c += 2) {
+    for (int c = c_begin; c < c_end; c += 2) {  // even chunk counts
         ptx::tmem_ld_wait();
         ptx::tmem_ld_32x16(t_addr + (c + 1) * 16, vb);
         process(c, va);
         ptx::tmem_ld_wait();
-        if (c + 2 < BN / 16) ptx::tmem_ld_32x16(t_addr + (c + 2) * 16, va);
+        if (c + 2 < c_end) ptx::tmem_ld_32x16(t_addr + (c + 2) * 16, va);
         process(c + 1, vb);
     }
 }

@@ -217,8 +217,11 @@ struct Cfg2 {
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + BN * 4 /*epilogue addend row*/;
 };
 
+// Warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-7 and 8-11 epilogue (two warps per TMEM lane quarter, each
+// takes half of a tile's columns: with K = 256..1024 per item these kernels are epilogue-bound).
+constexpr int kThreads2 = 384;
 template <int BN, int MT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
     conv_gemm_2cta_kernel(const __grid_constant__ ConvGemmParams p) {
     using C = Cfg2<BN, MT>;
     extern __shared__ uint8_t smem_raw[];
@@ -249,7 +252,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp of both CTAs
+            ptx::mbar_init(&tempty_bar[i], 16);  // one arrive per epilogue warp (8) of both CTAs
         }
         ptx::fence_mbar_init();
     }
@@ -351,8 +354,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
             }
         }
     } else if (warp >= 4) {
-        // ================================================================= epilogue (4 warps per CTA, own 128 rows)
-        const int q = warp - 4;
+        // ================================================================= epilogue (8 warps per CTA, own 128 rows)
+        const int q = warp & 3;            // TMEM lane quarter == warp % 4
+        const int half = (warp - 4) >> 2;  // which half of the tile's columns
         int as = 0;
         uint32_t aparity = 0;
         for (int item = cluster_id; item < total_items; item += num_clusters) {
@@ -361,12 +365,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
             const int sub = g / gpp;
             const int m_group = g - sub * gpp;
             // fast path (plain store epilogue without a per-image addend): bias row staged in shared memory, 16-column
-            // chunks with double-buffered TMEM loads (conv_epilogue_tile16)
+            // chunks with double-buffered TMEM loads (conv_epilogue_tile16), columns split between the two warp groups
             const bool fast = p.mode == EPI_STORE && p.chan_add == nullptr;
             if (fast) {
-                asm volatile("bar.sync 2, 128;" ::: "memory");  // the previous item's readers are done
-                for (int i = threadIdx.x - 128; i < BN; i += 128) s_add[i] = p.bias ? __ldg(p.bias + n_tile * BN + i) : 0.f;
-                asm volatile("bar.sync 2, 128;" ::: "memory");
+                asm volatile("bar.sync 2, 256;" ::: "memory");  // the previous item's readers are done
+                for (int i = threadIdx.x - 128; i < BN; i += 256) s_add[i] = p.bias ? __ldg(p.bias + n_tile * BN + i) : 0.f;
+                asm volatile("bar.sync 2, 256;" ::: "memory");
             }
             ptx::mbar_wait(&tfull_bar[as], aparity);
             ptx::tc_fence_after();
@@ -374,8 +378,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
             for (int mt = 0; mt < MT; ++mt) {
                 const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * C::kAccCols + mt * BN;
                 const int m_tile = (m_group * 2 + static_cast<int>(rank)) * MT + mt;
-                if (fast) conv_epilogue_tile16<BN>(p, t_addr, m_tile, n_tile, sub, q, lane, s_add);
-                else conv_epilogue_tile<BN>(p, t_addr, m_tile, n_tile, sub, q, lane);
+                if (fast)
+                    conv_epilogue_tile16<BN>(p, t_addr, m_tile, n_tile, sub, q, lane, s_add, half * (BN / 32),
+                                             (half + 1) * (BN / 32));
+                else if (half == 0)
+                    conv_epilogue_tile<BN>(p, t_addr, m_tile, n_tile, sub, q, lane);
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -594,11 +601,11 @@ int conv_launch(const ConvLaunch& l, cudaStream_t stream) {
     cudaError_t e;
     if (l.cta_pair) {
         if (l.block_n == 256)
-            e = launch_pdl(conv_gemm_2cta_kernel<256, 1>, dim3(l.grid), dim3(256), Cfg2<256, 1>::kSmemBytes, stream, l.p);
+            e = launch_pdl(conv_gemm_2cta_kernel<256, 1>, dim3(l.grid), dim3(kThreads2), Cfg2<256, 1>::kSmemBytes, stream, l.p);
         else if (l.m_tiles_per_cta == 2)
-            e = launch_pdl(conv_gemm_2cta_kernel<128, 2>, dim3(l.grid), dim3(256), Cfg2<128, 2>::kSmemBytes, stream, l.p);
+            e = launch_pdl(conv_gemm_2cta_kernel<128, 2>, dim3(l.grid), dim3(kThreads2), Cfg2<128, 2>::kSmemBytes, stream, l.p);
         else
-            e = launch_pdl(conv_gemm_2cta_kernel<128, 1>, dim3(l.grid), dim3(256), Cfg2<128, 1>::kSmemBytes, stream, l.p);
+            e = launch_pdl(conv_gemm_2cta_kernel<128, 1>, dim3(l.grid), dim3(kThreads2), Cfg2<128, 1>::kSmemBytes, stream, l.p);
     } else if (l.block_n == 256)
         e = launch_pdl(conv_gemm_kernel<256, 1>, dim3(l.grid), dim3(256), Cfg<256, 1>::kSmemBytes, stream, l.p);
     else if (l.m_tiles_per_cta == 2)
