@@ -6,8 +6,10 @@
 
 Workload (configs[1] of BASELINE.json): FashionMNIST-shaped synthetic images 1x32x32 in [0,1), `small`
 DiffusionModelUNet with random non-zero weights, scaled_linear_beta 0.0015->0.0195, 100 inference steps,
-inference_skip_factor=4 -> 25 t-starts, 1250 UNet evaluations per batch; batch = the reference CLI's default
---batch_size 256 (reconstruct.py:89). A "step" is one batch: 256 x 25 = 6400 reconstructions.
+inference_skip_factor=4 -> 25 t-starts, 1250 UNet evaluations per batch. A "step" is one batch of `--batch` images x 25
+t-starts. The batch size is the reference CLI's free `--batch_size` knob (default 256, reconstruct.py:89; BASELINE.json
+does not fix it): the default here is 592 = 8 images per CTA pair of the 148-SM part, which makes every UNet level a
+whole number of waves (2403 reconstructions/s vs 2190 at 256, measured); `--batch 256` reproduces the reference default.
 Under torchrun every rank processes its own batch (images are what the reference shards, SURVEY.md §8e; weak scaling);
 the only collective is the gather of the [25, B, 2] score tensor.
 """
@@ -39,7 +41,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="images per rank per step (reference default batch_size)")
+    ap.add_argument("--batch", type=int, default=592,
+                    help="images per rank per step (8 per CTA pair on 148 SMs; the reference CLI default is 256)")
     ap.add_argument("--skip", type=int, default=4, help="inference_skip_factor")
     ap.add_argument("--plms_state", default="carry", choices=["carry", "reset"])
     ap.add_argument("--profile_every", type=int, default=50, help="event-profile every n-th UNet forward (0 = off)")
@@ -311,7 +314,7 @@ def run_ours(args):
                     "unit": "TFLOP/s", "frac": achieved / peak_tf,
                     # dram__bytes_read.sum + dram__bytes_write.sum per conv_halo launch, mean of the 22 launches of one
                     # forward at batch 256 (profiles/r01_halo_ncu_full_s3.md)
-                    "traffic": 83.4e6 if args.batch == 256 else None, "traffic_unit": "bytes/launch (ncu, conv_halo)",
+                    "traffic": 83.4e6 * args.batch / 256.0, "traffic_unit": "bytes/launch (ncu at batch 256, scaled by batch; conv_halo)",
                     "peak_source": peak_src,
                     "launches_timed": cg["launches"],
                     "avg_launch_us": 1000.0 * cg["ms"] / cg["launches"],
@@ -336,8 +339,8 @@ def run_ours(args):
         "dtype": "fp16 operands, fp32 accumulate", "data": "synthetic",
         "config": {"workload": workload_name(args), "global_batch": B * world, "t_starts": n_t,
                    "unet_evals_per_step_per_gpu": evals, "parallelism": f"images sharded over {world} rank(s)",
-                   "l2": "per-step working set (weights 35 MB + ~1.5 GB activations at batch 256) exceeds the 126 MB L2; "
-                         "no flush between steps"},
+                   "l2": f"per-step working set (weights 35 MB + ~{6 * B / 1024:.1f} GB activations at batch {B}) exceeds the "
+                         "126 MB L2; no flush between steps"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host_images.numel() * 4 * world,
                 "d2h_bytes_per_step": n_t * B * 2 * 4 * world, "ms_per_step": ms_e2e / args.steps},
