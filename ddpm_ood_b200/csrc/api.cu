@@ -144,13 +144,14 @@ int ddpm_conv_forward(const ddpm_conv_args* a, void* stream) {
         if (rc) return rc;
         rc = ddpm::conv_halo_launch(hl, static_cast<cudaStream_t>(stream));
         if (!rc && hl.p.dbg_cycles && getenv("DDPM_HALO_CYCLES_PRINT")) {  // experiment only
-            long long h[4 * 74];
-            if (!ddpm::conv_halo_read_cycles(hl, h, 4 * 74)) {
-                double s[4] = {0, 0, 0, 0};
+            long long h[8 * 74];
+            if (!ddpm::conv_halo_read_cycles(hl, h, 8 * 74)) {
+                double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 const int nc = hl.grid / 2;
-                for (int i = 0; i < nc; ++i) for (int k = 0; k < 4; ++k) s[k] += static_cast<double>(h[4 * i + k]);
-                fprintf(stderr, "halo cycles (mean over %d clusters): total %.0f  wait_tempty %.0f  wait_a_ready %.0f  wait_b_full %.0f\n",
-                        nc, s[0] / nc, s[1] / nc, s[2] / nc, s[3] / nc);
+                for (int i = 0; i < nc; ++i) for (int k = 0; k < 8; ++k) s[k] += static_cast<double>(h[8 * i + k]);
+                fprintf(stderr, "halo cycles (mean over %d clusters): total %.0f | MMA waits: tempty %.0f a_ready %.0f b_full %.0f | "
+                        "A producer waits a_empty %.0f | transform: table %.0f wait a_full %.0f work %.0f\n",
+                        nc, s[0] / nc, s[1] / nc, s[2] / nc, s[3] / nc, s[4] / nc, s[5] / nc, s[6] / nc, s[7] / nc);
             }
         }
         return rc;

@@ -194,6 +194,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         // ================================================================= A producer: one haloed tile per 64 channels
         int sa = 0;
         uint32_t pa = 0;
+        long long cyc_prod = 0;
         for (int item = cluster_id; item < total_items; item += num_clusters) {
             const int m_group = item / (p.num_n_tiles * p.num_phases);
             int w0[MT], h0[MT], n0[MT];
@@ -217,7 +218,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 const uint32_t bytes = (halo ? (PAIR ? kHaloRowsPair : kHaloRowsRegion) : kTileW * kTileH) * 128u;
                 const CUtensorMap* ma = seg == 0 ? &p.tmA[0] : (seg == 1 ? &p.tmA[1] : &p.tmA[2]);
                 {
+                    const long long tp0 = hp.dbg_cycles ? clock64() : 0;
                     ptx::mbar_wait(&a_empty[sa], pa ^ 1);
+                    if (hp.dbg_cycles) cyc_prod += clock64() - tp0;
                     if (ptx::elect_one()) {
                         ptx::mbar_arrive_expect_tx(&a_full[sa], MT * bytes);
 #pragma unroll
@@ -235,6 +238,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 }
             }
         }
+        if (hp.dbg_cycles && rank == 0 && lane == 0) hp.dbg_cycles[8 * cluster_id + 4] = cyc_prod;
     } else if (warp == kWarpB) {
         // ================================================================= B producer: this CTA's half of each weight tile
         int sb = 0;
@@ -327,7 +331,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 if (++as == 2) { as = 0; pt ^= 1; }
             }
             if (prof && lane == 0) {
-                long long* o = hp.dbg_cycles + 4 * cluster_id;
+                long long* o = hp.dbg_cycles + 8 * cluster_id;
                 o[0] = clock64() - t_begin; o[1] = cyc_t; o[2] = cyc_a; o[3] = cyc_b;
             }
         }
@@ -344,6 +348,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         const int slot_of_thread = PAIR ? (tid >> 7) : 0;
         int sa = 0;
         uint32_t pa = 0;
+        long long cyc_tab = 0, cyc_full = 0, cyc_x = 0;
+        const bool xprof = hp.dbg_cycles != nullptr;
         for (int item = cluster_id; item < total_items; item += num_clusters) {
             const int m_group = item / (p.num_n_tiles * p.num_phases);
             // validity of this thread's rows of a HALOED tile (zero padding must stay zero), per M tile
@@ -373,6 +379,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 }
                 mask_halo[mt] = m;
             }
+            const long long tt0 = xprof ? clock64() : 0;
             if (any_gn) {
                 // (scale, shift) rows of this item's images -> shared memory, once per item: either copied from the
                 // precomputed table or derived here from the producers' partial statistics (same code as gn_finalize)
@@ -404,6 +411,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 }
                 xsync();
             }
+            if (xprof) cyc_tab += clock64() - tt0;
             for (int st = 0; st < hp.n_stages; ++st) {  // (segment, 64-channel chunk) in the host's schedule order
                 const int seg = hp.sched_seg[st], chunk = hp.sched_chunk[st];
                 const int gn = (hp.dbg & 1) ? 0 : hp.seg_gn[seg];
@@ -435,7 +443,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) { ga[j] *= 0.5f; gb[j] *= 0.5f; }
                             }
+                            long long tf0 = xprof ? clock64() : 0;
                             if (mt == 0) ptx::mbar_wait(&a_full[sa], pa);
+                            if (xprof) { const long long now = clock64(); cyc_full += now - tf0; tf0 = now; }
                             const uint32_t tile = smem_a_u32 + sa * C::kAStageBytes + mt * kATileBytes;
                             // all loads first (6-7 rows in flight), then the math, then the stores
                             uint4 raw[kRowIters];
@@ -450,6 +460,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                                     sts128(tile + off[i], raw[i]);
                                 }
                             }
+                            if (xprof) cyc_x += clock64() - tf0;
                         }
                         ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core
                     } else {
@@ -460,6 +471,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                     if (++sa == kAStages) { sa = 0; pa ^= 1; }
                 }
             }
+        }
+        if (xprof && rank == 0 && tid == 0) {
+            long long* o = hp.dbg_cycles + 8 * cluster_id;
+            o[5] = cyc_tab; o[6] = cyc_full; o[7] = cyc_x;
         }
     } else if (warp < kEpiWarp0 + 4) {
         // ================================================================= epilogue (4 warps per CTA, own 128 rows)
@@ -683,7 +698,7 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_cha
         p.dbg = hp.dbg;
         static long long* cyc_buf = nullptr;  // experiment only: one buffer for the process, read back by the caller
         if (getenv("DDPM_HALO_CYCLES")) {
-            if (!cyc_buf) cudaMalloc(&cyc_buf, 4 * 128 * sizeof(long long));
+            if (!cyc_buf) cudaMalloc(&cyc_buf, 8 * 128 * sizeof(long long));
             hp.dbg_cycles = cyc_buf;
         }
     }
