@@ -135,6 +135,9 @@ SIGNATURES = {
                                       C.c_longlong, C.c_void_p]),
     "ddpm_clamp_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong,
                                  C.c_void_p]),
+    "ddpm_val_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ddpm_mean_z": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "ddpm_auc_counts": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ddpm_lpips_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "ddpm_lpips_destroy": (None, [C.c_void_p]),
     "ddpm_lpips_set_param": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong, C.c_void_p]),

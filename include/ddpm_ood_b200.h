@@ -217,6 +217,19 @@ DDPM_API int ddpm_lpips_forward(void* handle, const float* in0, const float* in1
                                 int normalize, void* workspace, long long workspace_bytes, void* stream);
 DDPM_API long long ddpm_lpips_launch_count(void* handle);
 
+/* ------------------------------------------------------------------------------------------------ score post-processing
+ * ("next" row) The arithmetic of ood_detection.py:150-206 for score tensors already on the device,
+ * [n_t, n_images] fp32 per dataset and target (mse / perceptual_difference):
+ *   ddpm_val_stats   mean and sample std (ddof 1, pandas' default) per t over the validation images      (:150-158)
+ *   ddpm_mean_z      per image: mean over t of (score - mean_t) / std_t                                    (:159-161,174)
+ *   ddpm_auc_counts  counts[0] = #{out > in}, counts[1] = #{out == in} over all (out, in) pairs;
+ *                    roc_auc_score = (counts[0] + counts[1] / 2) / (n_in * n_out)                          (:191-206) */
+DDPM_API int ddpm_val_stats(const float* val, int n_t, int n_val, float* mean, float* std, void* stream);
+DDPM_API int ddpm_mean_z(const float* scores, const float* mean, const float* std, int n_t, int n, float* out,
+                         void* stream);
+DDPM_API int ddpm_auc_counts(const float* in_scores, int n_in, const float* out_scores, int n_out,
+                             unsigned long long* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
