@@ -507,9 +507,10 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
         };
         // ResnetBlock on the halo-tile kernel: both GroupNorm+SiLU layers are applied inside the consuming conv (the
         // normalised tensors never exist), each preceded by a tiny statistics -> scale/shift kernel.
-        auto halo_ok = [&](const Act& h, const Act* skip, int cout) {
+        auto halo_ok = [&](const Act& h, const Act* skip, int cout, int gn2_channels = 0) {
             if (!use_halo_ || h.parts <= 0 || (skip && skip->parts <= 0)) return false;
-            if (h.C + (skip ? skip->C : 0) > 512) return false;  // scale/shift rows the kernel stages in shared memory
+            // scale/shift rows the kernel stages in shared memory: conv1 normalises cat(h, skip), conv2 its own input
+            if (h.C + (skip ? skip->C : 0) > 512 || gn2_channels > 512) return false;
             ConvProblem q{};
             q.spatial_dims = sd; q.N = N; q.D = h.D; q.H = h.H; q.W = h.W; q.stride = 1; q.n_seg = 1;
             q.seg[0] = {nullptr, h.C, 3};
@@ -590,7 +591,7 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             return out;
         };
         auto resblock = [&](const ResW& r, const Act& h, const Act* skip) -> Act {
-            if (halo_ok(h, skip, r.cout)) return resblock_halo(r, h, skip);
+            if (halo_ok(h, skip, r.cout, r.cout)) return resblock_halo(r, h, skip);
             const int cin = r.c0 + r.c1;
             if (measure) {
                 const size_t ch = static_cast<size_t>(N) * h.S() * r.cout;

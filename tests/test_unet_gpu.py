@@ -55,6 +55,21 @@ def test_forward_matches_oracle(name):
     assert rel < 3e-3, (name, rel)
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 16, 16), (1, 3, 32, 32)])
+def test_forward_big_model_matches_oracle(shape):
+    """`--model_type big` (src/trainers/base.py:76-86): channels (256, 512, 768), attention at every level with 1 / 2 / 3
+    heads of 256 channels, two ResnetBlocks per level. Not a BASELINE config, but part of the constructor surface."""
+    ref, ours = _pair(2, 3, seed=5, big=True)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(shape, generator=g)
+    t = torch.randint(0, 1000, (shape[0],), generator=g)
+    with torch.no_grad():
+        want = ref(x, t)
+    got = ours(x.cuda(), timesteps=t.cuda()).cpu()
+    rel = _rel(got, want)
+    assert rel < 4e-3, rel
+
+
 def test_forward_3d_latent():
     ref, ours = _pair(3, 128, seed=3)
     g = torch.Generator().manual_seed(11)
