@@ -138,6 +138,7 @@ SIGNATURES = {
     "ddpm_val_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ddpm_mean_z": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ddpm_auc_counts": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ddpm_scale_intensity": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "ddpm_lpips_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "ddpm_lpips_destroy": (None, [C.c_void_p]),
     "ddpm_lpips_set_param": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong, C.c_void_p]),

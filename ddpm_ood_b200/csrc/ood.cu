@@ -109,3 +109,52 @@ int ddpm_auc_counts(const float* in_scores, int n_in, const float* out_scores, i
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ data ingest (f-4)
+// Per-image intensity scaling to [0, 1] on the device: MONAI's ScaleIntensityd(minv=0, maxv=1) as the reference's
+// loader applies it (src/data/get_train_and_val_dataloader.py:76), for a batch of raw images that was copied to the
+// GPU as stored (uint8 or float32, [N, per_image] contiguous). A constant image maps to zeros.
+namespace ddpm {
+
+template <typename T>
+__global__ void __launch_bounds__(256) scale_intensity_kernel(const T* __restrict__ src, float* __restrict__ dst,
+                                                              long long per_image) {
+    __shared__ float s_min[8], s_max[8];
+    const T* in = src + static_cast<size_t>(blockIdx.x) * per_image;
+    float* out = dst + static_cast<size_t>(blockIdx.x) * per_image;
+    float mn = INFINITY, mx = -INFINITY;
+    for (long long i = threadIdx.x; i < per_image; i += blockDim.x) {
+        const float v = static_cast<float>(in[i]);
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = mn; s_max[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    mn = s_min[0]; mx = s_max[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { mn = fminf(mn, s_min[i]); mx = fmaxf(mx, s_max[i]); }
+    const float range = mx - mn;
+    for (long long i = threadIdx.x; i < per_image; i += blockDim.x) {
+        const float v = static_cast<float>(in[i]) - mn;
+        out[i] = range > 0.f ? v / range : v;
+    }
+}
+
+}  // namespace ddpm
+
+extern "C" int ddpm_scale_intensity(const void* src, int src_is_u8, float* dst, int N, long long per_image, void* stream) {
+    if (!src || !dst || N < 1 || per_image < 1) { ddpm::set_error("ddpm_scale_intensity: bad argument"); return 2; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (src_is_u8)
+        ddpm::scale_intensity_kernel<unsigned char><<<N, 256, 0, s>>>(static_cast<const unsigned char*>(src), dst, per_image);
+    else
+        ddpm::scale_intensity_kernel<float><<<N, 256, 0, s>>>(static_cast<const float*>(src), dst, per_image);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ddpm::set_error("ddpm_scale_intensity: %s", cudaGetErrorString(e)); return 5; }
+    return 0;
+}

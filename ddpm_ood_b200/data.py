@@ -64,7 +64,21 @@ def _load(path: str) -> np.ndarray:
 
 def _transform(arr: np.ndarray, is_grayscale: bool, spatial_dimension: int, image_size, image_roi, add_vflip: bool,
                add_hflip: bool) -> torch.Tensor:
-    x = torch.from_numpy(np.ascontiguousarray(arr)).float()
+    x = _select(torch.from_numpy(np.ascontiguousarray(arr)), is_grayscale, spatial_dimension, image_roi).float()
+    if image_size:
+        size = (int(image_size),) * spatial_dimension
+        x = F.interpolate(x[None], size=size, mode="area")[0]  # monai Resize default mode
+    mn, mx = x.min(), x.max()
+    x = (x - mn) / (mx - mn) if mx > mn else x - mn  # ScaleIntensityd(minv=0, maxv=1)
+    if add_vflip:
+        x = torch.flip(x, dims=(1,))
+    if add_hflip:
+        x = torch.flip(x, dims=(2,))
+    return x.contiguous()
+
+
+def _select(x: torch.Tensor, is_grayscale: bool, spatial_dimension: int, image_roi) -> torch.Tensor:
+    """The index-only head of the transform chain (channel selection + centre crop), in the stored dtype."""
     if is_grayscale:
         if x.dim() == spatial_dimension:  # EnsureChannelFirstd
             x = x[None]
@@ -80,22 +94,36 @@ def _transform(arr: np.ndarray, is_grayscale: bool, spatial_dimension: int, imag
                 start = (size - r) // 2
                 sl.append(slice(start, start + r))
         x = x[tuple(sl)]
-    if image_size:
-        size = (int(image_size),) * spatial_dimension
-        x = F.interpolate(x[None], size=size, mode="area")[0]  # monai Resize default mode
-    mn, mx = x.min(), x.max()
-    x = (x - mn) / (mx - mn) if mx > mn else x - mn  # ScaleIntensityd(minv=0, maxv=1)
-    if add_vflip:
-        x = torch.flip(x, dims=(1,))
-    if add_hflip:
-        x = torch.flip(x, dims=(2,))
-    return x.contiguous()
+    return x
+
+
+def scale_intensity_on_device(raw: torch.Tensor) -> torch.Tensor:
+    """Per-image min-max scaling to [0, 1] (ScaleIntensityd(minv=0, maxv=1), get_train_and_val_dataloader.py:76) of a
+    batch of raw images already on the GPU, uint8 or float32 [N, ...]: the GPU-resident ingest path."""
+    from . import _lib
+
+    if not raw.is_cuda or raw.dtype not in (torch.uint8, torch.float32):
+        raise _lib.DdpmError("scale_intensity_on_device needs a CUDA uint8 / float32 tensor; there is no CPU fallback")
+    raw = raw.contiguous()
+    n = raw.shape[0]
+    out = torch.empty(raw.shape, dtype=torch.float32, device=raw.device)
+    with torch.cuda.device(raw.device):
+        _lib.check(_lib.lib().ddpm_scale_intensity(raw.data_ptr(), int(raw.dtype == torch.uint8), out.data_ptr(), n,
+                                                   raw.numel() // max(n, 1), torch.cuda.current_stream().cuda_stream),
+                   "ddpm_scale_intensity")
+    return out
 
 
 class SimpleLoader:
     """Sequential, un-shuffled batches (the reference's val loader: ThreadDataLoader(shuffle=False))."""
 
-    def __init__(self, dicts: Sequence[Dict[str, str]], batch_size: int, drop_last: bool, **tf):
+    def __init__(self, dicts: Sequence[Dict[str, str]], batch_size: int, drop_last: bool, device=None, **tf):
+        """device: a CUDA device turns on GPU-resident ingest: images are copied as stored (uint8 stays
+        uint8: a quarter of the PCIe bytes) in one transfer per batch and scaled per image by ddpm_scale_intensity;
+        batches come out on that device. Not available with image_size (area resize happens before the scaling)."""
+        self.device = torch.device(device) if device is not None else None
+        if self.device is not None and (self.device.type != "cuda" or tf.get("image_size")):
+            raise ValueError("device ingest needs a CUDA device and no image_size resize")
         self.dicts = list(dicts)
         self.batch_size = batch_size
         self.drop_last = drop_last
@@ -112,24 +140,43 @@ class SimpleLoader:
             idx = list(range(s, min(s + self.batch_size, n)))
             if self.drop_last and len(idx) < self.batch_size:
                 return
+            names = {"filename_or_obj": [self.dicts[i]["image"] for i in idx]}
+            if self.device is not None:
+                yield {"image": self._device_batch(idx), "image_meta_dict": names}
+                continue
             imgs = []
             for i in idx:
                 if i not in self._cache:
                     self._cache[i] = _transform(_load(self.dicts[i]["image"]), **self.tf)
                 imgs.append(self._cache[i])
-            yield {"image": torch.stack(imgs), "image_meta_dict": {"filename_or_obj": [self.dicts[i]["image"] for i in idx]}}
+            yield {"image": torch.stack(imgs), "image_meta_dict": names}
+
+    def _device_batch(self, idx) -> torch.Tensor:
+        tf = self.tf
+        raws = []
+        for i in idx:
+            if i not in self._cache:
+                x = _select(torch.from_numpy(np.ascontiguousarray(_load(self.dicts[i]["image"]))), tf["is_grayscale"],
+                            tf["spatial_dimension"], tf["image_roi"])
+                self._cache[i] = x.contiguous() if x.dtype == torch.uint8 else x.float().contiguous()
+            raws.append(self._cache[i])
+        if len({r.dtype for r in raws}) > 1:
+            raws = [r.float() for r in raws]
+        x = scale_intensity_on_device(torch.stack(raws).pin_memory().to(self.device, non_blocking=True))
+        flips = [d for d, on in ((2, tf["add_vflip"]), (3, tf["add_hflip"])) if on]
+        return torch.flip(x, dims=flips) if flips else x
 
 
 def get_training_data_loader(batch_size: int, training_ids: str, validation_ids: str, only_val: bool = False,
                              augmentation: bool = True, drop_last: bool = False, num_workers: int = 8,
                              num_val_workers: int = 3, cache_data=True, first_n=None, is_grayscale=False,
                              add_vflip=False, add_hflip=False, image_size=None, image_roi=None, spatial_dimension=2,
-                             rank: Optional[int] = None, world_size: Optional[int] = None):
+                             rank: Optional[int] = None, world_size: Optional[int] = None, device=None):
     """Same signature as the reference's get_training_data_loader (get_train_and_val_dataloader.py:36-53); only the
     validation-style loader (only_val=True) is on the reconstruction path."""
     if not only_val:
         raise NotImplementedError("training loaders are out of scope for the reconstruction path")
     dicts = get_data_dicts(validation_ids, first_n=first_n if first_n else False, rank=rank, world_size=world_size)
-    return SimpleLoader(dicts, batch_size, bool(drop_last), is_grayscale=bool(is_grayscale),
+    return SimpleLoader(dicts, batch_size, bool(drop_last), device=device, is_grayscale=bool(is_grayscale),
                         spatial_dimension=spatial_dimension, image_size=image_size, image_roi=image_roi,
                         add_vflip=add_vflip, add_hflip=add_hflip)

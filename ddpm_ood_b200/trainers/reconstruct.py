@@ -58,7 +58,10 @@ class Reconstruct(BaseTrainer):
             cache_data=bool(args.cache_data), drop_last=bool(args.drop_last),
             first_n=int(first_n) if first_n else first_n, is_grayscale=bool(args.is_grayscale),
             spatial_dimension=args.spatial_dimension, image_size=self.image_size, image_roi=args.image_roi,
-            rank=rank, world_size=world, **flip)
+            rank=rank, world_size=world,
+            # GPU-resident ingest whenever no area resize precedes the intensity scaling
+            device=self.device if (not self.image_size and torch.device(self.device).type == "cuda") else None,
+            **flip)
 
     def _engine(self) -> BatchReconstructor:
         if self._pl is None:

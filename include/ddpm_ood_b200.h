@@ -230,6 +230,12 @@ DDPM_API int ddpm_mean_z(const float* scores, const float* mean, const float* st
 DDPM_API int ddpm_auc_counts(const float* in_scores, int n_in, const float* out_scores, int n_out,
                              unsigned long long* counts, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ data ingest
+ * ("next" row) ScaleIntensityd(minv=0, maxv=1) of the reference's loader
+ * (src/data/get_train_and_val_dataloader.py:76) per image on the device: src [N, per_image] uint8 (src_is_u8) or fp32
+ * as stored on disk, dst fp32 in [0, 1]; a constant image maps to zeros. */
+DDPM_API int ddpm_scale_intensity(const void* src, int src_is_u8, float* dst, int N, long long per_image, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,83 @@
+"""End to end through the reference-facing CLI surface (root reconstruct.py -> trainers.Reconstruct, the mirror of
+reconstruct.py:91-96 + src/trainers/reconstruct.py:96-335): .npy images + split files + checkpoint.pth in, results_*.csv
+out, and the CSV contract ood_detection.py:150-206 consumes (columns, row order t-start outer / image inner, every
+out-of-distribution set typed "out", flip datasets by file-name suffix)."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _dataset(tmp_path, name, n, seed):
+    rng = np.random.default_rng(seed)
+    d = tmp_path / name
+    d.mkdir()
+    paths = []
+    for i in range(n):
+        np.save(d / f"{name}_{i}.npy", rng.integers(0, 256, (32, 32), dtype=np.uint8))
+        paths.append(str(d / f"{name}_{i}.npy"))
+    ids = tmp_path / f"{name}_ids.csv"
+    ids.write_text(",".join(paths) + "\n")  # one csv row of paths (get_train_and_val_dataloader.py:10-17)
+    return ids, paths
+
+
+def test_cli_writes_the_reference_csv_contract(tmp_path):
+    sys.path.insert(0, str(ROOT))
+    import reconstruct as cli
+    from ddpm_ood_b200.data import SimpleLoader
+    from ddpm_ood_b200.trainers import Reconstruct
+    from oracle import unet as ou
+
+    val_ids, val_paths = _dataset(tmp_path, "val", 5, 0)
+    in_ids, _ = _dataset(tmp_path, "in", 2, 1)
+    out_ids, out_paths = _dataset(tmp_path, "other", 3, 2)
+    run = tmp_path / "runs" / "m"
+    run.mkdir(parents=True)
+    weights = ou.randomize_(ou.make_small(2, 1), seed=5).state_dict()
+    torch.save({"epoch": 7, "global_step": 1, "best_loss": 0.5, "model_state_dict": weights}, run / "checkpoint.pth")
+
+    out_flag = str(out_ids).replace(".csv", "_vflip.csv")  # "<set>_vflip" names the same ids file, flipped
+    args = cli.parse_args([
+        "--output_dir", str(tmp_path / "runs"), "--model_name", "m", "--validation_ids", str(val_ids),
+        "--in_ids", str(in_ids), "--out_ids", f"{out_ids},{out_flag}", "--is_grayscale", "1", "--batch_size", "3",
+        "--beta_schedule", "scaled_linear_beta", "--beta_start", "0.0015", "--beta_end", "0.0195",
+        "--inference_skip_factor", "64"])
+    recon = Reconstruct(args)
+    torch.manual_seed(11)
+    recon.reconstruct(args)
+
+    ood = run / "ood"
+    assert sorted(p.name for p in ood.glob("*.csv")) == ["results_in.csv", "results_other.csv",
+                                                        "results_other_vflip.csv", "results_val.csv"]
+    val = pd.read_csv(ood / "results_val.csv", index_col=0)
+    assert list(val.columns) == ["filename", "type", "t", "perceptual_difference", "mse"]
+    # 5 images in batches of 3 and 2; per batch: t-start outer (10, 650 at skip 64), image inner
+    stems = [Path(p).stem for p in val_paths]
+    assert list(val["filename"]) == stems[:3] * 2 + stems[3:] * 2
+    assert list(val["t"]) == [10] * 3 + [650] * 3 + [10] * 2 + [650] * 2
+    assert set(val["type"]) == {"val"}
+    assert np.isfinite(val[["perceptual_difference", "mse"]].to_numpy()).all()
+    # more noise, worse reconstruction
+    assert (val[val.t == 650].mse.mean() > val[val.t == 10].mse.mean())
+    for name in ("results_other.csv", "results_other_vflip.csv"):
+        df = pd.read_csv(ood / name, index_col=0)
+        assert set(df["type"]) == {"out"} and list(df["filename"]) == [Path(p).stem for p in out_paths] * 2
+
+    # the values are the engine's: same seed, the HOST loader (the CLI ingested on the device), direct score_batch calls
+    torch.manual_seed(11)
+    engine = recon._engine()
+    rows = []
+    tf = dict(is_grayscale=True, spatial_dimension=2, image_size=None, image_roi=None, add_vflip=False, add_hflip=False)
+    for batch in SimpleLoader([{"image": p} for p in val_paths], 3, False, **tf):
+        res = engine.score_batch(batch["image"], 64)
+        for i in range(len(res["t"])):
+            rows += [(float(a), float(b)) for a, b in zip(res["perceptual_difference"][i].cpu(), res["mse"][i].cpu())]
+    want = np.array(rows)
+    got = val[["perceptual_difference", "mse"]].to_numpy()
+    assert np.allclose(got, want, rtol=1e-5, atol=0)

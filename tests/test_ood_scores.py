@@ -79,3 +79,44 @@ def test_device_post_processing_matches_oracle(seed, n_in, n_out):
     assert got == ood_scores.roc_auc(zi, zo.cpu().numpy())
     # and end to end it agrees with the float64 route up to near-tie flips
     assert abs(ood.ood_auc(dv, di, do) - ood_scores.ood_auc(val, ins, outs)) < 2e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.float32])
+def test_device_intensity_scaling_matches_host_transform(dtype):
+    """per-image min-max scaling on the device equals the host loader's transform
+    (ddpm_ood_b200/data.py:_transform, ScaleIntensityd of get_train_and_val_dataloader.py:76), incl. a constant image."""
+    from ddpm_ood_b200.data import _transform, scale_intensity_on_device
+
+    g = torch.Generator().manual_seed(3)
+    raw = torch.randint(0, 256, (5, 1, 28, 28), generator=g).to(dtype)
+    if dtype == torch.float32:
+        raw = raw * 0.37 - 11.0
+    raw[3] = raw[3, 0, 0, 0]  # constant image
+    want = torch.stack([_transform(r.numpy(), is_grayscale=True, spatial_dimension=2, image_size=None, image_roi=None,
+                                   add_vflip=False, add_hflip=False) for r in raw])
+    got = scale_intensity_on_device(raw.cuda()).cpu()
+    assert torch.allclose(got, want, rtol=0, atol=1e-7)
+    assert float(got[3].abs().max()) == 0.0
+
+
+@pytest.mark.gpu
+def test_loader_device_ingest_matches_host_loader(tmp_path):
+    """The loader's GPU-resident ingest (uint8 over PCIe, scaling + flips on the device) yields the host loader's batches."""
+    import numpy as np
+
+    from ddpm_ood_b200.data import SimpleLoader
+
+    rng = np.random.default_rng(0)
+    dicts = []
+    for i in range(5):
+        np.save(tmp_path / f"{i}.npy", rng.integers(0, 256, (28, 28), dtype=np.uint8))
+        dicts.append({"image": str(tmp_path / f"{i}.npy")})
+    tf = dict(is_grayscale=True, spatial_dimension=2, image_size=None, image_roi=[24, 24], add_vflip=True, add_hflip=True)
+    host = list(SimpleLoader(dicts, 2, False, **tf))
+    dev = list(SimpleLoader(dicts, 2, False, device="cuda", **tf))
+    assert len(host) == len(dev) == 3
+    for h, d in zip(host, dev):
+        assert d["image"].is_cuda and d["image"].shape == h["image"].shape
+        assert torch.allclose(d["image"].cpu(), h["image"], rtol=0, atol=1e-7)
+        assert d["image_meta_dict"] == h["image_meta_dict"]
