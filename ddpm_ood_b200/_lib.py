@@ -138,6 +138,11 @@ SIGNATURES = {
     "ddpm_val_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ddpm_mean_z": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ddpm_auc_counts": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ddpm_conv_in_stats_parts": (C.c_int, [C.c_int] * 6),
+    "ddpm_conv_in": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 7 + [C.c_void_p, C.c_void_p]),
+    "ddpm_out_norm_conv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_float, C.c_void_p]),
     "ddpm_scale_intensity": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "ddpm_lpips_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "ddpm_lpips_destroy": (None, [C.c_void_p]),

@@ -188,6 +188,29 @@ int ddpm_gn_apply(const void* src0, int C0, const float* st0, int parts0, const 
                           static_cast<cudaStream_t>(stream));
 }
 
+int ddpm_conv_in_stats_parts(int Cin, int Cout, int spatial_dims, int D, int H, int W) {
+    return ddpm::conv_in_has_stats(Cin, Cout, spatial_dims) ? ddpm::conv_in_stats_parts(D, H, W) : 0;
+}
+
+int ddpm_conv_in(const float* x, const float* w, const float* b, void* out, int N, int Cin, int D, int H, int W, int Cout,
+                 int spatial_dims, float* stats_out, void* stream) {
+    if (!x || !w || !b || !out) { ddpm::set_error("ddpm_conv_in: null argument"); return 2; }
+    return ddpm::conv_in_small(x, w, b, static_cast<__half*>(out), N, Cin, D, H, W, Cout, spatial_dims, stats_out,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int ddpm_out_norm_conv(const void* src, const float* st, int parts, const float* gamma, const float* beta,
+                       const float* w, const float* b, float* taps_ws, float* out, int N, int C, int H, int W, int Cout,
+                       int groups, float eps, void* stream) {
+    if (!src || !st || !gamma || !beta || !w || !b || !taps_ws || !out) { ddpm::set_error("ddpm_out_norm_conv: null argument"); return 2; }
+    if (!ddpm::conv_out_taps_supported(C, Cout, 2)) { ddpm::set_error("ddpm_out_norm_conv: C=%d Cout=%d unsupported", C, Cout); return 2; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = ddpm::gn_apply_taps(static_cast<const __half*>(src), C, st, parts, gamma, beta, w, Cout, taps_ws, N, H * W,
+                                 groups, eps, s);
+    if (rc) return rc;
+    return ddpm::conv_out_gather(taps_ws, b, out, N, H, W, Cout, nullptr, nullptr, nullptr, nullptr, s);
+}
+
 int ddpm_pack_upconv_weight(const float* w, int Cout, int Cin, int spatial_dims, void* dst, void* stream) {
     if (!w || !dst || (spatial_dims != 2 && spatial_dims != 3)) { ddpm::set_error("ddpm_pack_upconv_weight: bad argument"); return 2; }
     return ddpm::pack_upconv_weight(w, Cout, Cin, spatial_dims, static_cast<__half*>(dst), static_cast<cudaStream_t>(stream));

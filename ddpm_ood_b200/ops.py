@@ -162,6 +162,39 @@ def gn_apply(src0: torch.Tensor, st0: torch.Tensor, src1: Optional[torch.Tensor]
     return out
 
 
+def conv_in(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, with_stats: bool = True):
+    """The UNet's first conv: x fp32 [N, Cin, (D,) H, W], w fp32 [Cout, Cin, 3(,3),3] -> (fp16 [N, (D,) H, W, Cout],
+    statistics partials [N, parts, Cout/4, 2] or None)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and w.is_contiguous()
+    sd = x.dim() - 2
+    n, cin = x.shape[:2]
+    d = x.shape[2] if sd == 3 else 1
+    h, wd = x.shape[-2:]
+    cout = w.shape[0]
+    out = torch.empty((n,) + tuple(x.shape[2:]) + (cout,), dtype=torch.float16, device=x.device)
+    parts = lib().ddpm_conv_in_stats_parts(cin, cout, sd, d, h, wd) if with_stats else 0
+    st = torch.full((n, parts, cout // 4, 2), float("nan"), dtype=torch.float32, device=x.device) if parts else None
+    check(lib().ddpm_conv_in(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), n, cin, d, h, wd, cout, sd,
+                             _ptr(st), current_stream_ptr()), "ddpm_conv_in")
+    return out, st
+
+
+def out_norm_conv(src: torch.Tensor, st: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, w: torch.Tensor,
+                  b: torch.Tensor, groups: int, eps: float) -> torch.Tensor:
+    """The UNet tail GroupNorm -> SiLU -> 3x3 conv to Cout in {1, 3} channels without the normalised tensor in HBM.
+    src fp16 [N, H, W, C] with statistics partials st [N, parts, C/4, 2]; w fp32 [Cout, C, 3, 3]; returns fp32
+    [N, Cout, H, W]."""
+    assert src.dtype == torch.float16 and src.is_contiguous() and src.dim() == 4
+    n, h, wd, c = src.shape
+    cout = w.shape[0]
+    ws = torch.empty((n, h * wd, 9 * cout), dtype=torch.float32, device=src.device)
+    out = torch.empty((n, cout, h, wd), dtype=torch.float32, device=src.device)
+    check(lib().ddpm_out_norm_conv(src.data_ptr(), st.data_ptr(), st.shape[1], gamma.data_ptr(), beta.data_ptr(),
+                                   w.data_ptr(), b.data_ptr(), ws.data_ptr(), out.data_ptr(), n, c, h, wd, cout, groups,
+                                   eps, current_stream_ptr()), "ddpm_out_norm_conv")
+    return out
+
+
 def attention(qkv: torch.Tensor, n: int, t: int, heads: int, scale: float, impl: int = 0) -> torch.Tensor:
     """qkv: fp16 [n*t, 3C] (q | k | v); returns fp16 [n*t, C] = softmax(q k^T * scale) v per (image, head)."""
     assert qkv.dtype == torch.float16 and qkv.is_contiguous() and qkv.shape[0] == n * t

@@ -105,6 +105,22 @@ DDPM_API int ddpm_gn_finalize(int C0, const float* st0, int parts0, int C1, cons
                               const float* gamma, const float* beta, float* ab, int N, int S, int groups, float eps,
                               void* stream);
 
+/* The UNet's first conv (DiffusionModelUNet.conv_in: image channels -> num_channels[0], 3x3 / 3x3x3, pad 1) from the
+ * fp32 NC(D)HW sample to the fp16 channels-last activation, with the GroupNorm statistics partials of the next norm
+ * ([N, ddpm_conv_in_stats_parts, Cout/4, 2] fp32; NULL to skip, and required NULL where ddpm_conv_in_stats_parts is 0). */
+DDPM_API int ddpm_conv_in_stats_parts(int Cin, int Cout, int spatial_dims, int D, int H, int W);
+DDPM_API int ddpm_conv_in(const float* x, const float* w, const float* b, void* out, int N, int Cin, int D, int H, int W,
+                          int Cout, int spatial_dims, float* stats_out, void* stream);
+
+/* The UNet's tail, `out` = GroupNorm -> SiLU -> 3x3 conv to the image's few channels (DiffusionModelUNet.out,
+ * generative/networks/nets/diffusion_model_unet.py, called from src/trainers/reconstruct.py:150), without materialising
+ * the normalised tensor: src fp16 [N, H*W, C] with its statistics partials st [N, parts, C/4, 2] (sum, sum of squares
+ * per 4-channel quad, as the producing conv's epilogue emits them); w fp32 [Cout, C, 3, 3], b fp32 [Cout];
+ * taps_ws fp32 [N, H*W, 9*Cout] scratch; out fp32 [N, Cout, H, W]. 2-D, (C, Cout) in {(128,1), (128,3), (256,1)}. */
+DDPM_API int ddpm_out_norm_conv(const void* src, const float* st, int parts, const float* gamma, const float* beta,
+                                const float* w, const float* b, float* taps_ws, float* out, int N, int C, int H, int W,
+                                int Cout, int groups, float eps, void* stream);
+
 /* fp32 conv weight [Cout][Cin][3^dims] -> fp16 sub-pixel phase weights [2^dims * Cout][2^dims * Cin] for upsample2. */
 DDPM_API int ddpm_pack_upconv_weight(const float* w, int Cout, int Cin, int spatial_dims, void* dst, void* stream);
 

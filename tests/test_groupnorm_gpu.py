@@ -78,3 +78,56 @@ def test_groupnorm_kernels_match_torch(case):
             err = (got - want).abs().max().item()
             assert err < 4e-3 * max(1.0, want.abs().max().item()), (name, silu, err)
         assert ((one - two).abs() > 0).float().mean().item() < 2e-3, "only rare 1-ulp rounding flips may differ"
+
+
+@pytest.mark.parametrize("n,hw,c,cout,parts", [(3, (32, 32), 128, 1, 4), (2, (32, 32), 128, 3, 1), (2, (64, 64), 128, 3, 2),
+                                              (5, (28, 28), 128, 1, 1), (2, (16, 16), 256, 1, 3), (300, (32, 32), 128, 1, 2)])
+def test_out_norm_conv_matches_torch(n, hw, c, cout, parts):
+    """UNet tail (GroupNorm -> SiLU -> 3x3 conv to the image channels; generative DiffusionModelUNet.out) through
+    ddpm_out_norm_conv: warp-MMA tap reduction + gather vs torch fp32 on the same fp16 activation. The normalised value
+    is rounded to fp16 (as everywhere in the UNet), the weights stay fp32-accurate (hi + lo halves): 2e-3 of the output
+    scale."""
+    from ddpm_ood_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(n + c + cout)
+    h, w_ = hw
+    x = (torch.randn((n, h, w_, c), generator=g, device="cuda") * 1.3 + 0.2).half()
+    # statistics partials as a producer would emit them: split the pixels into `parts` slices
+    xs = x.float().reshape(n, h * w_, c // 4, 4)
+    bounds = [round(i * h * w_ / parts) for i in range(parts + 1)]
+    st = torch.stack([torch.stack([xs[:, a:b].sum(dim=(1, 3)), (xs[:, a:b] ** 2).sum(dim=(1, 3))], dim=-1)
+                      for a, b in zip(bounds[:-1], bounds[1:])], dim=1).contiguous()
+    gamma = 1 + 0.1 * torch.randn(c, generator=g, device="cuda")
+    beta = 0.1 * torch.randn(c, generator=g, device="cuda")
+    w = (torch.randn((cout, c, 3, 3), generator=g, device="cuda") * 0.05).contiguous()
+    b = torch.randn(cout, generator=g, device="cuda")
+    got = ops.out_norm_conv(x, st, gamma, beta, w, b, 32, 1e-6)
+    z = F.silu(F.group_norm(x.float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-6))
+    want = F.conv2d(z.double(), w.double(), b.double(), padding=1).float()  # fp64: cuDNN fp32 may use TF32
+    assert got.shape == want.shape
+    err = (got - want).abs().max().item()
+    assert err < 2e-3 * max(1.0, want.abs().max().item()), err
+
+
+@pytest.mark.parametrize("n,cin,hw,cout", [(3, 1, (32, 32), 128), (2, 3, (32, 32), 128), (2, 3, (64, 64), 128),
+                                           (5, 1, (28, 28), 128), (2, 1, (8, 8), 128), (2, 1, (32, 32), 256),
+                                           (2, 1, (20, 12), 128), (300, 1, (32, 32), 128)])
+def test_conv_in_matches_torch(n, cin, hw, cout):
+    """UNet head (DiffusionModelUNet.conv_in) through ddpm_conv_in: fp32 image -> fp16 channels-last activation + the
+    GroupNorm statistics of the next norm. The warp-MMA kernel splits both operands into fp16 hi + lo halves, so the only
+    rounding is the fp16 output (2^-11 relative)."""
+    from ddpm_ood_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(n + cin + cout)
+    x = torch.randn((n, cin) + hw, generator=g, device="cuda") * 1.7
+    w = (torch.randn((cout, cin, 3, 3), generator=g, device="cuda") * 0.3).contiguous()
+    b = torch.randn(cout, generator=g, device="cuda")
+    out, st = ops.conv_in(x, w, b)
+    want = F.conv2d(x.double(), w.double(), b.double(), padding=1).permute(0, 2, 3, 1).float()  # fp64: cuDNN fp32 may use TF32
+    err = ((out.float() - want).abs() / want.abs().clamp_min(1.0)).max().item()
+    assert err < 6e-4, err
+    assert st is not None and torch.isfinite(st).all(), "every statistics part must be written"
+    want_s, want_q = _stats_from(out, st.shape[1])
+    got = st.sum(dim=1)
+    assert torch.allclose(got[..., 0], want_s, rtol=1e-5, atol=1e-2), (got[..., 0] - want_s).abs().max()
+    assert torch.allclose(got[..., 1], want_q, rtol=1e-5, atol=1e-2), (got[..., 1] - want_q).abs().max()
