@@ -242,7 +242,9 @@ class DiffusionModelUNet(nn.Module):
             self._synced_versions = ver
 
     def _workspace(self, n: int, d: int, h: int, w: int, device) -> torch.Tensor:
-        key = (n, d, h, w)
+        # one workspace (and engine plan) per shape and per concurrent lane: two chains in flight on two streams must
+        # not share activations (BatchReconstructor sets workspace_lane around its calls)
+        key = (n, d, h, w, getattr(self, "workspace_lane", 0))
         ws = self._workspaces.get(key)
         if ws is None:
             need = _lib.lib().ddpm_unet_workspace_bytes(self._handle, n, d, h, w)
