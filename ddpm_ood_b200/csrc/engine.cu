@@ -14,6 +14,18 @@ __global__ void add_vec_kernel(const float* a, const float* b, float* out, int n
     if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);
 }
 
+// conv2's packed weights widened by an identity block: out = W z + I x puts the ResnetBlock's identity residual on the
+// tensor pipe (fp16 x times 1.0 is exact in the fp32 accumulator) instead of latency-bound loads in the epilogue.
+__global__ void widen_with_identity_kernel(const __half* __restrict__ w, int cout, long long k, __half* __restrict__ dst) {
+    const long long kw = k + cout;
+    const long long total = static_cast<long long>(cout) * kw;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / kw, c = i - r * kw;
+        dst[i] = c < k ? w[r * k + c] : __float2half_rn(c - k == r ? 1.f : 0.f);
+    }
+}
+
 __global__ void pack_conv_weight_kernel2(const float* __restrict__ w, int Cout, int Cin, int taps,
                                          __half* __restrict__ dst, long long ktot, long long koff) {
     const long long total = static_cast<long long>(Cout) * Cin * taps;
@@ -108,6 +120,8 @@ ResW UNet::make_res(const std::string& prefix, int c0, int c1, int cout) {
     const long long k2 = static_cast<long long>(taps) * cout + (r.skip_conv ? cin : 0);
     r.w1 = arena_alloc<__half>(static_cast<size_t>(cout) * k1, true);
     r.w2 = arena_alloc<__half>(static_cast<size_t>(cout) * k2, true);
+    r.w2_id = (!r.skip_conv && use_halo_ && id_residual_mma_)
+                  ? arena_alloc<__half>(static_cast<size_t>(cout) * (k2 + cout), true) : nullptr;
     r.temb_off = P_;
     add_copy(prefix + ".norm1.weight", r.g1, cin);
     add_copy(prefix + ".norm1.bias", r.b1, cin);
@@ -141,6 +155,7 @@ AttnW UNet::make_attn(const std::string& prefix, int C, int head_channels) {
     a.bproj = arena_alloc<float>(C, false);
     a.wqkv = arena_alloc<__half>(static_cast<size_t>(3) * C * C, true);
     a.wproj = arena_alloc<__half>(static_cast<size_t>(C) * C, true);
+    a.wproj_id = attn_id_residual_mma_ ? arena_alloc<__half>(static_cast<size_t>(C) * 2 * C, true) : nullptr;
     add_copy(prefix + ".norm.weight", a.g, C);
     add_copy(prefix + ".norm.bias", a.b, C);
     const char* names[3] = {"to_q", "to_k", "to_v"};
@@ -171,6 +186,8 @@ int UNet::init() {
     if (const char* e = getenv("DDPM_FUSE_GN")) fuse_gn_stats_ = fuse_gn_stats_ && atoi(e) != 0;  // A/B switch for tests
     if (const char* e = getenv("DDPM_CONV_HALO")) use_halo_ = atoi(e) != 0;  // A/B switch for tests
     if (const char* e = getenv("DDPM_HALO_GN_IN_KERNEL")) halo_gn_in_kernel_ = atoi(e) != 0;  // A/B switch for tests
+    if (const char* e = getenv("DDPM_ID_RESIDUAL_MMA")) id_residual_mma_ = atoi(e) != 0;     // A/B switch for tests
+    if (const char* e = getenv("DDPM_ATTN_ID_RESIDUAL_MMA")) attn_id_residual_mma_ = atoi(e) != 0;
     use_halo_ = use_halo_ && fuse_gn_stats_ && c.spatial_dims == 2;
     in_gemm_ = (c.in_channels % 64 == 0);
     out_gemm_ = (c.out_channels % 128 == 0);
@@ -344,10 +361,24 @@ int UNet::finalize(cudaStream_t stream) {
     auto fold = [&](ResW& r) {
         add_vec_kernel<<<(r.cout + 255) / 256, 256, 0, stream>>>(r.bias2, r.bias_skip, r.bias2_total, r.cout);
     };
-    for (auto& L : down_) for (auto& r : L.res) fold(r);
-    fold(mid1_);
-    fold(mid2_);
-    for (auto& L : up_) for (auto& r : L.res) fold(r);
+    auto fold0 = fold;
+    auto fold_and_widen = [&](ResW& r) {
+        fold0(r);
+        if (r.w2_id) {
+            const long long k2 = static_cast<long long>(cfg_.spatial_dims == 3 ? 27 : 9) * r.cout;
+            widen_with_identity_kernel<<<148 * 4, 256, 0, stream>>>(r.w2, r.cout, k2, r.w2_id);
+        }
+    };
+    auto widen_attn = [&](AttnW& a) {
+        if (a.wproj_id) widen_with_identity_kernel<<<148 * 4, 256, 0, stream>>>(a.wproj, a.C, a.C, a.wproj_id);
+    };
+    for (auto& L : down_) for (auto& a : L.attn) widen_attn(a);
+    for (auto& L : up_) for (auto& a : L.attn) widen_attn(a);
+    widen_attn(mid_attn_);
+    for (auto& L : down_) for (auto& r : L.res) fold_and_widen(r);
+    fold_and_widen(mid1_);
+    fold_and_widen(mid2_);
+    for (auto& L : up_) for (auto& r : L.res) fold_and_widen(r);
     // timestep-embedding table: row t = all time_emb_proj outputs for timestep t (depends on weights only)
     if (!temb_table_) {
         if (cudaMalloc(&temb_table_, static_cast<size_t>(temb_rows_) * P_ * sizeof(float)) != cudaSuccess ||
@@ -533,12 +564,13 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             src.gamma = g; src.beta = bt; src.S = static_cast<int>(a.S()); src.groups = c.norm_num_groups; src.eps = c.norm_eps;
             return src;
         };
-        auto halo_conv = [&](ConvProblem q, const float* ab, int ab_channels, int temb_off, const HaloGnSource* src = nullptr) {
+        auto halo_conv = [&](ConvProblem q, const float* ab, int ab_channels, int temb_off, const HaloGnSource* src = nullptr,
+                             double flops = -1.0) {
             Op op{};
             op.type = Op::CONV_HALO;
             op.uses_temb = temb_off >= 0;
             op.temb_off = temb_off;
-            op.flops = conv_flops(q);
+            op.flops = flops >= 0.0 ? flops : conv_flops(q);
             if (!dry) {
                 int r = conv_halo_prepare(q, ab, ab_channels, sms, &op.halo, src);
                 if (r && !rc) rc = r;
@@ -577,17 +609,22 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             q2.spatial_dims = sd; q2.N = N; q2.D = h.D; q2.H = h.H; q2.W = h.W; q2.stride = 1;
             q2.n_seg = 1;
             q2.seg[0] = {hB, r.cout, 3};
+            q2.Cout = r.cout;
+            double flops2 = -1.0;
             if (r.skip_conv) {
                 q2.seg[q2.n_seg++] = {h.p, h.C, 1};
                 if (skip) q2.seg[q2.n_seg++] = {skip->p, skip->C, 1};
+            } else if (r.w2_id) {
+                flops2 = conv_flops(q2);             // the identity block is not algorithmic work
+                q2.seg[q2.n_seg++] = {h.p, h.C, 1};  // identity residual as a K segment against the I block of w2_id
             } else {
                 q2.residual = h.p;
             }
-            q2.weights = r.w2; q2.w_rows = r.cout; q2.Cout = r.cout; q2.mode = EPI_STORE;
+            q2.weights = (!r.skip_conv && r.w2_id) ? r.w2_id : r.w2; q2.w_rows = r.cout; q2.Cout = r.cout; q2.mode = EPI_STORE;
             q2.bias = r.bias2_total; q2.out = out.p; q2.stats_out = out.stats;
             q2.gn_silu = 1;
             const HaloGnSource src2 = gn_source(h1, nullptr, r.g2, r.b2);
-            halo_conv(q2, ab2, r.cout, -1, halo_gn_in_kernel_ ? &src2 : nullptr);
+            halo_conv(q2, ab2, r.cout, -1, halo_gn_in_kernel_ ? &src2 : nullptr, flops2);
             return out;
         };
         auto resblock = [&](const ResW& r, const Act& h, const Act* skip) -> Act {
@@ -652,7 +689,19 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
                 plan.ops.push_back(op);
             }
             Act out = measure ? shape_act(a.C, h.D, h.H, h.W) : new_act(a.C, h.D, h.H, h.W);
-            conv1x1(h, hB, a.wproj, a.bproj, a.C, h.p, out);
+            if (a.wproj_id) {  // out = Wproj attn + I h: the residual as a K segment (no loads in the epilogue)
+                ConvProblem q{};
+                q.spatial_dims = sd; q.N = N; q.D = h.D; q.H = h.H; q.W = h.W; q.stride = 1;
+                q.n_seg = 2;
+                q.seg[0] = {hB, a.C, 1};
+                q.seg[1] = {h.p, a.C, 1};
+                q.weights = a.wproj_id; q.w_rows = a.C; q.Cout = a.C; q.mode = EPI_STORE;
+                q.bias = a.bproj; q.out = out.p; q.stats_out = out.stats;
+                gemm(q, -1);
+                if (!measure) plan.ops.back().flops *= 0.5;  // the identity block is not algorithmic work
+            } else {
+                conv1x1(h, hB, a.wproj, a.bproj, a.C, h.p, out);
+            }
             return out;
         };
 

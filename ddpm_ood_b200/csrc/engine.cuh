@@ -41,6 +41,7 @@ struct ResW {
     float* bias1;
     __half* w2;  // [cout][9*cout (+ c0 + c1 when skip_conv)]
     float *bias2, *bias_skip, *bias2_total;
+    __half* w2_id;  // identity-residual blocks only: [cout][(taps + 1) * cout] = conv2 weights | I (residual as one more K segment)
     int temb_off;
     std::string prefix;
 };
@@ -50,6 +51,7 @@ struct AttnW {
     __half* wqkv;  // [3C][C]
     float* bqkv;
     __half* wproj;  // [C][C]
+    __half* wproj_id;  // [C][2C] = wproj | I (residual as a K segment), or null
     float* bproj;
     std::string prefix;
 };
@@ -187,6 +189,8 @@ class UNet {
     bool use_attn_tc_ = true;
     bool upconv_phases_ = true;  // nearest-x2 + conv as sub-pixel 2x2 convs (4/9 of the MACs, no upsampled tensor)
     bool fuse_gn_stats_ = true;  // GroupNorm statistics from the producers' epilogues (cpg % 4 == 0 required)
+    bool attn_id_residual_mma_ = false;  // same for the output projection of an AttentionBlock: measured no gain (K doubles)
+    bool id_residual_mma_ = true;    // identity residuals of halo-kernel ResnetBlocks ride the MMA as an I-weighted K segment
     bool halo_gn_in_kernel_ = true;  // the halo conv derives scale/shift from producer statistics itself (no gn_finalize)
     bool use_halo_ = true;       // halo-tile conv kernel with GroupNorm+SiLU applied on the fly (2-D, images >= 16 x 8)
     // arenas

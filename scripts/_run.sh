@@ -1,5 +1,8 @@
 cd /root/repo
-(timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
- python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
- timeout 600 python bench.py > gpurun_out/bench_s5.json 2> gpurun_out/bench_s5.err; tail -c 3000 gpurun_out/bench_s5.json
-) > gpurun_out/run54.log 2>&1
+(timeout 400 python -m pytest tests/test_unet_gpu.py tests/test_recon_gpu.py -q -x 2>&1 | tail -4
+ for v in 1 0; do
+ DDPM_ATTN_ID_RESIDUAL_MMA=$v timeout 200 python bench.py --batch 592 --steps 2 --warmup 3 --no_cpu_baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('attn_id_residual_mma=$v', d['value'], d['unet_fwd_ms'], d['roofline']['frac'], d['clocks']['sm_mhz'])"
+ done
+) > gpurun_out/run57.log 2>&1
