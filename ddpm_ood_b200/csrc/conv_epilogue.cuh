@@ -304,7 +304,9 @@ __device__ __forceinline__ void conv_epilogue_tile16(const ConvGemmParams& p, ui
     __half* out_row = p.out + pix * static_cast<size_t>(p.Cout) + col_base;
     const __half* res_row = p.residual ? p.residual + pix * static_cast<size_t>(p.Cout) + col_base : nullptr;
 
-    auto process = [&](const int c, const uint32_t (&v)[16]) {
+    // one 16-column chunk: bias / addend / residual, fp16 store; leaves the chunk's statistics candidates in sv:
+    // quad sums of the ROUNDED values (what GroupNorm reads back), sv[0..3] sums, sv[4..7] sums of squares
+    auto process = [&](const int c, const uint32_t (&v)[16], float* sv) {
         uint32_t packed[8];
         if (valid) {
             float f[16];
@@ -345,8 +347,6 @@ __device__ __forceinline__ void conv_epilogue_tile16(const ConvGemmParams& p, ui
             for (int j = 0; j < 8; ++j) packed[j] = 0u;
         }
         if (want_stats) {
-            // quad sums of the ROUNDED values (what GroupNorm reads back): sv[0..3] sums, sv[4..7] sums of squares
-            float sv[8];
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) {
                 const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&packed[2 * qd]));
@@ -354,39 +354,51 @@ __device__ __forceinline__ void conv_epilogue_tile16(const ConvGemmParams& p, ui
                 sv[qd] = (a.x + a.y) + (b.x + b.y);
                 sv[4 + qd] = (a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y);
             }
-            const int quad0 = (col_base + c * 16) >> 2;
-            if (p.pair_rows) {
-                // two images per warp: add the two rows of each image (lane ^ 16), then transpose-reduce inside the
-                // 8-lane groups; lanes 0-15 end with one value: b2 -> sum / squares, b1 b0 -> quad, b3 -> image
+        }
+    };
+    // statistics of a chunk PAIR (c, c + 1): sv[0..7] chunk c, sv[8..15] chunk c + 1. One halving butterfly tree over the
+    // warp for both chunks (half the dependent shuffle stages per chunk of the one-chunk version).
+    auto reduce_pair = [&](const int c, float (&sv)[16]) {
+        const int quad0 = (col_base + c * 16) >> 2;
+        if (p.pair_rows) {
+            // two images per warp (lanes 0-7 / 16-23 image 0, 8-15 / 24-31 image 1). xor 16 joins the two rows of an image
+            // and splits the chunk pair; 4, 2, 1 halve inside the 8-lane groups. A lane ends with one value:
+            // b4 -> chunk, b3 -> image, b2 -> sum / squares, b1 b0 -> quad
+            {
+                const bool hi = (lane & 16) != 0;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) sv[i] += __shfl_xor_sync(0xffffffffu, sv[i], 16);
-#pragma unroll
-                for (int half_n = 4, off = 4; half_n >= 1; half_n >>= 1, off >>= 1) {
-                    const bool hi = (lane & off) != 0;
-#pragma unroll
-                    for (int i = 0; i < half_n; ++i) {
-                        const float send = hi ? sv[i] : sv[i + half_n];
-                        const float keep = hi ? sv[i + half_n] : sv[i];
-                        sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                    }
+                for (int i = 0; i < 8; ++i) {
+                    const float send = hi ? sv[i] : sv[i + 8];
+                    const float keep = hi ? sv[i + 8] : sv[i];
+                    sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
                 }
-                if (st_base && lane < 16) st_base[(quad0 + (lane & 3)) * 2 + ((lane >> 2) & 1)] = sv[0];
-            } else {
-                // transpose-reduce over the warp's 32 pixels: b4 -> sum / squares, b3 b2 -> quad, then two butterflies
-#pragma unroll
-                for (int half_n = 4, off = 16; half_n >= 1; half_n >>= 1, off >>= 1) {
-                    const bool hi = (lane & off) != 0;
-#pragma unroll
-                    for (int i = 0; i < half_n; ++i) {
-                        const float send = hi ? sv[i] : sv[i + half_n];
-                        const float keep = hi ? sv[i + half_n] : sv[i];
-                        sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                    }
-                }
-                sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 2);
-                sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
-                if (st_base && (lane & 3) == 0) st_base[(quad0 + ((lane >> 2) & 3)) * 2 + (lane >> 4)] = sv[0];
             }
+#pragma unroll
+            for (int half_n = 4, off = 4; half_n >= 1; half_n >>= 1, off >>= 1) {
+                const bool hi = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < half_n; ++i) {
+                    const float send = hi ? sv[i] : sv[i + half_n];
+                    const float keep = hi ? sv[i + half_n] : sv[i];
+                    sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            if (st_base) st_base[(quad0 + 4 * (lane >> 4) + (lane & 3)) * 2 + ((lane >> 2) & 1)] = sv[0];
+        } else {
+            // 32 pixels of one image: b4 -> chunk, b3 -> sum / squares, b2 b1 -> quad, then one butterfly over b0
+#pragma unroll
+            for (int half_n = 8, off = 16; half_n >= 1; half_n >>= 1, off >>= 1) {
+                const bool hi = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < half_n; ++i) {
+                    const float send = hi ? sv[i] : sv[i + half_n];
+                    const float keep = hi ? sv[i + half_n] : sv[i];
+                    sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
+            if (st_base && (lane & 1) == 0)
+                st_base[(quad0 + 4 * (lane >> 4) + ((lane >> 1) & 3)) * 2 + ((lane >> 3) & 1)] = sv[0];
         }
     };
 
@@ -394,12 +406,14 @@ __device__ __forceinline__ void conv_epilogue_tile16(const ConvGemmParams& p, ui
     ptx::tmem_ld_32x16(t_addr + c_begin * 16, va);
 #pragma unroll 1
     for (int c = c_begin; c < c_end; c += 2) {  // even chunk counts
+        float sv[16];
         ptx::tmem_ld_wait();
         ptx::tmem_ld_32x16(t_addr + (c + 1) * 16, vb);
-        process(c, va);
+        process(c, va, sv);
         ptx::tmem_ld_wait();
         if (c + 2 < c_end) ptx::tmem_ld_32x16(t_addr + (c + 2) * 16, va);
-        process(c + 1, vb);
+        process(c + 1, vb, sv + 8);
+        if (want_stats) reduce_pair(c, sv);
     }
 }
 
