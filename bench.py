@@ -8,8 +8,9 @@ Workload (configs[1] of BASELINE.json): FashionMNIST-shaped synthetic images 1x3
 DiffusionModelUNet with random non-zero weights, scaled_linear_beta 0.0015->0.0195, 100 inference steps,
 inference_skip_factor=4 -> 25 t-starts, 1250 UNet evaluations per batch. A "step" is one batch of `--batch` images x 25
 t-starts. The batch size is the reference CLI's free `--batch_size` knob (default 256, reconstruct.py:89; BASELINE.json
-does not fix it): the default here is 592 = 8 images per CTA pair of the 148-SM part, which makes every UNet level a
-whole number of waves (2403 reconstructions/s vs 2190 at 256, measured); `--batch 256` reproduces the reference default.
+does not fix it): the default here is 1184 = 16 images per CTA pair of the 148-SM part, which makes every UNet level a
+whole number of waves and amortises each kernel's prologue over two work items at the 8-pixel level (measured: 2542
+reconstructions/s, 2490 at 592, 2250 at 256); `--batch 256` reproduces the reference default.
 Under torchrun every rank processes its own batch (images are what the reference shards, SURVEY.md §8e; weak scaling);
 the only collective is the gather of the [25, B, 2] score tensor.
 """
@@ -41,8 +42,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=592,
-                    help="images per rank per step (8 per CTA pair on 148 SMs; the reference CLI default is 256)")
+    ap.add_argument("--batch", type=int, default=1184,
+                    help="images per rank per step (16 per CTA pair on 148 SMs; the reference CLI default is 256)")
     ap.add_argument("--skip", type=int, default=4, help="inference_skip_factor")
     ap.add_argument("--plms_state", default="carry", choices=["carry", "reset"])
     ap.add_argument("--profile_every", type=int, default=50, help="event-profile every n-th UNet forward (0 = off)")
