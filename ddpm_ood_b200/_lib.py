@@ -143,6 +143,7 @@ SIGNATURES = {
     "ddpm_out_norm_conv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_float, C.c_void_p]),
+    "ddpm_simplex_noise": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_double, C.c_double, C.c_void_p]),
     "ddpm_scale_intensity": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "ddpm_lpips_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "ddpm_lpips_destroy": (None, [C.c_void_p]),

@@ -13,6 +13,7 @@ import torch.distributed as dist
 from ..networks import DiffusionModelUNet, PassthroughVQVAE
 from ..reconstruction import snr_shift_
 from ..schedulers import DDPMScheduler
+from ..simplex_noise import Simplex_CLASS
 
 
 class BaseTrainer:
@@ -70,7 +71,9 @@ class BaseTrainer:
             snr_shift_(self.scheduler, self.snr_shift)
         self.simplex_noise = bool(args.simplex_noise)
         if self.simplex_noise:
-            raise NotImplementedError("simplex noise is SURVEY.md §8(f)-2 'next' (default --simplex_noise=0)")
+            if args.spatial_dimension != 2:
+                raise NotImplementedError("simplex noise is defined for 2-D images (src/utils/simplex_noise.py:15-79)")
+            self.simplex = Simplex_CLASS()
         self.spatial_dimension = args.spatial_dimension
         self.image_size = int(args.image_size) if args.image_size else args.image_size
         if args.latent_pad:

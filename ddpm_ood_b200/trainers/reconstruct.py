@@ -20,6 +20,7 @@ import torch.distributed as dist
 from ..data import get_training_data_loader
 from ..losses import PerceptualLoss
 from ..reconstruction import BatchReconstructor, ReconConfig
+from ..simplex_noise import generate_simplex_noise
 from .base import BaseTrainer
 
 
@@ -78,6 +79,22 @@ class Reconstruct(BaseTrainer):
         return BatchReconstructor(self.model, self._pl, cfg, self.device, vqvae_model=None,
                                   latent_pad=self.latent_pad if self.do_latent_pad else None)
 
+    def _simplex_fn(self, images):
+        """--simplex_noise=1: generate_simplex_noise per t-start (reference trainers/reconstruct.py:133-139), else None
+        (Gaussian noise drawn by the engine)."""
+        if not self.simplex_noise:
+            return None
+        if self.do_latent_pad:
+            raise NotImplementedError("simplex noise with --latent_pad (latent models are SURVEY §8 f-1)")
+        shape = tuple(images.shape)
+        probe = torch.empty(shape, device=self.device)
+
+        def fn(i, t_start):
+            t = torch.full((shape[0],), int(t_start), dtype=torch.long)
+            return generate_simplex_noise(self.simplex, x=probe, t=t, in_channels=shape[1])
+
+        return fn
+
     def get_scores(self, loader, dataset_name, inference_skip_factor):
         if dist.is_initialized():
             sys.stdout = sys.__stdout__
@@ -90,7 +107,7 @@ class Reconstruct(BaseTrainer):
         names, ts, pds, mses = [], [], [], []
         for batch in loader:
             t1 = time.time()
-            res = engine.score_batch(batch["image"], inference_skip_factor)
+            res = engine.score_batch(batch["image"], inference_skip_factor, noise_fn=self._simplex_fn(batch["image"]))
             t_grid = res["t"]
             pd_host = res["perceptual_difference"].cpu()  # one D2H per batch
             mse_host = res["mse"].cpu()

@@ -252,6 +252,14 @@ DDPM_API int ddpm_auc_counts(const float* in_scores, int n_in, const float* out_
  * as stored on disk, dst fp32 in [0, 1]; a constant image maps to zeros. */
 DDPM_API int ddpm_scale_intensity(const void* src, int src_is_u8, float* dst, int N, long long per_image, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ simplex noise
+ * ("next" row) generate_simplex_noise of src/utils/simplex_noise.py:15-79 for --simplex_noise=1
+ * (src/trainers/reconstruct.py:133-139): seeds int64 [C * B] in drawing order (channel outer, image inner; device),
+ * t int64 [B] (device), out fp32 [B, C, H, W]; tables_ws: C * B * 256 bytes of scratch for the permutation tables
+ * (_init, :559-577). fp64 arithmetic in the reference's operand order: bit-identical values. */
+DDPM_API int ddpm_simplex_noise(const long long* seeds, const long long* t, float* out, unsigned char* tables_ws, int B,
+                                int C, int H, int W, int octaves, double persistence, double frequency, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,3 +81,41 @@ def test_cli_writes_the_reference_csv_contract(tmp_path):
     want = np.array(rows)
     got = val[["perceptual_difference", "mse"]].to_numpy()
     assert np.allclose(got, want, rtol=1e-5, atol=0)
+
+
+def test_cli_simplex_noise_mode(tmp_path):
+    """--simplex_noise=1 (reference reconstruct.py:83-88, trainers/reconstruct.py:133-139): the CLI's scores are the
+    engine's with generate_simplex_noise as the noise source under the same numpy seed."""
+    sys.path.insert(0, str(ROOT))
+    import reconstruct as cli
+    from ddpm_ood_b200.data import SimpleLoader
+    from ddpm_ood_b200.simplex_noise import Simplex_CLASS, generate_simplex_noise
+    from ddpm_ood_b200.trainers import Reconstruct
+    from oracle import unet as ou
+
+    val_ids, val_paths = _dataset(tmp_path, "val", 3, 0)
+    run = tmp_path / "runs" / "m"
+    run.mkdir(parents=True)
+    weights = ou.randomize_(ou.make_small(2, 1), seed=5).state_dict()
+    torch.save({"epoch": 7, "global_step": 1, "best_loss": 0.5, "model_state_dict": weights}, run / "checkpoint.pth")
+    args = cli.parse_args([
+        "--output_dir", str(tmp_path / "runs"), "--model_name", "m", "--validation_ids", str(val_ids),
+        "--in_ids", str(val_ids), "--out_ids", str(val_ids), "--run_in", "0", "--run_out", "0", "--is_grayscale", "1",
+        "--batch_size", "3", "--beta_schedule", "scaled_linear_beta", "--beta_start", "0.0015", "--beta_end", "0.0195",
+        "--inference_skip_factor", "64", "--simplex_noise", "1"])
+    np.random.seed(3)
+    recon = Reconstruct(args)  # Simplex_CLASS() draws its first seed here, like the reference's BaseTrainer
+    recon.reconstruct(args)
+    val = pd.read_csv(run / "ood" / "results_val.csv", index_col=0)
+    assert list(val["t"]) == [10] * 3 + [650] * 3 and np.isfinite(val[["perceptual_difference", "mse"]].to_numpy()).all()
+
+    np.random.seed(3)
+    simplex = Simplex_CLASS()
+    engine = recon._engine()
+    tf = dict(is_grayscale=True, spatial_dimension=2, image_size=None, image_roi=None, add_vflip=False, add_hflip=False)
+    batch = next(iter(SimpleLoader([{"image": p} for p in val_paths], 3, False, **tf)))["image"]
+    probe = torch.empty(tuple(batch.shape), device="cuda")
+    res = engine.score_batch(batch, 64, noise_fn=lambda i, t: generate_simplex_noise(
+        simplex, x=probe, t=torch.full((3,), int(t), dtype=torch.long), in_channels=1))
+    want = np.stack([res["perceptual_difference"].cpu().numpy().reshape(-1), res["mse"].cpu().numpy().reshape(-1)], axis=1)
+    assert np.allclose(val[["perceptual_difference", "mse"]].to_numpy(), want, rtol=1e-5, atol=0)
