@@ -358,12 +358,9 @@ int UNet::finalize(cudaStream_t stream) {
     for (auto& kv : slots_) {
         if (!kv.second.set) { set_error("unet: parameter '%s' was never set", kv.first.c_str()); return 8; }
     }
-    auto fold = [&](ResW& r) {
-        add_vec_kernel<<<(r.cout + 255) / 256, 256, 0, stream>>>(r.bias2, r.bias_skip, r.bias2_total, r.cout);
-    };
-    auto fold0 = fold;
+    // per ResnetBlock: conv2 bias + skip-conv bias in one vector; identity-residual blocks get conv2's weights | I
     auto fold_and_widen = [&](ResW& r) {
-        fold0(r);
+        add_vec_kernel<<<(r.cout + 255) / 256, 256, 0, stream>>>(r.bias2, r.bias_skip, r.bias2_total, r.cout);
         if (r.w2_id) {
             const long long k2 = static_cast<long long>(cfg_.spatial_dims == 3 ? 27 : 9) * r.cout;
             widen_with_identity_kernel<<<148 * 4, 256, 0, stream>>>(r.w2, r.cout, k2, r.w2_id);
