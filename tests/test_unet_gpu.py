@@ -223,3 +223,23 @@ def test_uniform_timestep_table_equals_per_sample_path():
         eps = ours(b, timesteps=torch.full((2,), t, dtype=torch.long, device="cuda"))
         b, _ = sched2.step(eps, t, b)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["fashionmnist_1x32x32", "native_1x28x28"])
+def test_identity_residual_on_the_tensor_pipe_equals_epilogue_add(name, monkeypatch):
+    """ResnetBlocks without a skip conv feed their input as one more K segment against an identity block of conv2's
+    weights (engine.cu: widen_with_identity_kernel) instead of loading it in the epilogue. fp16 x times 1.0 is exact in
+    the fp32 accumulator: the two paths differ by summation order only (same fp16 noise floor as the GroupNorm test)."""
+    case = FWD_CASES[name]
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(case["shape"], generator=g).cuda()
+    t = torch.randint(0, 1000, (case["shape"][0],), generator=g).cuda()
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("DDPM_ID_RESIDUAL_MMA", flag)
+        ref, ours = _pair(case["sd"], case["ch"])
+        outs[flag] = ours(x, timesteps=t).cpu()
+    assert _rel(outs["1"], outs["0"]) < 2.5e-3
+    with torch.no_grad():
+        want = ref(x.cpu(), t.cpu())
+    assert _rel(outs["1"], want) < 4e-3 and _rel(outs["0"], want) < 4e-3
