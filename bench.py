@@ -215,7 +215,7 @@ def run_ours(args):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         pl = PerceptualLoss(dimensions=2, include_pixel_loss=False, is_fake_3d=False, lpips_normalize=True,
-                            spatial=False).to(dev)
+                            spatial=False, allow_synthetic_weights=True).to(dev)
     cfg = ReconConfig(beta_schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0195,
                       plms_state=args.plms_state)
     eng = BatchReconstructor(model, pl, cfg, dev)

@@ -156,22 +156,48 @@ SIGNATURES = {
 }
 
 
+ABI_VERSION = 5  # must equal ddpm_abi_version() of the loaded library (include/ddpm_ood_b200.h DDPM_ABI_VERSION)
+
+
+def _verify(L: C.CDLL) -> None:
+    """A stale or foreign .so must not load silently: every declared symbol resolves, the ABI version matches and the
+    struct layouts the library was compiled with equal the ctypes mirrors above."""
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(L, name)
+        except AttributeError as e:
+            raise DdpmError(f"{LIB_PATH} does not export {name}: the library is stale, rebuild it with "
+                            f"`python -m ddpm_ood_b200.csrc.build --force`") from e
+        fn.restype = res
+        fn.argtypes = args
+    got = L.ddpm_abi_version()
+    if got != ABI_VERSION:
+        raise DdpmError(f"{LIB_PATH} has ABI version {got}, this package needs {ABI_VERSION}: rebuild it with "
+                        f"`python -m ddpm_ood_b200.csrc.build --force`")
+    sizes = [C.c_int(0) for _ in range(4)]
+    L.ddpm_struct_sizes(*[C.byref(v) for v in sizes])
+    want = [C.sizeof(ConvArgs), C.sizeof(UNetConfig), C.sizeof(PlmsStep), C.sizeof(OpProfile)]
+    if [v.value for v in sizes] != want:
+        raise DdpmError(f"{LIB_PATH}: struct layouts {[v.value for v in sizes]} differ from the Python mirrors {want} "
+                        f"(ConvArgs, UNetConfig, PlmsStep, OpProfile): rebuild the library")
+
+
 def lib() -> C.CDLL:
-    """Load the shared library (building it first if it is missing and nvcc is present)."""
+    """Load the shared library. If it is missing or older than its sources and nvcc is present it is (re)built first,
+    under an exclusive file lock and with an atomic rename, so concurrent ranks of one torchrun launch neither build
+    twice nor load a half-written file."""
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        from .csrc.build import build
+    from .csrc import build as _build
 
-        build(verbose=False)
+    if _build.needs_build() and _build.have_nvcc():
+        _build.build(verbose=False)
     if not LIB_PATH.exists():
-        raise DdpmError(f"{LIB_PATH} is missing: build it with `python -m ddpm_ood_b200.csrc.build`")
+        raise DdpmError(f"{LIB_PATH} is missing and cannot be built here (no nvcc): build it with "
+                        f"`python -m ddpm_ood_b200.csrc.build`")
     L = C.CDLL(str(LIB_PATH))
-    for name, (res, args) in SIGNATURES.items():
-        fn = getattr(L, name)  # AttributeError here means header and library disagree
-        fn.restype = res
-        fn.argtypes = args
+    _verify(L)
     _lib = L
     return L
 

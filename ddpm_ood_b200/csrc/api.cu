@@ -89,7 +89,7 @@ int pack_upconv_weight(const float* w, int Cout, int Cin, int dims, __half* dst,
 extern "C" {
 
 const char* ddpm_last_error(void) { return ddpm::last_error(); }
-int ddpm_abi_version(void) { return 4; }
+int ddpm_abi_version(void) { return DDPM_ABI_VERSION; }
 
 void ddpm_struct_sizes(int* conv_args, int* unet_config, int* plms_step, int* op_profile) {
     if (conv_args) *conv_args = static_cast<int>(sizeof(ddpm_conv_args));

@@ -5,8 +5,10 @@ lpips_normalize, spatial)`, `pl(y, y_pred)`; src/trainers/reconstruct.py:82-88,1
 `lpips.LPIPS.state_dict()` under the `perceptual_function.` prefix, so real LPIPS weights load with `load_state_dict`.
 
 Weights: the `lpips` package (which bundles the linear heads and pulls torchvision's pretrained AlexNet) is used when it
-is importable; otherwise a seeded synthetic initialisation is used and a warning is printed, because scores are then
-self-consistent but not comparable with the reference's.
+is importable, or a saved state dict (lpips_kwargs["model_path"] / DDPM_LPIPS_STATE_DICT). Without either the constructor
+RAISES: a seeded synthetic initialisation exists only behind an explicit opt-in (allow_synthetic_weights=True or
+DDPM_LPIPS_ALLOW_SYNTHETIC=1) for tests, bench.py and smoke(), whose scores are self-consistent but not comparable with
+the reference's.
 """
 from __future__ import annotations
 
@@ -153,7 +155,7 @@ def _try_real_lpips_weights(model: _LPIPSAlex, lpips_kwargs: Dict) -> bool:
 class PerceptualLoss(nn.Module):
     def __init__(self, dimensions: int, include_pixel_loss: bool = True, is_fake_3d: bool = True,
                  drop_ratio: float = 0.0, fake_3d_axis: Tuple[int, ...] = (2, 3, 4), lpips_kwargs: Dict = None,
-                 lpips_normalize: bool = True, spatial: bool = False):
+                 lpips_normalize: bool = True, spatial: bool = False, allow_synthetic_weights: bool = False):
         super().__init__()
         if dimensions not in (2, 3):
             raise NotImplementedError("Perceptual loss is implemented only in 2D and 3D.")
@@ -178,9 +180,17 @@ class PerceptualLoss(nn.Module):
         self.lpips_normalize = lpips_normalize
         self.perceptual_function = _LPIPSAlex()
         if not _try_real_lpips_weights(self.perceptual_function, self.lpips_kwargs):
-            warnings.warn("lpips weights not found (no `lpips` package, no model_path/DDPM_LPIPS_STATE_DICT): using a "
-                          "seeded synthetic AlexNet/linear-head initialisation; perceptual_difference values are "
-                          "self-consistent but not comparable with the reference's.")
+            # Production (trainers.Reconstruct, the CLI) must not write `perceptual_difference` columns computed with
+            # made-up weights into reference-shaped CSVs: refuse unless the caller opts in (tests, bench, smoke - which
+            # then load the oracle's weights or only time the kernels).
+            if not (allow_synthetic_weights or os.environ.get("DDPM_LPIPS_ALLOW_SYNTHETIC") == "1"):
+                raise _lib.DdpmError(
+                    "LPIPS weights not found: install the `lpips` package, or point lpips_kwargs['model_path'] / "
+                    "DDPM_LPIPS_STATE_DICT at a saved lpips.LPIPS(net='alex').state_dict(). A seeded synthetic "
+                    "initialisation exists for tests and benchmarks only (allow_synthetic_weights=True or "
+                    "DDPM_LPIPS_ALLOW_SYNTHETIC=1); its scores are not comparable with the reference's.")
+            warnings.warn("LPIPS: synthetic AlexNet/linear-head weights (explicit opt-in); perceptual_difference values "
+                          "are self-consistent but not comparable with the reference's.")
         self.perceptual_factor = 1
 
     @torch.no_grad()

@@ -8,7 +8,7 @@ scores stay on the device until the batch is done (the reference syncs with `.it
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Callable, Dict, Optional
+from typing import Callable, Dict, List, Optional, Sequence
 
 import torch
 import torch.nn.functional as F
@@ -45,6 +45,47 @@ def clamp_mse(x: torch.Tensor, x0: torch.Tensor, b_scale: float):
     return recon, mse
 
 
+def partition_t_starts(chain_lens: Sequence[int], world: int) -> List[List[int]]:
+    """Split the t-start grid over `world` ranks, balancing UNet evaluations (a chain from t costs ~t/10 forwards, so a
+    round-robin split leaves the last rank with up to twice the work of the first): longest chain first onto the least
+    loaded rank, ties to the lowest rank - deterministic, every rank computes the same table. Returns the grid
+    positions of each rank, ascending."""
+    order = sorted(range(len(chain_lens)), key=lambda i: (-int(chain_lens[i]), i))
+    load = [0] * world
+    parts: List[List[int]] = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        parts[r].append(i)
+        load[r] += int(chain_lens[i])
+    # local search: move or swap chains between the most loaded rank and any other while that lowers the larger of the two
+    for _ in range(64 * world):
+        hi = max(range(world), key=lambda k: (load[k], -k))
+        best, best_max = None, load[hi]
+        for lo in range(world):
+            if lo == hi:
+                continue
+            for a in parts[hi]:
+                la = int(chain_lens[a])
+                for b in [None] + parts[lo]:
+                    lb = int(chain_lens[b]) if b is not None else 0
+                    m = max(load[hi] - la + lb, load[lo] + la - lb)
+                    if m < best_max:
+                        best, best_max = (lo, a, b), m
+        if best is None:
+            break
+        lo, a, b = best
+        parts[hi].remove(a)
+        parts[lo].append(a)
+        load[hi] -= int(chain_lens[a])
+        load[lo] += int(chain_lens[a])
+        if b is not None:
+            parts[lo].remove(b)
+            parts[hi].append(b)
+            load[lo] -= int(chain_lens[b])
+            load[hi] += int(chain_lens[b])
+    return [sorted(p) for p in parts]
+
+
 @dataclass
 class ReconConfig:
     prediction_type: str = "epsilon"
@@ -66,27 +107,49 @@ class BatchReconstructor:
         self.device = torch.device(device)
         self.vqvae_model = vqvae_model
         self.latent_pad = latent_pad
+        self._sched = None
         if cfg.plms_state not in ("carry", "reset"):
             raise ValueError("plms_state must be 'carry' or 'reset'")
 
     def make_scheduler(self) -> PNDMScheduler:
+        """The reference builds a fresh PNDMScheduler per batch (trainers/reconstruct.py:98-118); here ONE object is
+        kept and `set_timesteps` puts it back into the freshly-constructed state (empty PLMS history, counter 0), so
+        its cached per-chain coefficient tables survive from batch to batch."""
         c = self.cfg
-        s = PNDMScheduler(num_train_timesteps=1000, skip_prk_steps=True, prediction_type=c.prediction_type,
-                          schedule=c.beta_schedule, beta_start=c.beta_start, beta_end=c.beta_end)
-        snr_shift_(s, c.snr_shift)
-        s.set_timesteps(c.num_inference_steps)
-        return s
+        if self._sched is None:
+            s = PNDMScheduler(num_train_timesteps=1000, skip_prk_steps=True, prediction_type=c.prediction_type,
+                              schedule=c.beta_schedule, beta_start=c.beta_start, beta_end=c.beta_end)
+            snr_shift_(s, c.snr_shift)
+            self._sched = s
+        self._sched.set_timesteps(c.num_inference_steps)
+        return self._sched
 
     @torch.no_grad()
     def score_batch(self, images_original: torch.Tensor, inference_skip_factor: int,
                     noise_fn: Optional[Callable[[int, int], torch.Tensor]] = None,
-                    keep_recons: bool = False) -> Dict[str, object]:
+                    keep_recons: bool = False, t_starts: Optional[Sequence[int]] = None,
+                    t_indices: Optional[Sequence[int]] = None) -> Dict[str, object]:
         """images_original: [B, C, ...] in [0, 1], host or device. Returns device tensors:
-        {"t": int64 [n_t] (host), "perceptual_difference": fp32 [n_t, B], "mse": fp32 [n_t, B]}."""
+        {"t": int64 [n_t] (host), "perceptual_difference": fp32 [n_t, B], "mse": fp32 [n_t, B]}.
+
+        t_starts: run these grid values instead of the whole grid (bounded parity samples).
+        t_indices: run only these positions of the grid - this rank's share when the grid is sharded over ranks
+        (`partition_t_starts`; exact only with plms_state="reset"). `noise_fn(i, t)` always receives the
+        position i in the FULL grid, so every rank draws the noise the single-rank run would."""
         c = self.cfg
         sched = self.make_scheduler()
         timesteps = sched.timesteps
         starts = reversed(timesteps)[1::inference_skip_factor]  # the t-start grid, trainers/reconstruct.py:119-120
+        grid_pos = list(range(len(starts)))
+        if t_starts is not None:
+            starts = torch.tensor([int(t) for t in t_starts], dtype=torch.long)
+            grid_pos = list(range(len(starts)))
+        if t_indices is not None:
+            if c.plms_state != "reset":
+                raise ValueError("sharding the t-start grid needs plms_state='reset': in 'carry' mode the PLMS history "
+                                 "couples every chain to its predecessor")
+            grid_pos = [int(i) for i in t_indices]
+            starts = starts[torch.tensor(grid_pos, dtype=torch.long)] if grid_pos else starts[:0]
         images_original = images_original.to(self.device, non_blocking=True).float().contiguous()
         images = images_original if self.vqvae_model is None else self.vqvae_model.encode_stage_2_inputs(images_original)
         if self.latent_pad:
@@ -102,7 +165,7 @@ class BatchReconstructor:
             if c.plms_state == "reset":
                 sched.reset_chain()
             start_timesteps = torch.Tensor([t_start] * B).long()
-            noise = noise_fn(i, int(t_start)) if noise_fn is not None else torch.randn_like(images)
+            noise = noise_fn(grid_pos[i], int(t_start)) if noise_fn is not None else torch.randn_like(images)
             x = sched.add_noise(original_samples=scaled, noise=noise, timesteps=start_timesteps)
             chain = [int(s) for s in timesteps[timesteps <= t_start]]
             sched.run_chain(self.model, x, chain)
@@ -111,7 +174,9 @@ class BatchReconstructor:
             if self.vqvae_model is not None:
                 x = self.vqvae_model.decode_stage_2_outputs(x).float().contiguous()
             recon, mse = clamp_mse(x, images_original, c.b_scale)
-            if c.spatial_dimension == 2:
+            if self.pl is None:  # latent-only runs (a 128-channel latent is not an LPIPS input): MSE only
+                pd_all[i] = float("nan")
+            elif c.spatial_dimension == 2:
                 if images_original.shape[3] == 28:
                     pd = self.pl(F.pad(images_original, (2, 2, 2, 2)), F.pad(recon, (2, 2, 2, 2)))
                 else:
@@ -123,7 +188,8 @@ class BatchReconstructor:
             mse_all[i] = mse
             if keep_recons:
                 recons.append(recon)
-        out: Dict[str, object] = {"t": starts.clone(), "perceptual_difference": pd_all, "mse": mse_all}
+        out: Dict[str, object] = {"t": starts.clone(), "t_index": grid_pos, "perceptual_difference": pd_all,
+                                  "mse": mse_all}
         if keep_recons:
             out["recons"] = recons
         return out

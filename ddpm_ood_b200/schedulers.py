@@ -101,6 +101,8 @@ class PNDMScheduler(Scheduler):
         self._hist: List[int] = []
         self._ring: Optional[torch.Tensor] = None
         self._stash: Optional[torch.Tensor] = None
+        self._coeff_key = None
+        self._chain_cache = {}
         self.set_timesteps(num_train_timesteps)
 
     # ------------------------------------------------------------------ reference surface
@@ -134,6 +136,19 @@ class PNDMScheduler(Scheduler):
             self._ring = torch.zeros((4, numel), dtype=torch.float32, device=like.device)
             self._stash = torch.zeros((numel,), dtype=torch.float32, device=like.device)
         return self._ring, self._stash
+
+    def _coeff_table(self):
+        """Host copy of alphas_cumprod (fp32, as the reference's torch scalars) and final_alpha_cumprod, refreshed when
+        the caller overwrites the schedule attributes (SNR shift, src/trainers/reconstruct.py:106-117)."""
+        ac = self.alphas_cumprod
+        fa = self.final_alpha_cumprod
+        key = (ac.data_ptr(), ac._version, fa.data_ptr(), fa._version)
+        if self._coeff_key != key:
+            self._ac_host = ac.detach().float().cpu().numpy().astype(np.float32)
+            self._fa_host = np.float32(float(fa.detach().float().cpu()))
+            self._coeff_key = key
+            self._chain_cache.clear()
+        return self._ac_host, self._fa_host
 
     def _plan_step(self, timestep: int) -> _lib.PlmsStep:
         """Advance the host-side PLMS state by one step and return the device coefficients (step_plms + _get_prev_sample)."""
@@ -170,25 +185,47 @@ class PNDMScheduler(Scheduler):
         newest_first = list(reversed(before))
         for i in range(3):
             st.slot[i] = newest_first[i] if i < len(newest_first) else 0
-        # _get_prev_sample, in fp32 like the reference's torch scalars
-        ac = self.alphas_cumprod.detach().float().cpu()
+        # _get_prev_sample in fp32 scalars, like the reference's 0-d torch tensors (numpy float32 arithmetic, no
+        # per-step tensor traffic)
+        ac, fa = self._coeff_table()
         a_t = ac[timestep]
-        a_prev = ac[prev_timestep] if prev_timestep >= 0 else self.final_alpha_cumprod.detach().float().cpu()
-        b_t = 1 - a_t
-        b_prev = 1 - a_prev
+        a_prev = ac[prev_timestep] if prev_timestep >= 0 else fa
+        one = np.float32(1.0)
+        b_t = one - a_t
+        b_prev = one - a_prev
         if self.prediction_type == "v_prediction":
-            st.vA = float(a_t ** 0.5)
-            st.vB = float(b_t ** 0.5)
+            st.vA = float(np.sqrt(a_t))
+            st.vB = float(np.sqrt(b_t))
         else:
             st.vA, st.vB = 1.0, 0.0
-        st.A = float((a_prev / a_t) ** 0.5)
-        denom = a_t * b_prev ** 0.5 + (a_t * b_t * a_prev) ** 0.5
+        st.A = float(np.sqrt(a_prev / a_t))
+        denom = a_t * np.sqrt(b_prev) + np.sqrt(a_t * b_t * a_prev)
         st.Bc = float((a_prev - a_t) / denom)
         # state advance
         if st.push:
             self._hist = before + [st.slot_new]
         self.counter += 1
         return st
+
+    def plan_chain(self, timesteps: Sequence[int]):
+        """Coefficients of a whole chain (ctypes array of PlmsStep), advancing the host state. The result depends only
+        on (timesteps, counter in {0, 1, >=2}, ring occupancy, schedule): cached, so the 25-100 chains of every batch
+        after the first cost one dictionary lookup instead of per-step Python."""
+        self._coeff_table()
+        ts = tuple(int(t) for t in timesteps)
+        key = (ts, min(self.counter, 2), tuple(self._hist), self.num_inference_steps, self.prediction_type)
+        hit = self._chain_cache.get(key)
+        if hit is not None:
+            steps, hist_after = hit
+            self.counter += len(ts)
+            self._hist = list(hist_after)
+            return steps
+        steps = (_lib.PlmsStep * max(len(ts), 1))()
+        for i, t in enumerate(ts):
+            steps[i] = self._plan_step(t)
+        if len(self._chain_cache) < 4096:
+            self._chain_cache[key] = (steps, tuple(self._hist))
+        return steps
 
     def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor) -> Tuple[torch.Tensor, None]:
         if not sample.is_cuda:
@@ -213,8 +250,6 @@ class PNDMScheduler(Scheduler):
             raise ValueError("run_chain needs a contiguous fp32 sample")
         ring, stash = self._buffers(sample)
         ts = [int(t) for t in timesteps]
-        steps = (_lib.PlmsStep * len(ts))()
-        for i, t in enumerate(ts):
-            steps[i] = self._plan_step(t)
+        steps = self.plan_chain(ts)
         model.run_chain(sample, ts, steps, ring, stash)
         return sample

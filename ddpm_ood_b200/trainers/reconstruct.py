@@ -19,7 +19,7 @@ import torch.distributed as dist
 
 from ..data import get_training_data_loader
 from ..losses import PerceptualLoss
-from ..reconstruction import BatchReconstructor, ReconConfig
+from ..reconstruction import BatchReconstructor, ReconConfig, partition_t_starts
 from ..simplex_noise import generate_simplex_noise
 from .base import BaseTrainer
 
@@ -38,6 +38,19 @@ def gather_scores(scores: torch.Tensor, names, device):
     return gathered.cpu(), [n for sub in all_names for n in sub]
 
 
+def gather_t_sharded(full: torch.Tensor, owner: torch.Tensor, device):
+    """t-start sharding (second bullet): every rank holds the same [n_t, n_images, 2] score tensor with
+    only the rows of ITS t-starts filled. One all-gather of that tensor (NCCL / gloo), then row i is taken from rank
+    owner[i]. Returns the complete tensor on every rank."""
+    world = dist.get_world_size()
+    local = full.to(device).contiguous()
+    gathered = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=device)
+    dist.all_gather_into_tensor(gathered, local)  # concatenated along dim 0 in rank order
+    gathered = gathered.view((world,) + tuple(local.shape))
+    idx = owner.to(device=device, dtype=torch.long).view(1, -1, 1, 1).expand(1, *local.shape)
+    return torch.gather(gathered, 0, idx)[0]
+
+
 class Reconstruct(BaseTrainer):
     def __init__(self, args):
         super().__init__(args)
@@ -53,6 +66,8 @@ class Reconstruct(BaseTrainer):
     def _loader(self, args, ids, first_n, **flip):
         rank = dist.get_rank() if dist.is_initialized() else None
         world = dist.get_world_size() if dist.is_initialized() else None
+        if getattr(args, "shard", "images") == "t_starts":
+            rank = world = None  # every rank sees every image and takes a share of the t-start grid instead
         return get_training_data_loader(
             batch_size=args.batch_size, training_ids=ids, validation_ids=ids, augmentation=bool(args.augmentation),
             only_val=True, num_workers=args.num_workers, num_val_workers=args.num_workers,
@@ -104,6 +119,8 @@ class Reconstruct(BaseTrainer):
             print(f"{dataset_name}")
         engine = self._engine()
         self.model.eval()
+        if dist.is_initialized() and getattr(self.args, "shard", "images") == "t_starts":
+            return self._get_scores_t_sharded(engine, loader, dataset_name, inference_skip_factor)
         names, ts, pds, mses = [], [], [], []
         for batch in loader:
             t1 = time.time()
@@ -136,6 +153,50 @@ class Reconstruct(BaseTrainer):
              "perceptual_difference": float(scores[r, 1]), "mse": float(scores[r, 2])}
             for r in range(scores.shape[0])
         ]
+
+    def _get_scores_t_sharded(self, engine, loader, dataset_name, inference_skip_factor):
+        """`--shard t_starts`: rank r runs its share of the t-start grid (balanced by chain length) on EVERY image, so a
+        dataset too small to fill 8 GPUs by images still does; scores meet in one all-gather of the [n_t, n, 2] tensor.
+        Exact because plms_state='reset' gives every chain its own PLMS history (refused otherwise)."""
+        rank, world = dist.get_rank(), dist.get_world_size()
+        sched = engine.make_scheduler()
+        timesteps = sched.timesteps
+        grid = reversed(timesteps)[1::inference_skip_factor]
+        lens = [int((timesteps <= t).sum()) for t in grid]
+        parts = partition_t_starts(lens, world)
+        owner = torch.empty(len(grid), dtype=torch.long)
+        for r, idxs in enumerate(parts):
+            owner[idxs] = r
+        fulls, names, sizes = [], [], []
+        for batch in loader:
+            t1 = time.time()
+            res = engine.score_batch(batch["image"], inference_skip_factor, noise_fn=self._simplex_fn(batch["image"]),
+                                     t_indices=parts[rank])
+            B = res["mse"].shape[1]
+            full = torch.full((len(grid), B, 2), float("nan"), dtype=torch.float32, device=self.device)
+            if parts[rank]:
+                sel = torch.tensor(parts[rank], dtype=torch.long, device=self.device)
+                full[sel] = torch.stack([res["perceptual_difference"], res["mse"]], dim=-1)
+            fulls.append(full)
+            sizes.append(B)
+            names.append([Path(f).stem.replace(".nii", "").replace(".gz", "")
+                          for f in batch["image_meta_dict"]["filename_or_obj"]])
+            print(f"{rank}: Took {time.time()-t1}s for {len(parts[rank])} of {len(grid)} t-starts, batch size {B}")
+        rows = []
+        if fulls:
+            scores = gather_t_sharded(torch.cat(fulls, dim=1), owner, self.device).cpu().double()
+            off = 0
+            for stems, B in zip(names, sizes):  # the reference's row order: per batch, t-start outer, item inner
+                for i in range(len(grid)):
+                    for b in range(B):
+                        rows.append({"filename": stems[b], "type": dataset_name, "t": int(grid[i]),
+                                     "perceptual_difference": float(scores[i, off + b, 0]),
+                                     "mse": float(scores[i, off + b, 1])})
+                off += B
+        local_rank = int(os.environ["LOCAL_RANK"])
+        if local_rank != 0:
+            sys.stdout = sys.stderr = open(os.devnull, "w")
+        return rows
 
     def reconstruct(self, args):
         if bool(args.run_val):

@@ -27,7 +27,9 @@ extern "C" {
 
 /* ------------------------------------------------------------------------------------------------ general */
 DDPM_API const char* ddpm_last_error(void);
-/* ABI version, bumped on any signature change. */
+/* ABI version, bumped on any signature or struct-layout change; the Python binding refuses a library whose version or
+ * struct sizes (ddpm_struct_sizes) differ from its own. */
+#define DDPM_ABI_VERSION 5
 DDPM_API int ddpm_abi_version(void);
 
 /* ------------------------------------------------------------------------------------------------ building block

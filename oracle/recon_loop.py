@@ -76,7 +76,9 @@ def reconstruct_batch(
                 x, _ = sched.step(eps, step, x)
             x = x / cfg.b_scale
             x = x.clamp(0, 1)
-            if cfg.spatial_dimension == 2:
+            if perceptual is None:  # latent-only checks (a 128-channel latent is not an LPIPS input): MSE only
+                pd = torch.full((B,), float("nan"))
+            elif cfg.spatial_dimension == 2:
                 if images_original.shape[3] == 28:
                     pd = perceptual(F.pad(images_original, (2, 2, 2, 2)), F.pad(x, (2, 2, 2, 2)))
                 else:

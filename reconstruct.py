@@ -1,11 +1,14 @@
 """Reconstruction CLI: the flag surface of the reference's `reconstruct.py` (same names, types and defaults, so existing
 launch scripts work unchanged) driving the B200 engine.
 
-Two extra, optional flags that the reference does not have:
+Three extra, optional flags that the reference does not have:
   --plms_state carry|reset            carry (default) keeps the PNDM scheduler state across t-starts of a batch, exactly
                                       like the reference; reset gives every t-start chain a fresh PLMS history.
   --honour_num_inference_steps 0|1    the reference parses --num_inference_steps but always uses 100
                                       (src/trainers/reconstruct.py:118); 1 makes the flag effective.
+  --shard images|t_starts             under torchrun, what the ranks divide: the images (default, what the reference
+                                      does) or the t-start grid (every rank runs its share of the grid on every image;
+                                      exact only with --plms_state reset, refused otherwise).
 """
 import argparse
 import ast
@@ -53,6 +56,9 @@ FLAGS = [
     # extensions (see module docstring)
     ("--plms_state", dict(default="carry", choices=["carry", "reset"], help="PLMS history across t-starts.")),
     ("--honour_num_inference_steps", dict(type=int, default=0, help="Make --num_inference_steps effective.")),
+    ("--shard", dict(default="images", choices=["images", "t_starts"],
+                     help="Under torchrun: split images over ranks (the reference) or the t-start grid (needs "
+                          "--plms_state reset).")),
 ]
 
 

@@ -27,7 +27,8 @@ def _dataset(tmp_path, name, n, seed):
     return ids, paths
 
 
-def test_cli_writes_the_reference_csv_contract(tmp_path):
+def test_cli_writes_the_reference_csv_contract(tmp_path, monkeypatch):
+    monkeypatch.setenv("DDPM_LPIPS_ALLOW_SYNTHETIC", "1")  # no lpips package / weights on the box: explicit opt-in
     sys.path.insert(0, str(ROOT))
     import reconstruct as cli
     from ddpm_ood_b200.data import SimpleLoader
@@ -83,7 +84,38 @@ def test_cli_writes_the_reference_csv_contract(tmp_path):
     assert np.allclose(got, want, rtol=1e-5, atol=0)
 
 
-def test_cli_simplex_noise_mode(tmp_path):
+def test_cli_refuses_made_up_lpips_weights(tmp_path, monkeypatch):
+    """Without real LPIPS weights (and without the explicit opt-in) the production path raises instead of writing
+    meaningless perceptual_difference columns into a reference-shaped CSV."""
+    try:
+        import lpips  # noqa: F401
+        pytest.skip("lpips is installed: real weights load")
+    except ImportError:
+        pass
+    monkeypatch.delenv("DDPM_LPIPS_ALLOW_SYNTHETIC", raising=False)
+    monkeypatch.delenv("DDPM_LPIPS_STATE_DICT", raising=False)
+    sys.path.insert(0, str(ROOT))
+    import reconstruct as cli
+    from ddpm_ood_b200._lib import DdpmError
+    from ddpm_ood_b200.trainers import Reconstruct
+    from oracle import unet as ou
+
+    val_ids, _ = _dataset(tmp_path, "val", 2, 0)
+    run = tmp_path / "runs" / "m"
+    run.mkdir(parents=True)
+    torch.save({"epoch": 1, "global_step": 1, "best_loss": 0.5,
+                "model_state_dict": ou.randomize_(ou.make_small(2, 1), seed=5).state_dict()}, run / "checkpoint.pth")
+    args = cli.parse_args(["--output_dir", str(tmp_path / "runs"), "--model_name", "m", "--validation_ids", str(val_ids),
+                           "--in_ids", str(val_ids), "--out_ids", str(val_ids), "--run_in", "0", "--run_out", "0",
+                           "--is_grayscale", "1", "--batch_size", "2", "--inference_skip_factor", "64"])
+    recon = Reconstruct(args)
+    with pytest.raises(DdpmError, match="LPIPS weights not found"):
+        recon.reconstruct(args)
+    assert not (run / "ood" / "results_val.csv").exists()
+
+
+def test_cli_simplex_noise_mode(tmp_path, monkeypatch):
+    monkeypatch.setenv("DDPM_LPIPS_ALLOW_SYNTHETIC", "1")
     """--simplex_noise=1 (reference reconstruct.py:83-88, trainers/reconstruct.py:133-139): the CLI's scores are the
     engine's with generate_simplex_noise as the noise source under the same numpy seed."""
     sys.path.insert(0, str(ROOT))
