@@ -32,8 +32,24 @@ if str(ROOT) not in sys.path:
 
 METRIC = "reconstructions/sec (image x t-start)"
 UNIT = "reconstructions/s"
-CHANNELS, SIZE = 1, 32
 NUM_CHANNELS, ATTN, NRES = (128, 256, 256), (False, False, True), (1, 1, 1)
+
+# BASELINE.json configs as bench workloads. `fmnist` (configs[1]) is the default and the one the metric is quoted on; the
+# others are secondary lines (python bench.py --config NAME). Grids that would take many minutes per step are run on a
+# stated sample of the grid with the same mean chain length (`sample_skip`).
+WORKLOADS = {
+    # name: spatial_dims, channels, spatial size, inference steps, skip factor of the config, skip actually run, batch
+    "fmnist": dict(sd=2, ch=1, size=(32, 32), steps=100, skip=4, run_skip=4, batch=1184,
+                   label="FashionMNIST-shaped 1x32x32 (BASELINE configs[1])"),
+    "fmnist_b8": dict(sd=2, ch=1, size=(32, 32), steps=100, skip=16, run_skip=16, batch=8,
+                      label="FashionMNIST-shaped 1x32x32, batch 8, skip 16 (BASELINE configs[0], the CPU reference's case)"),
+    "cifar": dict(sd=2, ch=3, size=(32, 32), steps=1000, skip=4, run_skip=40, batch=296,
+                  label="CIFAR10-shaped 3x32x32, 1000 inference steps honoured (BASELINE configs[2])"),
+    "celeba64": dict(sd=2, ch=3, size=(64, 64), steps=100, skip=1, run_skip=4, batch=296,
+                     label="CelebA-shaped 3x64x64 (BASELINE configs[3])"),
+    "brats_latent": dict(sd=3, ch=128, size=(8, 8, 8), steps=100, skip=4, run_skip=4, batch=592,
+                         label="BraTS LDM latent 128x8x8x8, 3-D UNet (BASELINE configs[4], latent side)"),
+}
 
 
 def parse():
@@ -42,28 +58,50 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=1184,
-                    help="images per rank per step (16 per CTA pair on 148 SMs; the reference CLI default is 256)")
-    ap.add_argument("--skip", type=int, default=4, help="inference_skip_factor")
-    ap.add_argument("--plms_state", default="carry", choices=["carry", "reset"])
+    ap.add_argument("--config", default="fmnist", choices=sorted(WORKLOADS), help="BASELINE.json workload")
+    ap.add_argument("--batch", type=int, default=None,
+                    help="images per rank per step (default per workload; fmnist: 1184 = 16 per CTA pair on 148 SMs; "
+                         "the reference CLI default is 256)")
+    ap.add_argument("--skip", type=int, default=None, help="inference_skip_factor actually run (default per workload)")
+    ap.add_argument("--plms_state", default=None, choices=["carry", "reset"])
+    ap.add_argument("--shard", default="images", choices=["images", "t_starts"],
+                    help="N > 1: images = every rank its own batch (weak scaling, what the reference shards); t_starts = "
+                         "ONE global batch, the t-start grid split over ranks (strong scaling, needs plms_state=reset)")
     ap.add_argument("--profile_every", type=int, default=50, help="event-profile every n-th UNet forward (0 = off)")
     ap.add_argument("--no_cpu_baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    w = WORKLOADS[a.config]
+    if a.batch is None:
+        a.batch = w["batch"]
+    if a.skip is None:
+        a.skip = w["run_skip"]
+    if a.plms_state is None:
+        a.plms_state = "reset" if a.shard == "t_starts" else "carry"
+    if a.shard == "t_starts" and a.plms_state != "reset":
+        ap.error("--shard t_starts needs --plms_state reset (carry couples every chain to its predecessor)")
+    return a
 
 
 def workload_name(args) -> str:
-    return (f"FashionMNIST-shaped 1x{SIZE}x{SIZE}, small UNet, 100 steps, skip_factor={args.skip} "
-            f"({len(_chains(args.skip))} t-starts), batch={args.batch}/GPU, plms_state={args.plms_state}")
+    w = WORKLOADS[args.config]
+    n_t = len(_chains(args))
+    grid = f"skip_factor={args.skip} ({n_t} t-starts)"
+    if args.skip != w["skip"]:
+        grid += (f" - a sample of the config's skip_factor={w['skip']} grid "
+                 f"({len(_chains(args, w['skip']))} t-starts) with the same mean chain length")
+    per = "/GPU" if args.shard == "images" else " global (t-starts sharded over ranks)"
+    return (f"{w['label']}, small UNet, {w['steps']} steps, {grid}, batch={args.batch}{per}, "
+            f"plms_state={args.plms_state}")
 
 
-def _chains(skip):
+def _chains(args, skip=None):
     from ddpm_ood_b200.synthetic import chain_lengths
 
-    return chain_lengths(100, skip)
+    return chain_lengths(WORKLOADS[args.config]["steps"], skip if skip is not None else args.skip)
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle)
-def _cpu_sample(budget_s: float, n_runs: int):
+def _cpu_sample(args, budget_s: float, n_runs: int):
     """Time the oracle loop (fp32 PyTorch on all host cores) on a bounded sample of the workload.
     Returns (recon_per_s_per_run list, cores, sample description). The sample keeps the workload's mean of 50 UNet
     evaluations per reconstruction: t-starts {10,330,650,970} (skip 32) or the single t-start 490."""
@@ -73,12 +111,15 @@ def _cpu_sample(budget_s: float, n_runs: int):
     from oracle.lpips import PerceptualLoss as OraclePL
     from oracle.recon_loop import LoopConfig, reconstruct_batch
 
+    w = WORKLOADS[args.config]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    model = ou.randomize_(ou.make_small(2, CHANNELS), seed=0).eval()
-    pl = OraclePL(dimensions=2, include_pixel_loss=False, is_fake_3d=False, lpips_normalize=True, spatial=False)
+    model = ou.randomize_(ou.make_small(w["sd"], w["ch"]), seed=0).eval()
+    # a 128-channel latent is not an LPIPS input: the latent workload scores MSE only (both arms)
+    pl = None if w["ch"] > 3 else OraclePL(dimensions=w["sd"], include_pixel_loss=False, is_fake_3d=(w["sd"] == 3),
+                                           lpips_normalize=True, spatial=False)
     B = int(os.environ.get("DDPM_REF_SAMPLE_BATCH", "8"))
-    x0 = torch.rand((B, CHANNELS, SIZE, SIZE), generator=torch.Generator().manual_seed(0))
+    x0 = torch.rand((B, w["ch"]) + tuple(w["size"]), generator=torch.Generator().manual_seed(0))
     g = torch.Generator().manual_seed(1)
     with torch.no_grad():
         ts = torch.full((B,), 500, dtype=torch.long)
@@ -87,11 +128,24 @@ def _cpu_sample(budget_s: float, n_runs: int):
         for _ in range(3):
             model(x0, ts)
         fwd = (time.perf_counter() - t0) / 3
-    if fwd * 200 * n_runs <= budget_s:
-        starts, desc = [10, 330, 650, 970], "t-starts {10,330,650,970}"
+    ratio = 1000 // w["steps"]
+    four = [ratio * 1, ratio * 33 * (w["steps"] // 100), ratio * 65 * (w["steps"] // 100), ratio * 97 * (w["steps"] // 100)]
+    one = [ratio * 49 * (w["steps"] // 100)]
+    evals4 = sum(t // ratio + 1 for t in four)
+    if w["batch"] <= 8:
+        # the CPU reference's own case (BASELINE configs[0]): identical batch and the WHOLE grid on both arms
+        B = w["batch"]
+        x0 = x0[:B]
+        from oracle.pndm import PNDMScheduler as _S, t_start_grid as _grid
+        _s = _S(num_train_timesteps=1000, skip_prk_steps=True)
+        _s.set_timesteps(w["steps"])
+        starts = [int(t) for t in _grid(_s.timesteps, w["run_skip"])]
+    elif fwd * evals4 * n_runs <= budget_s:
+        starts = four
     else:
-        starts, desc = [490], "t-start {490}"
-    cfg = LoopConfig(inference_skip_factor=1)
+        starts = one
+    desc = "t-starts {" + ",".join(str(t) for t in starts) + "}"
+    cfg = LoopConfig(inference_skip_factor=1, num_inference_steps=w["steps"], spatial_dimension=w["sd"])
     rates = []
     for _ in range(n_runs):
         noise = [torch.randn(x0.shape, generator=g) for _ in starts]
@@ -99,13 +153,10 @@ def _cpu_sample(budget_s: float, n_runs: int):
         reconstruct_batch(model, pl, x0, lambda i, t: noise[i], cfg, t_starts=starts)
         dt = time.perf_counter() - t0
         rates.append(B * len(starts) / dt)
-    sample = (f"oracle fp32 loop, batch {B}, {desc} of the 100-step grid ({sum(c for c in _chain_for(starts))} UNet "
-              f"evaluations, mean 50 per reconstruction), torch.set_num_threads({cores})")
-    return rates, cores, sample
-
-
-def _chain_for(starts):
-    return [t // 10 + 1 for t in starts]
+    evals = sum(t // ratio + 1 for t in starts)
+    sample = (f"oracle fp32 loop, batch {B}, {desc} of the {w['steps']}-step grid ({evals} UNet evaluations, mean "
+              f"{evals / len(starts):.0f} per reconstruction), torch.set_num_threads({cores})")
+    return rates, cores, sample, B * len(starts)
 
 
 def run_reference(args):
@@ -113,11 +164,9 @@ def run_reference(args):
     if rank != 0:
         return
     n_runs = args.warmup + args.steps
-    rates, cores, sample = _cpu_sample(budget_s=240.0, n_runs=n_runs)
+    rates, cores, sample, per_step = _cpu_sample(args, budget_s=240.0, n_runs=n_runs)
     timed = rates[args.warmup:]
     value = len(timed) / sum(1.0 / r for r in timed)  # total reconstructions / total time over the K timed steps
-    B = int(os.environ.get("DDPM_REF_SAMPLE_BATCH", "8"))
-    per_step = B * (4 if "330" in sample else 1)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * per_step / value, "higher_is_better": True, "scaling": "weak",
@@ -128,6 +177,20 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def _traffic(args):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel family, from the committed ncu
+    --set full capture of THIS command line (profiles/traffic.json names the capture); null when no capture matches the
+    workload and batch being run - it is a measured number, never scaled or assumed."""
+    path = ROOT / "profiles" / "traffic.json"
+    if path.exists():
+        for rec in json.loads(path.read_text()):
+            if rec.get("config") == args.config and rec.get("batch") == args.batch:
+                return {"traffic": rec["bytes_per_launch"],
+                        "traffic_unit": f"bytes/launch, mean over the conv launches of one forward ({rec['source']})",
+                        "algorithmic_bytes_per_launch": rec.get("algorithmic_bytes_per_launch")}
+    return {"traffic": None, "traffic_unit": "no ncu capture committed for this workload/batch"}
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -206,29 +269,53 @@ def run_ours(args):
         dist.init_process_group(backend="nccl", init_method="env://", device_id=dev)
     _lib.lib()  # fail loudly if the extension is missing
 
-    model = DiffusionModelUNet(spatial_dims=2, in_channels=CHANNELS, out_channels=CHANNELS, num_channels=NUM_CHANNELS,
+    from ddpm_ood_b200.reconstruction import partition_t_starts
+    from ddpm_ood_b200.trainers.reconstruct import gather_t_sharded
+
+    w = WORKLOADS[args.config]
+    model = DiffusionModelUNet(spatial_dims=w["sd"], in_channels=w["ch"], out_channels=w["ch"], num_channels=NUM_CHANNELS,
                                attention_levels=ATTN, num_res_blocks=1, num_head_channels=256)
     randomize_(model, seed=0)
     model = model.to(dev).eval()
     import warnings
 
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        pl = PerceptualLoss(dimensions=2, include_pixel_loss=False, is_fake_3d=False, lpips_normalize=True,
-                            spatial=False, allow_synthetic_weights=True).to(dev)
+    pl = None  # a 128-channel latent is not an LPIPS input: the latent workload scores MSE only
+    if w["ch"] <= 3:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            pl = PerceptualLoss(dimensions=w["sd"], include_pixel_loss=False, is_fake_3d=(w["sd"] == 3),
+                                lpips_normalize=True, spatial=False, allow_synthetic_weights=True).to(dev)
     cfg = ReconConfig(beta_schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0195,
-                      plms_state=args.plms_state)
+                      plms_state=args.plms_state, num_inference_steps=w["steps"], spatial_dimension=w["sd"])
     eng = BatchReconstructor(model, pl, cfg, dev)
     B = args.batch
-    chains = _chains(args.skip)
+    chains = _chains(args)
     n_t = len(chains)
-    recon_per_step = B * n_t
-    g = torch.Generator().manual_seed(1234 + rank)
-    host_images = torch.rand((B, CHANNELS, SIZE, SIZE), generator=g).pin_memory()
+    t_shard = world > 1 and args.shard == "t_starts"
+    # images sharded (weak scaling): every rank its own batch; t-starts sharded (strong): ONE global batch of B images
+    recon_per_step = B * n_t * (1 if t_shard else world)
+    g = torch.Generator().manual_seed(1234 + (0 if t_shard else rank))
+    host_images = torch.rand((B, w["ch"]) + tuple(w["size"]), generator=g).pin_memory()
     dev_images = host_images.to(dev)
-    gathered = torch.empty((world, n_t, B, 2), dtype=torch.float32, device=dev) if world > 1 else None
+    gathered = torch.empty((world * n_t, B, 2), dtype=torch.float32, device=dev) if world > 1 and not t_shard else None
+    parts = partition_t_starts(chains, world) if t_shard else None
+    owner = None
+    if t_shard:
+        owner = torch.empty(n_t, dtype=torch.long)
+        for r, idxs in enumerate(parts):
+            owner[idxs] = r
+        mine = torch.tensor(parts[rank], dtype=torch.long, device=dev)
+        my_chains = [chains[i] for i in parts[rank]]
+    else:
+        my_chains = chains
 
     def step(images):
+        if t_shard:
+            res = eng.score_batch(images, args.skip, t_indices=parts[rank])
+            full = torch.full((n_t, B, 2), float("nan"), dtype=torch.float32, device=dev)
+            if parts[rank]:
+                full[mine] = torch.stack([res["perceptual_difference"], res["mse"]], dim=-1)
+            return gather_t_sharded(full, owner, dev)  # one all-gather of the [n_t, B, 2] score tensor
         res = eng.score_batch(images, args.skip)
         scores = torch.stack([res["perceptual_difference"], res["mse"]], dim=-1)  # [n_t, B, 2] on device
         if world > 1:
@@ -246,10 +333,16 @@ def run_ours(args):
     fence()
 
     def launches():
-        return model.launch_count() + pl.perceptual_function.launch_count()
+        return model.launch_count() + (pl.perceptual_function.launch_count() if pl is not None else 0)
 
     # ---- timed region 1: inputs resident in HBM
-    if args.profile_every > 0:
+    # Per-op CUDA-event profiling samples every n-th forward INSIDE the timed region - except for launch-bound batches,
+    # where the engine replays each chain as one CUDA graph (no room for events): those get one extra profiled step
+    # after the timed regions instead.
+    import math
+
+    graph_mode = B * math.prod(w["size"]) <= 64 * 1024
+    if args.profile_every > 0 and not graph_mode:
         model.set_profile(args.profile_every)
         model.read_profile(reset=True)
     sampler = ClockSampler(local_rank)
@@ -264,8 +357,8 @@ def run_ours(args):
     e1.record()
     fence()
     ms = e0.elapsed_time(e1)
-    n_launch = launches() - l0 + args.steps * n_t * 2  # + add_noise and clamp_mse per t-start
-    prof = model.read_profile(reset=True) if args.profile_every > 0 else {}
+    n_launch = launches() - l0 + args.steps * len(my_chains) * 2  # + add_noise and clamp_mse per t-start
+    prof = model.read_profile(reset=True) if args.profile_every > 0 and not graph_mode else {}
     model.set_profile(0)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -280,7 +373,17 @@ def run_ours(args):
     e3.record()
     fence()
     ms_e2e = e2.elapsed_time(e3)
-    assert host_scores is not None and bool(torch.isfinite(host_scores).all())
+    assert host_scores is not None
+    finite = host_scores[..., 1] if pl is None else host_scores  # latent workload: the LPIPS column is NaN by design
+    assert bool(torch.isfinite(finite).all())
+
+    if args.profile_every > 0 and graph_mode:
+        model.set_profile(5)
+        model.read_profile(reset=True)
+        step(dev_images)
+        fence()
+        prof = model.read_profile(reset=True)
+        model.set_profile(0)
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -291,7 +394,7 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    total = recon_per_step * world * args.steps
+    total = recon_per_step * args.steps
     value = total / (ms / 1000.0)
     e2e_value = total / (ms_e2e / 1000.0)
 
@@ -313,9 +416,7 @@ def run_ours(args):
         roofline = {"kernel": "conv_halo_kernel + conv_gemm_2cta_kernel (tcgen05 implicit-GEMM convolutions)",
                     "bound": "tensor", "achieved": achieved, "peak": peak_tf,
                     "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    # dram__bytes_read.sum + dram__bytes_write.sum per conv_halo launch, mean of the 22 launches of one
-                    # forward at batch 256 (profiles/r01_halo_ncu_full_s3.md)
-                    "traffic": 83.4e6 * args.batch / 256.0, "traffic_unit": "bytes/launch (ncu at batch 256, scaled by batch; conv_halo)",
+                    **_traffic(args),
                     "peak_source": peak_src,
                     "launches_timed": cg["launches"],
                     "avg_launch_us": 1000.0 * cg["ms"] / cg["launches"],
@@ -330,21 +431,26 @@ def run_ours(args):
                 d["GB/s"] = v["bytes"] / (v["ms"] / 1000.0) / 1e9
                 d["frac_hbm_peak"] = d["GB/s"] / peak_hbm
             breakdown[k] = d
-    flops_img = unet_flops_per_image(NUM_CHANNELS, ATTN, NRES, CHANNELS, CHANNELS, (SIZE, SIZE))
-    evals = sum(chains)
-    unet_tflops = flops_img * B * evals * world * args.steps / (ms / 1000.0) / 1e12
+    flops_img = unet_flops_per_image(NUM_CHANNELS, ATTN, NRES, w["ch"], w["ch"], tuple(w["size"]))
+    evals = sum(chains)  # whole grid; with t-starts sharded the ranks split these, with images sharded each rank runs all
+    unet_tflops = flops_img * B * evals * (1 if t_shard else world) * args.steps / (ms / 1000.0) / 1e12
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if t_shard else "weak",
+        "vs_baseline": None,
         "dtype": "fp16 operands, fp32 accumulate", "data": "synthetic",
-        "config": {"workload": workload_name(args), "global_batch": B * world, "t_starts": n_t,
-                   "unet_evals_per_step_per_gpu": evals, "parallelism": f"images sharded over {world} rank(s)",
-                   "l2": f"per-step working set (weights 35 MB + ~{6 * B / 1024:.1f} GB activations at batch {B}) exceeds the "
-                         "126 MB L2; no flush between steps"},
+        "config": {"workload": workload_name(args), "name": args.config, "global_batch": B * (1 if t_shard else world),
+                   "t_starts": n_t, "unet_evals_per_step_per_gpu": sum(my_chains),
+                   "unet_gflop_per_image_forward": flops_img / 1e9,
+                   "parallelism": (f"t-start grid sharded over {world} rank(s), balanced by chain length"
+                                   if t_shard else f"images sharded over {world} rank(s)"),
+                   "chain_launch": "one CUDA graph per t-start chain" if graph_mode else "per-kernel launches with programmatic dependent launch",
+                   "l2": f"per-step working set (weights 35+ MB + activations of {B} images) exceeds the 126 MB L2"
+                         if B >= 64 else "small batch: launch/latency bound by construction; no L2 flush between steps"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host_images.numel() * 4 * world,
-                "d2h_bytes_per_step": n_t * B * 2 * 4 * world, "ms_per_step": ms_e2e / args.steps},
+                "d2h_bytes_per_step": n_t * B * 2 * 4 * (1 if t_shard else world), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(n_launch),
         "roofline": roofline,
         "unet_fwd_ms": fwd_ms,
@@ -353,7 +459,7 @@ def run_ours(args):
         "breakdown": breakdown,
     }
     if world == 1 and not args.no_cpu_baseline:
-        rates, cores, sample = _cpu_sample(budget_s=25.0, n_runs=1)
+        rates, cores, sample, _ = _cpu_sample(args, budget_s=25.0, n_runs=1)
         line["cpu_baseline"] = {"value": rates[0], "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(line), flush=True)
     if world > 1:

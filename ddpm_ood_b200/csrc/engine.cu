@@ -155,7 +155,6 @@ AttnW UNet::make_attn(const std::string& prefix, int C, int head_channels) {
     a.bproj = arena_alloc<float>(C, false);
     a.wqkv = arena_alloc<__half>(static_cast<size_t>(3) * C * C, true);
     a.wproj = arena_alloc<__half>(static_cast<size_t>(C) * C, true);
-    a.wproj_id = attn_id_residual_mma_ ? arena_alloc<__half>(static_cast<size_t>(C) * 2 * C, true) : nullptr;
     add_copy(prefix + ".norm.weight", a.g, C);
     add_copy(prefix + ".norm.bias", a.b, C);
     const char* names[3] = {"to_q", "to_k", "to_v"};
@@ -187,7 +186,7 @@ int UNet::init() {
     if (const char* e = getenv("DDPM_CONV_HALO")) use_halo_ = atoi(e) != 0;  // A/B switch for tests
     if (const char* e = getenv("DDPM_HALO_GN_IN_KERNEL")) halo_gn_in_kernel_ = atoi(e) != 0;  // A/B switch for tests
     if (const char* e = getenv("DDPM_ID_RESIDUAL_MMA")) id_residual_mma_ = atoi(e) != 0;     // A/B switch for tests
-    if (const char* e = getenv("DDPM_ATTN_ID_RESIDUAL_MMA")) attn_id_residual_mma_ = atoi(e) != 0;
+    if (const char* e = getenv("DDPM_ATTN_FUSED")) use_attn_fused_ = atoi(e) != 0;            // A/B switch for tests
     use_halo_ = use_halo_ && fuse_gn_stats_ && c.spatial_dims == 2;
     in_gemm_ = (c.in_channels % 64 == 0);
     out_gemm_ = (c.out_channels % 128 == 0);
@@ -366,12 +365,6 @@ int UNet::finalize(cudaStream_t stream) {
             widen_with_identity_kernel<<<148 * 4, 256, 0, stream>>>(r.w2, r.cout, k2, r.w2_id);
         }
     };
-    auto widen_attn = [&](AttnW& a) {
-        if (a.wproj_id) widen_with_identity_kernel<<<148 * 4, 256, 0, stream>>>(a.wproj, a.C, a.C, a.wproj_id);
-    };
-    for (auto& L : down_) for (auto& a : L.attn) widen_attn(a);
-    for (auto& L : up_) for (auto& a : L.attn) widen_attn(a);
-    widen_attn(mid_attn_);
     for (auto& L : down_) for (auto& r : L.res) fold_and_widen(r);
     fold_and_widen(mid1_);
     fold_and_widen(mid2_);
@@ -456,6 +449,8 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             qkv = lay.take<__half>(max_qkv);
             plan.x_half = in_gemm_ ? lay.take<__half>(static_cast<size_t>(N) * D * H * W * c.in_channels) : nullptr;
             plan.y_half = out_gemm_ ? lay.take<__half>(static_cast<size_t>(N) * D * H * W * c.out_channels) : nullptr;
+            // fp32 eps of the PLMS corrector step (counter == 1), which is blended but never enters the history ring
+            plan.eps_tmp = out_gemm_ ? lay.take<float>(static_cast<size_t>(N) * D * H * W * c.out_channels) : nullptr;
         }
         int rc = 0;
         auto gn = [&](const Act& a, const Act* b, const float* g, const float* bt, __half* dst, bool silu) {
@@ -654,24 +649,29 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
                 const size_t ch = static_cast<size_t>(rows) * a.C;
                 if (ch > max_h) max_h = ch;
             }
-            // (measured slower than gn_apply + the im2col GEMM for the 3-N-tile q/k/v projection: off unless asked for)
-            static const bool fuse_attn_norm = getenv("DDPM_ATTN_NORM_FUSE") && atoi(getenv("DDPM_ATTN_NORM_FUSE")) != 0;
-            if (!measure && fuse_attn_norm && halo_ok(h, nullptr, 3 * a.C)) {
-                // AttentionBlock norm (no activation) applied inside the q/k/v projection's operand staging
-                float* ab = lay.take<float>(static_cast<size_t>(N) * a.C * 2);
-                finalize_op(h, nullptr, a.g, a.b, ab);
-                ConvProblem q{};
-                q.spatial_dims = sd; q.N = N; q.D = h.D; q.H = h.H; q.W = h.W; q.stride = 1;
-                q.n_seg = 1;
-                q.seg[0] = {h.p, a.C, 1};
-                q.weights = a.wqkv; q.w_rows = 3 * a.C; q.Cout = 3 * a.C; q.mode = EPI_STORE;
-                q.bias = a.bqkv; q.out = qkv;
-                q.gn_silu = 0;
-                halo_conv(q, ab, a.C, -1);
-            } else {
-                gn(h, nullptr, a.g, a.b, zA, false);
-                linear(zA, rows, a.C, a.wqkv, a.bqkv, 3 * a.C, nullptr, qkv);
+            // One launch per AttentionBlock (attn_block.cu): GroupNorm, q/k/v, softmax, P v, projection and the residual
+            // add on 128-row tiles that never leave the SM. C = 256 / one head / T <= 128 tokens (the `small` UNet at
+            // 32 x 32, 28 x 28 and 8 x 8 x 8 inputs); other shapes take the four-launch path below.
+            if (use_attn_fused_ && attn_block_supported(static_cast<int>(h.S()), a.C, a.heads, c.norm_num_groups)) {
+                const int parts = fuse_gn_stats_ ? attn_block_stats_parts(static_cast<int>(h.S())) : 0;
+                if (measure) return shape_act(a.C, h.D, h.H, h.W);
+                Act out{lay.take<__half>(static_cast<size_t>(rows) * a.C), a.C, h.D, h.H, h.W, take_stats(a.C, parts), parts};
+                Op op{};
+                op.type = Op::ATTN_BLOCK;
+                op.T = static_cast<int>(h.S()); op.C = a.C; op.heads = a.heads;
+                const double T = static_cast<double>(h.S());
+                op.flops = 2.0 * N * T * a.C * 4.0 * a.C + 4.0 * N * T * T * a.C;  // q, k, v, proj Linears + the two matmuls
+                if (!dry) {
+                    int r = attn_block_prepare(h.p, out.p, N, op.T, a.C, a.heads, c.norm_num_groups, c.norm_eps,
+                                               1.0f / sqrtf(static_cast<float>(a.C) / static_cast<float>(a.heads)), a.g, a.b,
+                                               a.wqkv, a.bqkv, a.wproj, a.bproj, out.stats, sms, &op.attn_block);
+                    if (r && !rc) rc = r;
+                }
+                plan.ops.push_back(op);
+                return out;
             }
+            gn(h, nullptr, a.g, a.b, zA, false);
+            linear(zA, rows, a.C, a.wqkv, a.bqkv, 3 * a.C, nullptr, qkv);
             if (!measure) {
                 Op op{};
                 op.type = Op::ATTN;
@@ -686,19 +686,7 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
                 plan.ops.push_back(op);
             }
             Act out = measure ? shape_act(a.C, h.D, h.H, h.W) : new_act(a.C, h.D, h.H, h.W);
-            if (a.wproj_id) {  // out = Wproj attn + I h: the residual as a K segment (no loads in the epilogue)
-                ConvProblem q{};
-                q.spatial_dims = sd; q.N = N; q.D = h.D; q.H = h.H; q.W = h.W; q.stride = 1;
-                q.n_seg = 2;
-                q.seg[0] = {hB, a.C, 1};
-                q.seg[1] = {h.p, a.C, 1};
-                q.weights = a.wproj_id; q.w_rows = a.C; q.Cout = a.C; q.mode = EPI_STORE;
-                q.bias = a.bproj; q.out = out.p; q.stats_out = out.stats;
-                gemm(q, -1);
-                if (!measure) plan.ops.back().flops *= 0.5;  // the identity block is not algorithmic work
-            } else {
-                conv1x1(h, hB, a.wproj, a.bproj, a.C, h.p, out);
-            }
+            conv1x1(h, hB, a.wproj, a.bproj, a.C, h.p, out);
             return out;
         };
 
@@ -773,26 +761,20 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
                     q.mode = EPI_STORE;
                     q.bias = L.samp.bias;
                     q.upsample2 = 1;
-                    // halo-tile kernel: all four phases' taps are views of one staged low-resolution tile
-                    // (measured at batch 256: 2150 vs 2195 reconstructions/s - with 4 taps per staged tile the items are
-                    // short and epilogue-bound, the im2col-tile kernel is faster; DDPM_HALO_UPCONV=1 switches it on)
-                    static const bool halo_upconv = getenv("DDPM_HALO_UPCONV") && atoi(getenv("DDPM_HALO_UPCONV")) != 0;
-                    const bool halo_up = halo_upconv && use_halo_ && conv_halo_supported(q);
+                    // (the halo-tile kernel can run this too - all four phases' taps are views of one staged low-resolution
+                    // tile - but measured slower in the chain: with 4 taps per staged tile its items are short and
+                    // epilogue-bound; the im2col-tile kernel runs it. tests/test_conv_gemm_gpu.py still covers that mode.)
                     Act o = shape_act(h.C, h.D * fd, h.H * 2, h.W * 2);
                     if (!measure) {
                         o = new_act(h.C, h.D * fd, h.H * 2, h.W * 2, false);
                         if (fuse_gn_stats_) {
-                            o.parts = (halo_up ? conv_halo_stats_parts(h.H, h.W) : conv_stats_parts(sd, h.D, h.H, h.W)) * (1 << sd);
+                            o.parts = conv_stats_parts(sd, h.D, h.H, h.W) * (1 << sd);
                             o.stats = take_stats(h.C, o.parts);
                         }
                     }
                     q.out = o.p;
                     q.stats_out = o.stats;
-                    if (halo_up) {
-                        if (!measure) halo_conv(q, nullptr, 0, -1);
-                    } else {
-                        gemm(q, -1);
-                    }
+                    gemm(q, -1);
                     h = o;
                 } else {
                     const size_t cnt = static_cast<size_t>(N) * (h.D * fd) * (h.H * 2) * (h.W * 2) * h.C;
@@ -954,6 +936,9 @@ int UNet::forward(const float* x, const long long* timesteps, int t_uniform, flo
                 }
                 rc = conv_halo_launch(op.halo, stream);
                 break;
+            case Op::ATTN_BLOCK:
+                rc = attn_block_launch(op.attn_block, stream);
+                break;
             case Op::ATTN:
                 rc = op.attn_tc ? attention_tc_launch(op.attn, stream)
                                 : attention_core(op.src0, op.dst, N, op.T, op.C, op.heads, op.scale, stream);
@@ -973,8 +958,9 @@ int UNet::forward(const float* x, const long long* timesteps, int t_uniform, flo
             case Op::CONV_OUT_GEMM: {
                 rc = conv_launch(op.conv, stream);
                 if (rc) break;
-                float* eps = out ? out : ring + static_cast<long long>(plms ? plms->slot_new : 0) * N * c.out_channels * S;
-                if (!out && plms && !plms->push) { set_error("unet: fused PLMS corrector step needs an eps buffer"); rc = 2; break; }
+                float* eps = out ? out
+                                 : (plms && !plms->push) ? plan.eps_tmp
+                                                         : ring + static_cast<long long>(plms ? plms->slot_new : 0) * N * c.out_channels * S;
                 dim3 grid(static_cast<unsigned>((S + 31) / 32), (c.out_channels + 31) / 32, N);
                 nhwc_half_to_nchw_kernel<<<grid, dim3(32, 8), 0, stream>>>(plan.y_half, eps, c.out_channels, S);
                 ++launches_;
@@ -1005,10 +991,14 @@ int UNet::run_chain(int n_steps, const int* timesteps, const PlmsStep* steps, fl
         }
         return 0;
     };
-    // Measured on B200 (batch 256): 2201 vs 2196 reconstructions/s - the chain is kernel-bound and programmatic
-    // dependent launch already hides the launch gaps, so replay is off unless DDPM_CHAIN_GRAPH=1 asks for it.
-    static const bool graph_env = getenv("DDPM_CHAIN_GRAPH") && atoi(getenv("DDPM_CHAIN_GRAPH")) != 0;
-    if (!graph_env || !use_chain_graph_ || profile_every_ > 0 || !chain_warm_ || n_steps < 1) {
+    // CUDA-graph replay of the chain pays when the chain is launch-bound: at batch 256 it measured flat (2201 vs 2196
+    // reconstructions/s - kernel-bound, programmatic dependent launch already hides the gaps), at batch 8 (BASELINE
+    // configs[0]) a forward's ~45 kernels are shorter than their launch work. Policy: replay when one forward covers at
+    // most kGraphPixels pixels; DDPM_CHAIN_GRAPH=0 / 1 forces it off / on.
+    constexpr long long kGraphPixels = 64 * 1024;
+    static const int graph_env = getenv("DDPM_CHAIN_GRAPH") ? (atoi(getenv("DDPM_CHAIN_GRAPH")) != 0 ? 1 : 0) : -1;
+    const bool want_graph = graph_env >= 0 ? graph_env == 1 : static_cast<long long>(N) * D * H * W <= kGraphPixels;
+    if (!want_graph || !use_chain_graph_ || profile_every_ > 0 || !chain_warm_ || n_steps < 1) {
         int rc = run_plain();
         if (!rc) chain_warm_ = true;
         return rc;
@@ -1075,7 +1065,8 @@ void UNet::harvest(Plan& plan) {
         cudaEventElapsedTime(&ms, plan.events[1 + i], plan.events[2 + i]);
         // the appended op types report under their families: GroupNorm (2) and tensor-core conv (3)
         const int t = op.type == Op::GN_FINALIZE ? static_cast<int>(Op::GN)
-                                                 : (op.type == Op::CONV_HALO ? static_cast<int>(Op::GEMM) : static_cast<int>(op.type));
+                      : op.type == Op::CONV_HALO ? static_cast<int>(Op::GEMM)
+                      : op.type == Op::ATTN_BLOCK ? static_cast<int>(Op::ATTN) : static_cast<int>(op.type);
         prof_.ms[t] += ms;
         prof_.flops[t] += op.flops;
         prof_.bytes[t] += op.bytes;

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "attention.cuh"
+#include "attn_block.cuh"
 #include "conv_gemm.cuh"
 #include "conv_halo.cuh"
 #include "kernels.cuh"
@@ -51,7 +52,6 @@ struct AttnW {
     __half* wqkv;  // [3C][C]
     float* bqkv;
     __half* wproj;  // [C][C]
-    __half* wproj_id;  // [C][2C] = wproj | I (residual as a K segment), or null
     float* bproj;
     std::string prefix;
 };
@@ -76,7 +76,7 @@ struct Op {
     // GN_FINALIZE / CONV_HALO (appended so the profile indices of the older types stay put): GroupNorm statistics ->
     // per-(image, channel) scale/shift table, consumed by the halo-tile conv that normalises its input on the fly
     enum Type { CONV_IN_SMALL, CONV_IN_GEMM, GN, GEMM, ATTN, UPSAMPLE, CONV_OUT_SMALL, CONV_OUT_GEMM, GN_FINALIZE,
-                CONV_HALO } type;
+                CONV_HALO, ATTN_BLOCK } type;
     // GN
     const __half *src0, *src1;
     int C0, C1;
@@ -98,6 +98,7 @@ struct Op {
     float scale;
     bool attn_tc;       // tcgen05 kernel (attention.cu) instead of the generic CUDA-core one
     AttnTcLaunch attn;
+    AttnBlockLaunch attn_block;  // ATTN_BLOCK: the whole AttentionBlock in one launch (reports under ATTN in the profile)
     // UPSAMPLE
     int D, H, W;
     // profiling: algorithmic FLOPs (2 per MAC, real rows only) for GEMM-type ops, algorithmic bytes otherwise
@@ -127,6 +128,7 @@ struct Plan {
     __half* z_out;    // input of conv_out (small path)
     __half* x_half;   // conv_in gemm path: input in NDHWC fp16
     __half* y_half;   // conv_out gemm path: output in NDHWC fp16
+    float* eps_tmp;   // conv_out gemm path: fp32 eps of a PLMS step that does not push into the history ring
 };
 
 class UNet {
@@ -189,7 +191,7 @@ class UNet {
     bool use_attn_tc_ = true;
     bool upconv_phases_ = true;  // nearest-x2 + conv as sub-pixel 2x2 convs (4/9 of the MACs, no upsampled tensor)
     bool fuse_gn_stats_ = true;  // GroupNorm statistics from the producers' epilogues (cpg % 4 == 0 required)
-    bool attn_id_residual_mma_ = false;  // same for the output projection of an AttentionBlock: measured no gain (K doubles)
+    bool use_attn_fused_ = true;  // one kernel per AttentionBlock (attn_block.cu) where its shape limits allow
     bool id_residual_mma_ = true;    // identity residuals of halo-kernel ResnetBlocks ride the MMA as an I-weighted K segment
     bool halo_gn_in_kernel_ = true;  // the halo conv derives scale/shift from producer statistics itself (no gn_finalize)
     bool use_halo_ = true;       // halo-tile conv kernel with GroupNorm+SiLU applied on the fly (2-D, images >= 16 x 8)

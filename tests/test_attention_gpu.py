@@ -30,3 +30,71 @@ def test_attention_matches_torch(n, t, heads, impl):
     err = (got - want).abs().max().item()
     # fp16 P and fp16 output: ~2^-11 relative on O(1) values
     assert err < 4e-3, (n, t, heads, impl, err)
+
+
+# ------------------------------------------------------------------------------------------------ fused AttentionBlock
+def _block_ref(h, n, t, gamma, beta, wqkv, bqkv, wproj, bproj, eps=1e-6):
+    """fp32 PyTorch AttentionBlock on the same fp16 inputs / weights (oracle/unet.py:AttentionBlock, one head)."""
+    c = h.shape[1]
+    x = h.float().reshape(n, t, c)
+    xn = torch.nn.functional.group_norm(x.transpose(1, 2), 32, gamma, beta, eps).transpose(1, 2)
+    qkv = xn @ wqkv.float().t() + bqkv
+    q, k, v = qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:]
+    a = torch.softmax(q @ k.transpose(-1, -2) / c ** 0.5, dim=-1)
+    o = (a @ v) @ wproj.float().t() + bproj
+    return (o + x).reshape(n * t, c)
+
+
+# (images, tokens): 8x8 maps, native FashionMNIST 7x7, 3-D latent 2x2x2, 4x4, one-image tiles, ragged image counts
+BLOCK_CASES = [(2, 64), (5, 64), (1, 64), (7, 49), (40, 8), (17, 8), (3, 16), (3, 128), (2, 100), (300, 64)]
+
+
+@pytest.mark.parametrize("n,t", BLOCK_CASES)
+def test_attention_block_matches_torch(n, t):
+    from ddpm_ood_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(n * 1000 + t)
+    c = 256
+    h = (torch.randn((n * t, c), generator=g, device="cuda") * 1.5 + 0.3).half()
+    gamma = 1.0 + 0.1 * torch.randn(c, generator=g, device="cuda")
+    beta = 0.1 * torch.randn(c, generator=g, device="cuda")
+    wqkv = (torch.randn((3 * c, c), generator=g, device="cuda") / c ** 0.5).half()
+    bqkv = 0.05 * torch.randn(3 * c, generator=g, device="cuda")
+    wproj = (torch.randn((c, c), generator=g, device="cuda") / c ** 0.5).half()
+    bproj = 0.05 * torch.randn(c, generator=g, device="cuda")
+    with_stats = ops.lib().ddpm_attention_block_stats_parts(t) > 0
+    res = ops.attention_block(h, n, t, gamma, beta, wqkv, bqkv, wproj, bproj, with_stats=with_stats)
+    got = (res[0] if with_stats else res).float()
+    want = _block_ref(h, n, t, gamma, beta, wqkv, bqkv, wproj, bproj)
+    err = (got - want).abs().max().item()
+    # fp16 normalised input, q/k/v, P and O against fp32 throughout: a few 2^-11 relative steps on O(1..5) values
+    assert err < 2e-2, (n, t, err)
+    rel = ((got - want).norm() / want.norm()).item()
+    assert rel < 2e-3, (n, t, rel)
+    if with_stats:
+        # GroupNorm partial statistics of the fp16 output: sum over parts == per-(image, quad) sums of `out`
+        st = res[1].sum(dim=1)  # [n, c/4, 2]
+        o = res[0].float().reshape(n, t, c // 4, 4)
+        assert torch.allclose(st[..., 0], o.sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
+        assert torch.allclose(st[..., 1], (o * o).sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("shape", [(3, 1, 32, 32), (2, 1, 28, 28), (2, 128, 8, 8, 8)])
+def test_unet_forward_fused_attention_equals_four_launch_path(shape, monkeypatch):
+    """The engine with the fused AttentionBlock kernel agrees with the round-1 path (gn_apply + q|k|v GEMM + attention core +
+    projection GEMM) on whole UNet forwards: same fp16 intermediates, summation orders differ."""
+    from ddpm_ood_b200.networks import DiffusionModelUNet
+    from ddpm_ood_b200.synthetic import randomize_
+
+    sd = len(shape) - 2
+    outs = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("DDPM_ATTN_FUSED", fused)
+        m = DiffusionModelUNet(spatial_dims=sd, in_channels=shape[1], out_channels=shape[1], num_channels=(128, 256, 256),
+                               attention_levels=(False, False, True), num_res_blocks=1, num_head_channels=256)
+        randomize_(m, seed=3)
+        m = m.to("cuda").eval()
+        x = torch.randn(shape, generator=torch.Generator().manual_seed(1)).cuda()
+        outs.append(m(x, torch.full((shape[0],), 500, device="cuda")).float().cpu())
+    rel = ((outs[0] - outs[1]).norm() / outs[1].norm()).item()
+    assert rel < 2e-3, rel
