@@ -63,6 +63,19 @@ class UNetConfig(C.Structure):
     ]
 
 
+class VqVaeConfig(C.Structure):
+    _fields_ = [
+        ("spatial_dims", C.c_int),
+        ("in_channels", C.c_int), ("out_channels", C.c_int),
+        ("num_levels", C.c_int),
+        ("num_res_layers", C.c_int),
+        ("num_channels", C.c_int * MAX_LEVELS),
+        ("num_res_channels", C.c_int * MAX_LEVELS),
+        ("num_embeddings", C.c_int), ("embedding_dim", C.c_int),
+        ("precise_encode", C.c_int),
+    ]
+
+
 class PlmsStep(C.Structure):
     _fields_ = [
         ("c", C.c_float * 4),
@@ -114,6 +127,10 @@ SIGNATURES = {
     "ddpm_pack_upconv_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ddpm_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                  C.c_void_p]),
+    "ddpm_attention_block": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                       C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
+    "ddpm_attention_block_stats_parts": (C.c_int, [C.c_int]),
     "ddpm_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong,
                                         C.c_longlong, C.c_void_p]),
     "ddpm_unet_create": (C.c_int, [C.POINTER(UNetConfig), C.POINTER(C.c_void_p)]),
@@ -145,6 +162,16 @@ SIGNATURES = {
                                      C.c_float, C.c_void_p]),
     "ddpm_simplex_noise": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_double, C.c_double, C.c_void_p]),
     "ddpm_scale_intensity": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
+    "ddpm_vqvae_create": (C.c_int, [C.POINTER(VqVaeConfig), C.POINTER(C.c_void_p)]),
+    "ddpm_vqvae_destroy": (None, [C.c_void_p]),
+    "ddpm_vqvae_set_param": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "ddpm_vqvae_finalize": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ddpm_vqvae_workspace_bytes": (C.c_longlong, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ddpm_vqvae_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_longlong, C.c_void_p]),
+    "ddpm_vqvae_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "ddpm_vqvae_launch_count": (C.c_longlong, [C.c_void_p]),
     "ddpm_lpips_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "ddpm_lpips_destroy": (None, [C.c_void_p]),
     "ddpm_lpips_set_param": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong, C.c_void_p]),
@@ -156,7 +183,7 @@ SIGNATURES = {
 }
 
 
-ABI_VERSION = 5  # must equal ddpm_abi_version() of the loaded library (include/ddpm_ood_b200.h DDPM_ABI_VERSION)
+ABI_VERSION = 6  # must equal ddpm_abi_version() of the loaded library (include/ddpm_ood_b200.h DDPM_ABI_VERSION)
 
 
 def _verify(L: C.CDLL) -> None:

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "attention.cuh"
+#include "attn_block.cuh"
 #include "conv_gemm.cuh"
 #include "conv_halo.cuh"
 #include "kernels.cuh"
@@ -229,6 +230,20 @@ int ddpm_attention(const void* qkv, void* out, int N, int T, int C, int heads, f
                                 static_cast<cudaStream_t>(stream));
 }
 
+int ddpm_attention_block(const void* h, void* out, int N, int T, int C, int heads, int groups, float eps, float scale,
+                         const float* gamma, const float* beta, const void* wqkv, const float* bqkv, const void* wproj,
+                         const float* bproj, float* stats_out, void* stream) {
+    if (!h || !out || !gamma || !beta || !wqkv || !wproj) { ddpm::set_error("ddpm_attention_block: null argument"); return 2; }
+    ddpm::AttnBlockLaunch l;
+    int rc = ddpm::attn_block_prepare(static_cast<const __half*>(h), static_cast<__half*>(out), N, T, C, heads, groups, eps,
+                                      scale, gamma, beta, static_cast<const __half*>(wqkv), bqkv,
+                                      static_cast<const __half*>(wproj), bproj, stats_out, ddpm::num_sms(), &l);
+    if (rc) return rc;
+    return ddpm::attn_block_launch(l, static_cast<cudaStream_t>(stream));
+}
+
+int ddpm_attention_block_stats_parts(int T) { return ddpm::attn_block_stats_parts(T); }
+
 int ddpm_pack_conv_weight(const float* w, int Cout, int Cin, int taps, void* dst, long long ktot, long long koff,
                           void* stream) {
     const long long total = static_cast<long long>(Cout) * Cin * taps;
@@ -392,5 +407,62 @@ int ddpm_lpips_forward(void* handle, const float* in0, const float* in1, float* 
                                                       static_cast<cudaStream_t>(stream));
 }
 long long ddpm_lpips_launch_count(void* handle) { return handle ? static_cast<ddpm::Lpips*>(handle)->launches() : 0; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ VQ-VAE
+#include "vqvae.cuh"
+
+static_assert(DDPM_MAX_LEVELS == ddpm::kVqMaxLevels, "level capacity mismatch");
+
+extern "C" {
+
+int ddpm_vqvae_create(const ddpm_vqvae_config* cfg, void** handle) {
+    if (!cfg || !handle) { ddpm::set_error("ddpm_vqvae_create: null argument"); return 2; }
+    ddpm::VqVaeConfig c{};
+    c.spatial_dims = cfg->spatial_dims;
+    c.in_channels = cfg->in_channels;
+    c.out_channels = cfg->out_channels;
+    c.num_levels = cfg->num_levels;
+    c.num_res_layers = cfg->num_res_layers;
+    for (int i = 0; i < DDPM_MAX_LEVELS; ++i) {
+        c.num_channels[i] = cfg->num_channels[i];
+        c.num_res_channels[i] = cfg->num_res_channels[i];
+    }
+    c.num_embeddings = cfg->num_embeddings;
+    c.embedding_dim = cfg->embedding_dim;
+    c.precise_encode = cfg->precise_encode;
+    ddpm::VqVae* v = new ddpm::VqVae(c);
+    int rc = v->init();
+    if (rc) { delete v; *handle = nullptr; return rc; }
+    *handle = v;
+    return 0;
+}
+void ddpm_vqvae_destroy(void* handle) { delete static_cast<ddpm::VqVae*>(handle); }
+int ddpm_vqvae_set_param(void* handle, const char* name, const float* data, long long numel, void* stream) {
+    if (!handle || !name || !data) { ddpm::set_error("ddpm_vqvae_set_param: null argument"); return 2; }
+    return static_cast<ddpm::VqVae*>(handle)->set_param(name, data, numel, static_cast<cudaStream_t>(stream));
+}
+int ddpm_vqvae_finalize(void* handle, void* stream) {
+    if (!handle) { ddpm::set_error("ddpm_vqvae_finalize: null handle"); return 2; }
+    return static_cast<ddpm::VqVae*>(handle)->finalize(static_cast<cudaStream_t>(stream));
+}
+long long ddpm_vqvae_workspace_bytes(void* handle, int N, int D, int H, int W) {
+    if (!handle) { ddpm::set_error("ddpm_vqvae_workspace_bytes: null handle"); return 0; }
+    return static_cast<long long>(static_cast<ddpm::VqVae*>(handle)->workspace_bytes(N, D, H, W));
+}
+int ddpm_vqvae_encode(void* handle, const float* x, float* latent, int* indices, int N, int D, int H, int W, void* workspace,
+                      long long workspace_bytes, void* stream) {
+    if (!handle || !x || !latent || !workspace) { ddpm::set_error("ddpm_vqvae_encode: null argument"); return 2; }
+    return static_cast<ddpm::VqVae*>(handle)->encode(x, latent, indices, N, D, H, W, workspace,
+                                                     static_cast<size_t>(workspace_bytes), static_cast<cudaStream_t>(stream));
+}
+int ddpm_vqvae_decode(void* handle, const float* z, const int* indices_in, float* image, int* indices_out, int N, int D, int H,
+                      int W, void* workspace, long long workspace_bytes, void* stream) {
+    if (!handle || !image || !workspace) { ddpm::set_error("ddpm_vqvae_decode: null argument"); return 2; }
+    return static_cast<ddpm::VqVae*>(handle)->decode(z, indices_in, image, indices_out, N, D, H, W, workspace,
+                                                     static_cast<size_t>(workspace_bytes), static_cast<cudaStream_t>(stream));
+}
+long long ddpm_vqvae_launch_count(void* handle) { return handle ? static_cast<ddpm::VqVae*>(handle)->launches() : 0; }
 
 }  // extern "C"

@@ -162,7 +162,32 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint
                                 }
                             }
                         }
-                        if (p.mode == EPI_STORE_VT && col0 >= p.vt_col0) {
+                        if (p.residual_lo) {
+                            const uint4* r4 =
+                                reinterpret_cast<const uint4*>(p.residual_lo + pix * static_cast<size_t>(p.Cout) + col0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint4 rv = __ldg(r4 + j);
+                                const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 ff = __half22float2(h2[e]);
+                                    f[8 * j + 2 * e] += ff.x;
+                                    f[8 * j + 2 * e + 1] += ff.y;
+                                }
+                            }
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                        }
+                        if (p.mode == EPI_STORE_F32) {
+                            float4* d4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * static_cast<size_t>(p.Cout) + col0);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) d4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) packed[j] = 0u;
+                        } else if (p.mode == EPI_STORE_VT && col0 >= p.vt_col0) {
                             // transposed store for the attention V operand: out_vt[pair][c][token-in-pair], where a
                             // "pair" is the 128 consecutive tokens of one M tile.
                             const size_t tok = pix;  // token index == pixel index (N*T rows)
@@ -184,6 +209,18 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint
 #pragma unroll
                                 for (int j = 0; j < 4; ++j)
                                     d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                            }
+                            if (p.out_lo) {  // lo half: what fp16 rounding of the hi half lost
+                                uint32_t plo[16];
+#pragma unroll
+                                for (int j = 0; j < 32; j += 2) {
+                                    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&packed[j >> 1]));
+                                    __half2 ll = __floats2half2_rn(f[j] - hi.x, f[j + 1] - hi.y);
+                                    plo[j >> 1] = *reinterpret_cast<uint32_t*>(&ll);
+                                }
+                                uint4* l4 = reinterpret_cast<uint4*>(p.out_lo + pix * static_cast<size_t>(p.Cout) + col0);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) l4[j] = make_uint4(plo[4 * j], plo[4 * j + 1], plo[4 * j + 2], plo[4 * j + 3]);
                             }
                         }
                     } else {
@@ -303,6 +340,8 @@ __device__ __forceinline__ void conv_epilogue_tile16(const ConvGemmParams& p, ui
     const bool want_stats = p.stats_out && !(p.dbg & 8);
     __half* out_row = p.out + pix * static_cast<size_t>(p.Cout) + col_base;
     const __half* res_row = p.residual ? p.residual + pix * static_cast<size_t>(p.Cout) + col_base : nullptr;
+    const __half* res_lo_row = p.residual_lo ? p.residual_lo + pix * static_cast<size_t>(p.Cout) + col_base : nullptr;
+    __half* out_lo_row = p.out_lo ? p.out_lo + pix * static_cast<size_t>(p.Cout) + col_base : nullptr;
 
     // one 16-column chunk: bias / addend / residual, fp16 store; leaves the chunk's statistics candidates in sv:
     // quad sums of the ROUNDED values (what GroupNorm reads back), sv[0..3] sums, sv[4..7] sums of squares
@@ -332,6 +371,24 @@ __device__ __forceinline__ void conv_epilogue_tile16(const ConvGemmParams& p, ui
                     }
                 }
             }
+            if (res_lo_row) {
+                const uint4* r4 = reinterpret_cast<const uint4*>(res_lo_row + c * 16);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint4 rv = __ldg(r4 + j);
+                    const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 ff = __half22float2(h2[e]);
+                        f[8 * j + 2 * e] += ff.x;
+                        f[8 * j + 2 * e + 1] += ff.y;
+                    }
+                }
+            }
+            if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
                 __half2 hh = __floats2half2_rn(f[j], f[j + 1]);
@@ -341,6 +398,18 @@ __device__ __forceinline__ void conv_epilogue_tile16(const ConvGemmParams& p, ui
                 uint4* d4 = reinterpret_cast<uint4*>(out_row + c * 16);
                 d4[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
                 d4[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            }
+            if (out_lo_row) {  // lo half: what fp16 rounding of the hi half lost
+                uint32_t plo[8];
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&packed[j >> 1]));
+                    __half2 ll = __floats2half2_rn(f[j] - hi.x, f[j + 1] - hi.y);
+                    plo[j >> 1] = *reinterpret_cast<uint32_t*>(&ll);
+                }
+                uint4* l4 = reinterpret_cast<uint4*>(out_lo_row + c * 16);
+                l4[0] = make_uint4(plo[0], plo[1], plo[2], plo[3]);
+                l4[1] = make_uint4(plo[4], plo[5], plo[6], plo[7]);
             }
         } else {
 #pragma unroll

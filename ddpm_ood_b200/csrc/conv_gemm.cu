@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
                     const int chunks = p.seg_chunks[seg];
                     const int tap = local / chunks;
                     const int chunk = local - tap * chunks;
-                    const int kw = p.seg_kw[seg], kh = p.seg_kh[seg], kd = p.seg_kd[seg];
+                    const int kw = p.seg_kw[seg], kh = p.seg_kh[seg], kd = p.seg_kd[seg], pad = p.seg_pad[seg];
                     const int iw = tap % kw;
                     const int ih = (tap / kw) % kh;
                     const int id = tap / (kw * kh);
@@ -123,9 +123,9 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt)
                         ptx::tma_load_5d(smem_a + (stage * MT + mt) * C::kABytes, ma, &full_bar[stage], chunk * kBlockK,
-                                         w0[mt] + iw + (phased ? pofw : -(kw >> 1)),
-                                         h0[mt] + ih + (phased ? pofh : -(kh >> 1)),
-                                         d0[mt] + id + (phased ? pofd : -(kd >> 1)), n0[mt]);
+                                         w0[mt] + iw + (phased ? pofw : -(kw > 1 ? pad : 0)),
+                                         h0[mt] + ih + (phased ? pofh : -(kh > 1 ? pad : 0)),
+                                         d0[mt] + id + (phased ? pofd : -(kd > 1 ? pad : 0)), n0[mt]);
                     ptx::tma_load_2d(smem_b + stage * C::kBBytes, &p.tmB, &full_bar[stage], kb * kBlockK, brow);
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
@@ -301,7 +301,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
                     const int chunks = p.seg_chunks[seg];
                     const int tap = local / chunks;
                     const int chunk = local - tap * chunks;
-                    const int kw = p.seg_kw[seg], kh = p.seg_kh[seg], kd = p.seg_kd[seg];
+                    const int kw = p.seg_kw[seg], kh = p.seg_kh[seg], kd = p.seg_kd[seg], pad = p.seg_pad[seg];
                     const int iw = tap % kw;
                     const int ih = (tap / kw) % kh;
                     const int id = tap / (kw * kh);
@@ -311,9 +311,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt)
                         ptx::tma_load_5d_2cta(smem_a + (stage * MT + mt) * C::kABytes, ma, &full_bar[stage],
-                                              chunk * kBlockK, w0[mt] + iw + (phased ? pofw : -(kw >> 1)),
-                                              h0[mt] + ih + (phased ? pofh : -(kh >> 1)),
-                                              d0[mt] + id + (phased ? pofd : -(kd >> 1)), n0[mt]);
+                                              chunk * kBlockK, w0[mt] + iw + (phased ? pofw : -(kw > 1 ? pad : 0)),
+                                              h0[mt] + ih + (phased ? pofh : -(kh > 1 ? pad : 0)),
+                                              d0[mt] + id + (phased ? pofd : -(kd > 1 ? pad : 0)), n0[mt]);
                     ptx::tma_load_2d_2cta(smem_b + stage * C::kBHalfBytes, &p.tmB, &full_bar[stage], kb * kBlockK, brow);
                     if (++stage == C::kStages) { stage = 0; parity ^= 1; }
                 }
@@ -478,11 +478,16 @@ int conv_prepare(const ConvProblem& q, int num_sms, ConvLaunch* out) {
     p.Cout = q.Cout;
     p.b_rows_per_mtile = q.b_rows_per_mtile;
     p.mode = q.mode;
+    p.relu = q.relu;
+    if (q.relu && q.mode != EPI_STORE) { set_error("conv: relu needs the store epilogue"); return 2; }
     p.bias = q.bias;
     p.chan_add = q.chan_add;
     p.chan_add_stride = q.chan_add_stride;
     p.residual = static_cast<const __half*>(q.residual);
     p.out = static_cast<__half*>(q.out);
+    p.out_lo = static_cast<__half*>(q.out_lo);
+    p.residual_lo = static_cast<const __half*>(q.residual_lo);
+    if ((q.out_lo || q.residual_lo) && q.mode != EPI_STORE) { set_error("conv: split-precision output needs the store epilogue"); return 2; }
     p.scale = q.scale;
     p.group = q.group;
     p.vt_col0 = q.vt_col0;
@@ -505,7 +510,12 @@ int conv_prepare(const ConvProblem& q, int num_sms, ConvLaunch* out) {
     for (int s = 0; s < q.n_seg; ++s) {
         const ConvSegment& g = q.seg[s];
         if (g.channels % kBlockK != 0) { set_error("conv: segment channels %d not a multiple of 64", g.channels); return 2; }
-        if (g.ksize != 1 && g.ksize != 3 && !(g.ksize == 2 && q.upsample2)) { set_error("conv: ksize %d unsupported", g.ksize); return 2; }
+        if (g.ksize != 1 && g.ksize != 3 && !(g.ksize == 2 && q.upsample2) && !(g.ksize == 4 && q.stride == 2)) {
+            set_error("conv: ksize %d unsupported", g.ksize);
+            return 2;
+        }
+        p.seg_pad[s] = q.pad > 0 ? q.pad : g.ksize >> 1;
+        if (g.ksize == 4 && p.seg_pad[s] != 1) { set_error("conv: 4-tap stride-2 convs need pad 1"); return 2; }
         p.seg_chunks[s] = g.channels / kBlockK;
         p.seg_kw[s] = g.ksize;
         p.seg_kh[s] = g.ksize;

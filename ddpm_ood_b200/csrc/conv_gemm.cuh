@@ -26,6 +26,7 @@ enum EpilogueMode : int {
     EPI_STORE = 0,       // out[pixel, c] = acc + bias (+chan_add) (+residual)
     EPI_SOFTMAX_BD = 1,  // block-diagonal softmax over groups of T columns (attention scores), writes P fp16
     EPI_STORE_VT = 2,    // like STORE but columns >= vt_col0 are written transposed ([pair][c][128 tokens])
+    EPI_STORE_F32 = 3,   // out is fp32 [pixel][Cout]: acc + bias (the VQ-VAE's last transposed conv keeps fp32 tap products)
 };
 
 struct ConvGemmParams {
@@ -35,7 +36,8 @@ struct ConvGemmParams {
     int n_seg;
     int seg_kb_end[kMaxSeg];  // exclusive prefix end in k-blocks
     int seg_chunks[kMaxSeg];  // channels/64
-    int seg_kw[kMaxSeg], seg_kh[kMaxSeg], seg_kd[kMaxSeg];  // tap extents (1 or 3)
+    int seg_kw[kMaxSeg], seg_kh[kMaxSeg], seg_kd[kMaxSeg];  // tap extents (1, 3, or 4 for the VQ-VAE's stride-2 convs)
+    int seg_pad[kMaxSeg];     // zero padding per spatial dim with extent > 1: input coord = out*stride + tap - pad
     int num_kb;
     // output geometry (output pixels)
     int N, D, H, W;
@@ -67,6 +69,11 @@ struct ConvGemmParams {
     int num_phases;
     int phase3d;
     int pair_rows;  // conv_halo pair tiles: accumulator row m = h * 16 + n' * 8 + w of images 2 * tile + n' (<= 8 x 8)
+    int relu;       // EPI_STORE: max(., 0) after bias / addend / residual (VQ-VAE convs and residual units)
+    // Split-precision activations (the VQ-VAE encoder, which the reference runs in fp32): a value is carried as fp16
+    // hi + fp16 lo (lo = fp16(x - hi), ~22 mantissa bits together). out_lo / residual_lo: the lo halves of out / residual.
+    __half* out_lo;
+    const __half* residual_lo;
     int dbg;  // timing experiments only: 8 skip the statistics, 16 skip the output stores (results wrong when set)
 };
 
@@ -82,7 +89,7 @@ struct ConvLaunch {
 struct ConvSegment {
     const void* ptr;  // NDHWC fp16
     int channels;     // multiple of 64
-    int ksize;        // 1 or 3 (per spatial dim); 2 only with ConvProblem::upsample2
+    int ksize;        // 1 or 3 (per spatial dim); 2 only with ConvProblem::upsample2; 4 with stride 2 and pad 1
 };
 
 struct ConvProblem {
@@ -115,6 +122,10 @@ struct ConvProblem {
     // then channel over the concatenation) instead of one K block per segment - a conv over torch.cat(inputs, dim=1)
     int concat3x3;
     int gn_silu;  // halo kernel with a scale/shift table: 1 = GroupNorm + SiLU, 0 = GroupNorm only
+    int relu;     // store epilogue: ReLU after bias / residual
+    void* out_lo;             // split-precision output: lo half (see ConvGemmParams::out_lo)
+    const void* residual_lo;  // split-precision residual: lo half
+    int pad;      // zero padding of segments with ksize > 1; 0 means the default ksize / 2 ("same" for odd kernels)
 };
 
 // Number of GroupNorm-statistics parts per image the epilogue emits for an OUTPUT of this geometry (0: the tile box

@@ -205,6 +205,26 @@ def attention(qkv: torch.Tensor, n: int, t: int, heads: int, scale: float, impl:
     return out
 
 
+def attention_block(h: torch.Tensor, n: int, t: int, gamma: torch.Tensor, beta: torch.Tensor, wqkv: torch.Tensor,
+                    bqkv: torch.Tensor, wproj: torch.Tensor, bproj: torch.Tensor, eps: float = 1e-6, groups: int = 32,
+                    with_stats: bool = False):
+    """The whole AttentionBlock in one launch. h: fp16 [n*t, C]; wqkv fp16 [3C, C]; wproj fp16 [C, C]; fp32 norm affine and
+    biases. Returns out fp16 [n*t, C] (and the GroupNorm partial statistics of out when with_stats)."""
+    assert h.dtype == torch.float16 and h.is_contiguous() and h.shape[0] == n * t
+    c = h.shape[1]
+    out = torch.empty_like(h)
+    stats = None
+    if with_stats:
+        parts = lib().ddpm_attention_block_stats_parts(t)
+        assert parts > 0
+        stats = torch.zeros((n, parts, c // 4, 2), dtype=torch.float32, device=h.device)
+    check(lib().ddpm_attention_block(h.data_ptr(), out.data_ptr(), n, t, c, 1, groups, eps, 1.0 / c ** 0.5,
+                                     gamma.data_ptr(), beta.data_ptr(), wqkv.data_ptr(), bqkv.data_ptr(),
+                                     wproj.data_ptr(), bproj.data_ptr(), _ptr(stats), current_stream_ptr()),
+          "ddpm_attention_block")
+    return (out, stats) if with_stats else out
+
+
 def pack_upconv_weight(w: torch.Tensor) -> torch.Tensor:
     """w: fp32 [Cout, Cin, 3(,3),3] -> fp16 [2^d * Cout, 2^d * Cin] sub-pixel phase weights for conv_forward(upsample2=True)."""
     assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()

@@ -165,7 +165,12 @@ class BatchReconstructor:
             if c.plms_state == "reset":
                 sched.reset_chain()
             start_timesteps = torch.Tensor([t_start] * B).long()
-            noise = noise_fn(grid_pos[i], int(t_start)) if noise_fn is not None else torch.randn_like(images)
+            if noise_fn is None:
+                noise = torch.randn_like(images)
+            elif getattr(noise_fn, "wants_like", False):  # noise shaped like what is noised (the latent for an LDM)
+                noise = noise_fn(grid_pos[i], int(t_start), images)
+            else:
+                noise = noise_fn(grid_pos[i], int(t_start))
             x = sched.add_noise(original_samples=scaled, noise=noise, timesteps=start_timesteps)
             chain = [int(s) for s in timesteps[timesteps <= t_start]]
             sched.run_chain(self.model, x, chain)

@@ -3,6 +3,7 @@ construction, SNR shift, checkpoint loading. Training-only state (optimizer, Gra
 scope."""
 from __future__ import annotations
 
+import json
 import os
 import sys
 from pathlib import Path
@@ -14,6 +15,7 @@ from ..networks import DiffusionModelUNet, PassthroughVQVAE
 from ..reconstruction import snr_shift_
 from ..schedulers import DDPMScheduler
 from ..simplex_noise import Simplex_CLASS
+from ..vqvae import VQVAE
 
 
 class BaseTrainer:
@@ -40,11 +42,27 @@ class BaseTrainer:
         for k, v in vars(args).items():
             print(f"  {k}: {v}")
 
-        if args.vqvae_checkpoint:
-            raise NotImplementedError("latent (VQ-VAE) reconstruction is SURVEY.md §8(f)-1 'next'; pixel-space DDPMs "
-                                      "use the PassthroughVQVAE path")
-        self.vqvae_model = PassthroughVQVAE()
-        ddpm_channels = 1 if args.is_grayscale else 3
+        if args.vqvae_checkpoint:  # latent diffusion: stage-1 VQ-VAE built from the json next to its checkpoint (base.py:44-61)
+            vqvae_checkpoint_path = Path(args.vqvae_checkpoint)
+            vqvae_config_path = vqvae_checkpoint_path.parent / "vqvae_config.json"
+            if not vqvae_checkpoint_path.exists():
+                raise FileNotFoundError(f"Cannot find VQ-VAE checkpoint {vqvae_checkpoint_path}")
+            if not vqvae_config_path.exists():
+                raise FileNotFoundError(f"Cannot find VQ-VAE config {vqvae_config_path}")
+            with open(vqvae_config_path, "r") as f:
+                self.vqvae_config = json.load(f)
+            self.vqvae_model = VQVAE(**self.vqvae_config)
+            vqvae_checkpoint = torch.load(vqvae_checkpoint_path, map_location="cpu", weights_only=False)
+            self.vqvae_model.load_state_dict(vqvae_checkpoint["model_state_dict"])
+            self.vqvae_model.to(self.device)
+            self.vqvae_model.eval()
+            print("Loaded vqvae model with config:")
+            for k, v in self.vqvae_config.items():
+                print(f"  {k}: {v}")
+            ddpm_channels = self.vqvae_config["embedding_dim"]
+        else:
+            self.vqvae_model = PassthroughVQVAE()
+            ddpm_channels = 1 if args.is_grayscale else 3
         if args.model_type == "small":
             self.model = DiffusionModelUNet(
                 spatial_dims=args.spatial_dimension, in_channels=ddpm_channels, out_channels=ddpm_channels,

@@ -19,6 +19,7 @@ import torch.distributed as dist
 
 from ..data import get_training_data_loader
 from ..losses import PerceptualLoss
+from ..networks import PassthroughVQVAE
 from ..reconstruction import BatchReconstructor, ReconConfig, partition_t_starts
 from ..simplex_noise import generate_simplex_noise
 from .base import BaseTrainer
@@ -91,23 +92,21 @@ class Reconstruct(BaseTrainer):
                           beta_start=self.beta_start, beta_end=self.beta_end, b_scale=self.b_scale,
                           snr_shift=self.snr_shift, spatial_dimension=self.spatial_dimension,
                           num_inference_steps=steps, plms_state=getattr(self.args, "plms_state", "carry"))
-        return BatchReconstructor(self.model, self._pl, cfg, self.device, vqvae_model=None,
+        vq = None if isinstance(self.vqvae_model, PassthroughVQVAE) else self.vqvae_model
+        return BatchReconstructor(self.model, self._pl, cfg, self.device, vqvae_model=vq,
                                   latent_pad=self.latent_pad if self.do_latent_pad else None)
 
     def _simplex_fn(self, images):
-        """--simplex_noise=1: generate_simplex_noise per t-start (reference trainers/reconstruct.py:133-139), else None
-        (Gaussian noise drawn by the engine)."""
+        """--simplex_noise=1: generate_simplex_noise per t-start over whatever is noised - the image, or the (padded)
+        latent of an LDM (reference trainers/reconstruct.py:133-139) - else None (Gaussian noise drawn by the engine)."""
         if not self.simplex_noise:
             return None
-        if self.do_latent_pad:
-            raise NotImplementedError("simplex noise with --latent_pad (latent models are SURVEY §8 f-1)")
-        shape = tuple(images.shape)
-        probe = torch.empty(shape, device=self.device)
 
-        def fn(i, t_start):
-            t = torch.full((shape[0],), int(t_start), dtype=torch.long)
-            return generate_simplex_noise(self.simplex, x=probe, t=t, in_channels=shape[1])
+        def fn(i, t_start, like):
+            t = torch.full((like.shape[0],), int(t_start), dtype=torch.long)
+            return generate_simplex_noise(self.simplex, x=like, t=t, in_channels=like.shape[1])
 
+        fn.wants_like = True
         return fn
 
     def get_scores(self, loader, dataset_name, inference_skip_factor):

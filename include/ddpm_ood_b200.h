@@ -29,7 +29,7 @@ extern "C" {
 DDPM_API const char* ddpm_last_error(void);
 /* ABI version, bumped on any signature or struct-layout change; the Python binding refuses a library whose version or
  * struct sizes (ddpm_struct_sizes) differ from its own. */
-#define DDPM_ABI_VERSION 5
+#define DDPM_ABI_VERSION 6
 DDPM_API int ddpm_abi_version(void);
 
 /* ------------------------------------------------------------------------------------------------ building block
@@ -131,6 +131,17 @@ DDPM_API int ddpm_pack_upconv_weight(const float* w, int Cout, int Cin, int spat
  * impl: 0 = pick (tcgen05 kernel when 128 % T == 0 or T == 256, else the generic kernel), 1 = force generic. */
 DDPM_API int ddpm_attention(const void* qkv, void* out, int N, int T, int C, int heads, float scale, int impl,
                             void* stream);
+
+/* The WHOLE AttentionBlock of monai-generative's DiffusionModelUNet in one launch (C = 256, one head, T <= 128 tokens per
+ * image): out = h + proj(softmax(q k^T * scale) v), q | k | v = Linear(GroupNorm(h)). Replaces the module the reference
+ * reaches through model(x, timesteps) at src/trainers/reconstruct.py:150-153 (attention_levels of base.py:66-75).
+ * h, out: fp16 [N*T, C] (tokens x channels, channels-last activations); gamma, beta: fp32 [C] (32 groups);
+ * wqkv: fp16 [3C, C] (to_q | to_k | to_v weights, rows = output channels), bqkv fp32 [3C]; wproj fp16 [C, C], bproj [C];
+ * stats_out: null, or fp32 [N][ddpm_attention_block_stats_parts(T)][C/4][2] GroupNorm partial sums of `out`. */
+DDPM_API int ddpm_attention_block(const void* h, void* out, int N, int T, int C, int heads, int groups, float eps,
+                                  float scale, const float* gamma, const float* beta, const void* wqkv, const float* bqkv,
+                                  const void* wproj, const float* bproj, float* stats_out, void* stream);
+DDPM_API int ddpm_attention_block_stats_parts(int T);
 
 /* fp32 PyTorch conv weight [Cout][Cin][taps] (or Linear weight with taps == 1) -> fp16 rows of a packed matrix:
  * dst[co * ktot + koff + tap * Cin + ci]. */
@@ -261,6 +272,44 @@ DDPM_API int ddpm_scale_intensity(const void* src, int src_is_u8, float* dst, in
  * (_init, :559-577). fp64 arithmetic in the reference's operand order: bit-identical values. */
 DDPM_API int ddpm_simplex_noise(const long long* seeds, const long long* t, float* out, unsigned char* tables_ws, int B,
                                 int C, int H, int W, int octaves, double persistence, double frequency, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ VQ-VAE (latent models)
+ * monai-generative's VQVAE as the reference builds it from vqvae_config.json (src/trainers/base.py:44-61): the stage-1
+ * model of the latent-diffusion path. Replaces `self.vqvae_model.encode_stage_2_inputs(images)`
+ * (src/trainers/reconstruct.py:124) and `self.vqvae_model.decode_stage_2_outputs(reconstructions)` (:166).
+ * Supported: downsample_parameters (2,4,1,1) and upsample_parameters (2,4,1,1,0) per level (the reference's README
+ * configuration), channel counts that are multiples of 128, ReLU, no dropout / output activation. */
+typedef struct ddpm_vqvae_config {
+    int spatial_dims;                 /* 2 or 3 */
+    int in_channels, out_channels;    /* image channels (1..3) */
+    int num_levels;
+    int num_res_layers;
+    int num_channels[DDPM_MAX_LEVELS];
+    int num_res_channels[DDPM_MAX_LEVELS];
+    int num_embeddings, embedding_dim;
+    int precise_encode;               /* 1: encoder on split-precision operands (fp16 hi + fp16 lo halves of every activation
+                                         and weight, three tensor-core products per MAC, fp32 accumulation) - the reference
+                                         encodes in fp32 (src/trainers/reconstruct.py:124 is outside its autocast block) and a
+                                         nearest-row search amplifies fp16 rounding into different rows; 0: fp16 operands */
+} ddpm_vqvae_config;
+
+DDPM_API int ddpm_vqvae_create(const ddpm_vqvae_config* cfg, void** handle);
+DDPM_API void ddpm_vqvae_destroy(void* handle);
+/* name: a key of VQVAE.state_dict() ("encoder.blocks.0.conv.weight", ..., "quantizer.quantizer.embedding.weight");
+ * data: fp32 device pointer in PyTorch layout. */
+DDPM_API int ddpm_vqvae_set_param(void* handle, const char* name, const float* data, long long numel, void* stream);
+DDPM_API int ddpm_vqvae_finalize(void* handle, void* stream);
+/* Workspace for encode / decode of N images of D x H x W voxels (D == 1 in 2-D). */
+DDPM_API long long ddpm_vqvae_workspace_bytes(void* handle, int N, int D, int H, int W);
+/* encode_stage_2_inputs: x fp32 [N, Cin, D, H, W] -> latent fp32 [N, E, D/2^L, H/2^L, W/2^L] (nearest codebook rows);
+ * indices: null or int32 [N, D/2^L, H/2^L, W/2^L] (index_quantize). */
+DDPM_API int ddpm_vqvae_encode(void* handle, const float* x, float* latent, int* indices, int N, int D, int H, int W,
+                               void* workspace, long long workspace_bytes, void* stream);
+/* decode_stage_2_outputs: z fp32 [N, E, d, h, w] -> nearest codebook rows -> image fp32 [N, Cout, D, H, W].
+ * indices_in (instead of z, which may then be null): decode_samples. indices_out: null or the rows chosen. */
+DDPM_API int ddpm_vqvae_decode(void* handle, const float* z, const int* indices_in, float* image, int* indices_out, int N,
+                               int D, int H, int W, void* workspace, long long workspace_bytes, void* stream);
+DDPM_API long long ddpm_vqvae_launch_count(void* handle);
 
 #ifdef __cplusplus
 }

@@ -46,8 +46,14 @@ def reconstruct_batch(
     cfg: LoopConfig,
     keep_recons: bool = False,
     t_starts: Optional[List[int]] = None,
+    vqvae=None,
+    latent_pad: Optional[List[int]] = None,
+    keep_indices: bool = False,
 ) -> Dict[str, object]:
-    """One batch of trainers/reconstruct.py:97-204 (PassthroughVQVAE, no latent pad).
+    """One batch of trainers/reconstruct.py:97-204. vqvae=None is the PassthroughVQVAE of pixel-space models; otherwise
+    `vqvae.encode_stage_2_inputs` before the t-start loop (:124), optional constant latent padding (:125-126, undone at
+    :159-165) and `vqvae.decode_stage_2_outputs` per t-start (:166). keep_indices (vqvae only): also return the codebook
+    rows of the encoding and of every reconstructed latent ("enc_indices", "dec_indices").
 
     noise_fn(i, t_start) -> noise tensor like images for the i-th t-start.
     Returns {"t": LongTensor[n_t], "perceptual_difference": [n_t, B], "mse": [n_t, B], ("recons": list)}.
@@ -57,7 +63,12 @@ def reconstruct_batch(
     starts = t_start_grid(timesteps, cfg.inference_skip_factor)
     if t_starts is not None:  # bounded samples of the grid (bench.py's CPU arm); every entry must be a grid value
         starts = torch.tensor([int(t) for t in t_starts], dtype=torch.long)
-    images = images_original  # PassthroughVQVAE.encode_stage_2_inputs
+    with torch.no_grad():
+        images = images_original if vqvae is None else vqvae.encode_stage_2_inputs(images_original)
+        enc_indices = vqvae.index_quantize(images_original) if (vqvae is not None and keep_indices) else None
+    if latent_pad:
+        images = F.pad(input=images, pad=latent_pad, mode="constant", value=0)
+    dec_indices: List[torch.Tensor] = []
     B = images.shape[0]
     out_t: List[int] = []
     out_p: List[torch.Tensor] = []
@@ -74,6 +85,12 @@ def reconstruct_batch(
                 ts = torch.Tensor([step] * B).long()
                 eps = model(x, ts)
                 x, _ = sched.step(eps, step, x)
+            if latent_pad:
+                x = F.pad(input=x, pad=[-p for p in latent_pad], mode="constant", value=0)
+            if vqvae is not None:
+                if keep_indices:
+                    dec_indices.append(vqvae.quantizer.quantize(x))
+                x = vqvae.decode_stage_2_outputs(x)
             x = x / cfg.b_scale
             x = x.clamp(0, 1)
             if perceptual is None:  # latent-only checks (a 128-channel latent is not an LPIPS input): MSE only
@@ -102,6 +119,9 @@ def reconstruct_batch(
     }
     if keep_recons:
         res["recons"] = recons
+    if enc_indices is not None:
+        res["enc_indices"] = enc_indices
+        res["dec_indices"] = torch.stack(dec_indices)
     return res
 
 

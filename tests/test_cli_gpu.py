@@ -151,3 +151,66 @@ def test_cli_simplex_noise_mode(tmp_path, monkeypatch):
         simplex, x=probe, t=torch.full((3,), int(t), dtype=torch.long), in_channels=1))
     want = np.stack([res["perceptual_difference"].cpu().numpy().reshape(-1), res["mse"].cpu().numpy().reshape(-1)], axis=1)
     assert np.allclose(val[["perceptual_difference", "mse"]].to_numpy(), want, rtol=1e-5, atol=0)
+
+
+def test_cli_latent_diffusion_with_vqvae_checkpoint(tmp_path, monkeypatch):
+    """--vqvae_checkpoint (reference src/trainers/base.py:44-61): the stage-1 VQ-VAE is built from vqvae_config.json next
+    to its checkpoint, the DDPM gets embedding_dim channels, 3-D volumes are encoded once per batch and every
+    reconstructed latent is decoded before scoring (src/trainers/reconstruct.py:124,166); per-item 2.5-D LPIPS."""
+    import json
+
+    monkeypatch.setenv("DDPM_LPIPS_ALLOW_SYNTHETIC", "1")
+    sys.path.insert(0, str(ROOT))
+    import reconstruct as cli
+    from ddpm_ood_b200.data import SimpleLoader
+    from ddpm_ood_b200.trainers import Reconstruct
+    from ddpm_ood_b200.vqvae import VQVAE
+    from oracle import unet as ou
+    from oracle import vqvae as ov
+
+    rng = np.random.default_rng(0)
+    d = tmp_path / "vol"
+    d.mkdir()
+    paths = []
+    for i in range(3):
+        np.save(d / f"vol_{i}.npy", rng.integers(0, 256, (32, 32, 32), dtype=np.uint8))
+        paths.append(str(d / f"vol_{i}.npy"))
+    ids = tmp_path / "vol_ids.csv"
+    ids.write_text(",".join(paths) + "\n")
+
+    vq_cfg = dict(spatial_dims=3, in_channels=1, out_channels=1, num_channels=[128, 256], num_res_layers=1,
+                  num_res_channels=[128, 256], downsample_parameters=[[2, 4, 1, 1]] * 2,
+                  upsample_parameters=[[2, 4, 1, 1, 0]] * 2, num_embeddings=256, embedding_dim=128)
+    vq_dir = tmp_path / "runs" / "vqvae"
+    vq_dir.mkdir(parents=True)
+    (vq_dir / "vqvae_config.json").write_text(json.dumps(vq_cfg))
+    torch.save({"model_state_dict": ov.randomize_(ov.VQVAE(**vq_cfg), seed=0).state_dict()}, vq_dir / "checkpoint.pth")
+    run = tmp_path / "runs" / "ldm"
+    run.mkdir(parents=True)
+    torch.save({"epoch": 1, "global_step": 1, "best_loss": 0.5,
+                "model_state_dict": ou.randomize_(ou.make_small(3, 128), seed=5).state_dict()}, run / "checkpoint.pth")
+    args = cli.parse_args([
+        "--output_dir", str(tmp_path / "runs"), "--model_name", "ldm", "--validation_ids", str(ids), "--in_ids", str(ids),
+        "--out_ids", str(ids), "--run_in", "0", "--run_out", "0", "--is_grayscale", "1", "--spatial_dimension", "3",
+        "--batch_size", "2", "--vqvae_checkpoint", str(vq_dir / "checkpoint.pth"), "--beta_schedule", "scaled_linear_beta",
+        "--beta_start", "0.0015", "--beta_end", "0.0195", "--inference_skip_factor", "64"])
+    recon = Reconstruct(args)
+    assert isinstance(recon.vqvae_model, VQVAE) and recon.model.in_channels == 128
+    torch.manual_seed(11)
+    recon.reconstruct(args)
+    val = pd.read_csv(run / "ood" / "results_val.csv", index_col=0)
+    stems = [Path(p).stem for p in paths]
+    assert list(val["filename"]) == stems[:2] * 2 + stems[2:] * 2
+    assert list(val["t"]) == [10] * 2 + [650] * 2 + [10] + [650]
+    assert np.isfinite(val[["perceptual_difference", "mse"]].to_numpy()).all()
+
+    torch.manual_seed(11)
+    engine = recon._engine()
+    assert engine.vqvae_model is recon.vqvae_model
+    rows = []
+    tf = dict(is_grayscale=True, spatial_dimension=3, image_size=None, image_roi=None, add_vflip=False, add_hflip=False)
+    for batch in SimpleLoader([{"image": p} for p in paths], 2, False, **tf):
+        res = engine.score_batch(batch["image"], 64)
+        for i in range(len(res["t"])):
+            rows += [(float(a), float(b)) for a, b in zip(res["perceptual_difference"][i].cpu(), res["mse"][i].cpu())]
+    assert np.allclose(val[["perceptual_difference", "mse"]].to_numpy(), np.array(rows), rtol=1e-5, atol=0)
