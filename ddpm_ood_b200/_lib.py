@@ -5,6 +5,7 @@ The product path has no CPU fallback: if the shared library is missing, loading 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _CSRC = Path(__file__).resolve().parent / "csrc"
@@ -218,6 +219,12 @@ def lib() -> C.CDLL:
         return _lib
     from .csrc import build as _build
 
+    variant = os.environ.get("DDPM_LIB_VARIANT")  # kernel A/B experiments only: an alternately compiled library
+    if variant:
+        L = C.CDLL(variant)
+        _verify(L)
+        _lib = L
+        return L
     if _build.needs_build() and _build.have_nvcc():
         _build.build(verbose=False)
     if not LIB_PATH.exists():

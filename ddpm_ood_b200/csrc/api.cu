@@ -14,20 +14,20 @@
 #include "conv_gemm.cuh"
 #include "conv_halo.cuh"
 #include "kernels.cuh"
+#include "launch.cuh"
 
 namespace ddpm {
 
 int num_sms() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
-            sms = 0;
-            return 148;
-        }
+    static int sms[ddpm::kMaxDevices] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return 148;
+    int& v = sms[dev % ddpm::kMaxDevices];
+    if (!v && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+        v = 0;
+        return 148;
     }
-    return sms;
+    return v;
 }
 
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps,

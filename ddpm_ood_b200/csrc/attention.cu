@@ -230,7 +230,8 @@ int attention_tc_prepare(const __half* qkv, __half* out, int N, int T, int C, in
 }
 
 int attention_tc_launch(const AttnTcLaunch& l, cudaStream_t stream) {
-    static bool attr_set = false;
+    static bool attr_set_dev[kMaxDevices] = {};
+    bool& attr_set = attr_set_dev[device_slot()];
     if (!attr_set) {
         cudaError_t e1 = cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
         cudaError_t e2 = cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);

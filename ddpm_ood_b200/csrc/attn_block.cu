@@ -534,7 +534,7 @@ int attn_block_prepare(const __half* h, __half* out, int N, int T, int C, int he
 }
 
 int attn_block_launch(const AttnBlockLaunch& l, cudaStream_t stream) {
-    static bool attr_set[64] = {};
+    static bool attr_set[kMaxDevices] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {

@@ -394,11 +394,7 @@ __device__ __forceinline__ void conv_epilogue_tile16(const ConvGemmParams& p, ui
                 __half2 hh = __floats2half2_rn(f[j], f[j + 1]);
                 packed[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
             }
-            if (!(p.dbg & 16)) {
-                uint4* d4 = reinterpret_cast<uint4*>(out_row + c * 16);
-                d4[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                d4[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-            }
+            if (!(p.dbg & 16)) ptx::st_global_256(out_row + c * 16, packed);  // rows are 256-byte aligned (Cout % 128 == 0)
             if (out_lo_row) {  // lo half: what fp16 rounding of the hi half lost
                 uint32_t plo[8];
 #pragma unroll

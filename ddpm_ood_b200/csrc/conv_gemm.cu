@@ -584,8 +584,9 @@ int conv_prepare(const ConvProblem& q, int num_sms, ConvLaunch* out) {
     return 0;
 }
 
-static bool g_attr_set = false;
 int conv_launch(const ConvLaunch& l, cudaStream_t stream) {
+    static bool attr_set_dev[kMaxDevices] = {};
+    bool& g_attr_set = attr_set_dev[device_slot()];
     if (!g_attr_set) {
         cudaError_t e1 = cudaFuncSetAttribute(conv_gemm_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               Cfg<128, 1>::kSmemBytes);

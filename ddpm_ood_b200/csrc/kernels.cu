@@ -455,7 +455,8 @@ int attention_core(const __half* qkv, __half* out, int N, int T, int C, int head
     const int Tp = (T + 3) & ~3;
     const size_t smem = static_cast<size_t>(kQT + kKT) * kPadHD * sizeof(__half) + static_cast<size_t>(kQT) * Tp * sizeof(float);
     if (smem > 220 * 1024) { set_error("attention_core: T=%d too large", T); return 2; }
-    static size_t smem_set = 0;
+    static size_t smem_set_dev[kMaxDevices] = {};
+    size_t& smem_set = smem_set_dev[device_slot()];
     if (smem > smem_set) {
         cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) { set_error("attention_core: %s", cudaGetErrorString(e)); return 4; }
@@ -863,8 +864,9 @@ int conv_in_small(const float* x, const float* w, const float* b, __half* out, i
     if (stats_out) { set_error("conv_in_small: fused statistics unsupported for Cin=%d", Cin); return 2; }
     const size_t smem = static_cast<size_t>(kd) * 9 * Cin * Cout * sizeof(float);
     if (Cout % 8 || smem > 200 * 1024) { set_error("conv_in_small: Cin=%d Cout=%d unsupported", Cin, Cout); return 2; }
-    static size_t smem_set = 48 * 1024;
-    if (smem > smem_set) {
+    static size_t smem_set_dev[kMaxDevices] = {};
+    size_t& smem_set = smem_set_dev[device_slot()];
+    if (smem > 48 * 1024 && smem > smem_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_in_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) { set_error("conv_in_small: %s", cudaGetErrorString(e)); return 4; }
         smem_set = smem;
@@ -1018,8 +1020,9 @@ int conv_out_small(const __half* z, const float* w, const float* b, float* eps_o
     const int kd = spatial_dims == 3 ? 3 : 1;
     const size_t smem = static_cast<size_t>(Cout) * kd * 9 * Cin * sizeof(float);
     if (Cout > kMaxCoutSmall || Cin % 64 || smem > 200 * 1024) { set_error("conv_out_small: Cin=%d Cout=%d unsupported", Cin, Cout); return 2; }
-    static size_t smem_set = 48 * 1024;
-    if (smem > smem_set) {
+    static size_t smem_set_dev[kMaxDevices] = {};
+    size_t& smem_set = smem_set_dev[device_slot()];
+    if (smem > 48 * 1024 && smem > smem_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_out_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) { set_error("conv_out_small: %s", cudaGetErrorString(e)); return 4; }
         smem_set = smem;

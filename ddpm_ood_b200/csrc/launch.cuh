@@ -9,6 +9,15 @@
 
 namespace ddpm {
 
+// Function attributes (cudaFuncSetAttribute) and the SM count are PER DEVICE: one process may drive several GPUs (the
+// module re-creates its engine when moved), so "already set" state is kept per device ordinal.
+constexpr int kMaxDevices = 64;
+inline int device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev % kMaxDevices;
+}
+
 inline bool pdl_enabled() {
     static int on = -1;
     if (on < 0) {

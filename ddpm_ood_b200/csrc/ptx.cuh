@@ -234,4 +234,12 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
     return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// 256-bit global store (sm_100: STG.E.256): one lane writes a whole 32-byte sector in one request instead of two
+// half-sector writes that L2 has to merge. p must be 32-byte aligned.
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
 }  // namespace ptx

@@ -3,6 +3,8 @@
 
 #include <string.h>
 
+#include "launch.cuh"
+
 namespace ddpm {
 
 int num_sms();  // api.cu
@@ -583,7 +585,7 @@ size_t VqVae::workspace_bytes(int N, int D, int H, int W) const {
 
 int VqVae::run(const Plan& plan, cudaStream_t stream) {
     const VqVaeConfig& c = cfg_;
-    static bool attr_set[64] = {};
+    static bool attr_set[kMaxDevices] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     const size_t qsmem = static_cast<size_t>(kQRows + kQCodes) * (c.embedding_dim + 1) * sizeof(float);
