@@ -53,8 +53,29 @@ def roc_auc(in_scores: torch.Tensor, out_scores: torch.Tensor) -> float:
     return (gt + 0.5 * eq) / (a.numel() * b.numel())
 
 
-def ood_auc(val: torch.Tensor, ins: torch.Tensor, outs: torch.Tensor) -> float:
+def select_t(t_values, min_t: int = 0, max_t: int = 1000):
+    """Row indices of the t-start grid the reference's post-processing keeps (host integer work): the first occurrence of
+    every t (`drop_duplicates(subset=["filename", "t"], keep="first")`, ood_detection.py:53-54,143-145 - a skip-1 grid
+    holds t = 980 twice) with MIN_T < t < MAX_T (:56-62,146-147)."""
+    keep, seen = [], set()
+    for i, t in enumerate(int(v) for v in t_values):
+        if t in seen:
+            continue
+        seen.add(t)
+        if min_t < t < max_t:
+            keep.append(i)
+    return keep
+
+
+def ood_auc(val: torch.Tensor, ins: torch.Tensor, outs: torch.Tensor, t=None, min_t: int = 0, max_t: int = 1000) -> float:
     """val / ins / outs: [n_t, n_*] scores of one target for the validation, in-distribution and out-of-distribution
-    sets (same t grid). Returns the AUC the reference prints (`Zscore_<target>`)."""
+    sets (same t grid). Returns the AUC the reference prints (`Zscore_<target>`). t: the grid's t values ([n_t], what
+    `score_batch` returns as "t"); when given, duplicate t rows are dropped (first kept) and the reference's
+    min_t < t < max_t filter is applied before averaging, as ood_detection.py does on the CSV rows."""
+    if t is not None:
+        rows = select_t(t.tolist() if hasattr(t, "tolist") else t, min_t, max_t)
+        if len(rows) != val.shape[0]:
+            idx = torch.tensor(rows, dtype=torch.long, device=val.device)
+            val, ins, outs = val.index_select(0, idx), ins.index_select(0, idx), outs.index_select(0, idx)
     m, s = val_stats(val)
     return roc_auc(mean_z(ins, m, s), mean_z(outs, m, s))

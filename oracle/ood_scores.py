@@ -14,6 +14,20 @@ from __future__ import annotations
 import numpy as np
 
 
+def select_t(t_values, min_t: int = 0, max_t: int = 1000) -> np.ndarray:
+    """Indices (first occurrences, in order) of the t-start columns the reference keeps: `drop_duplicates(subset=
+    ["filename", "t"], keep="first")` removes the second t = 980 column of a skip-1 grid (ood_detection.py:53-54,143-145)
+    and the strict filter MIN_T < t < MAX_T drops the rest (:56-62,146-147)."""
+    keep, seen = [], set()
+    for i, t in enumerate(np.asarray(t_values).tolist()):
+        if t in seen:
+            continue
+        seen.add(t)
+        if min_t < t < max_t:
+            keep.append(i)
+    return np.asarray(keep, dtype=np.int64)
+
+
 def val_stats(val: np.ndarray):
     """val: [n_t, n_val] -> (mean [n_t], std [n_t]) with ddof = 1 (ood_detection.py:153-158)."""
     val = np.asarray(val, dtype=np.float64)

@@ -1,8 +1,14 @@
 """Golden vectors for the simplex-noise row, made by RUNNING THE REFERENCE's own code
-(/root/reference/src/utils/simplex_noise.py) in this container. numba and matplotlib are not installed: they are
-replaced by inert stubs, so the very same Python source executes un-jitted (njit -> identity, prange -> range).
+(/root/reference/src/utils/simplex_noise.py) in this container under the real numba JIT (numba 0.65 is installed; the
+reference decorates its kernels with @njit(cache=True) / @njit(parallel=True)). matplotlib is absent and only imported
+for the reference's plotting helpers: it is replaced by an inert stub.
 
-    python tests/golden/make_simplex_golden.py      # writes tests/golden/simplex_golden.npz
+    python tests/golden/make_simplex_golden.py              # real numba; writes tests/golden/simplex_golden.npz
+    python tests/golden/make_simplex_golden.py --no-numba   # njit -> identity, prange -> range (the same Python source,
+                                                            # interpreted); --check compares with the committed file
+
+Both modes produce bit-identical arrays (checked when this file was regenerated in round 2): the arithmetic is plain
+IEEE fp64 without fastmath, so the JIT changes speed, not results.
 
 The GPU box has no /root/reference; the tests there use the committed .npz."""
 import sys
@@ -12,11 +18,17 @@ from pathlib import Path
 import numpy as np
 
 
-def import_reference():
-    nb = types.ModuleType("numba")
-    nb.njit = lambda *a, **k: (a[0] if a and callable(a[0]) else (lambda f: f))
-    nb.prange = range
-    sys.modules.setdefault("numba", nb)
+def import_reference(stub_numba: bool):
+    if stub_numba:
+        nb = types.ModuleType("numba")
+        nb.njit = lambda *a, **k: (a[0] if a and callable(a[0]) else (lambda f: f))
+        nb.prange = range
+        sys.modules["numba"] = nb
+    else:
+        import os
+
+        os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache")  # /root/reference is read-only (cache=True)
+        import numba  # noqa: F401
     for m in ("matplotlib", "matplotlib.pyplot", "matplotlib.animation"):
         sys.modules.setdefault(m, types.ModuleType(m))
     sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
@@ -30,7 +42,8 @@ def import_reference():
 def main():
     import torch
 
-    ref = import_reference()
+    stub = "--no-numba" in sys.argv
+    ref = import_reference(stub)
     out = {}
     # 1. raw lattice function on random points, cell-boundary points and ties
     perm, pgi = ref._init(424242)
@@ -54,7 +67,16 @@ def main():
         out[f"gen_{name}_shape"] = np.array(shape)
         out[f"gen_{name}_t"] = np.array(ts)
         out[f"gen_{name}_noise"] = noise.numpy()
-    np.savez_compressed(Path(__file__).parent / "simplex_golden.npz", **out)
+    path = Path(__file__).parent / "simplex_golden.npz"
+    if "--check" in sys.argv:
+        old = np.load(path)
+        same = all(np.array_equal(old[k], np.asarray(v)) for k, v in out.items() if k != "numba")
+        print("bit-identical to the committed file:", same)
+        sys.exit(0 if same else 1)
+    import numba as _nb
+
+    out["numba"] = np.array("stubbed" if stub else getattr(_nb, "__version__", "?"))
+    np.savez_compressed(path, **out)
     print({k: v.shape for k, v in out.items()})
 
 

@@ -120,3 +120,114 @@ def test_loader_device_ingest_matches_host_loader(tmp_path):
         assert d["image"].is_cuda and d["image"].shape == h["image"].shape
         assert torch.allclose(d["image"].cpu(), h["image"], rtol=0, atol=1e-7)
         assert d["image_meta_dict"] == h["image_meta_dict"]
+
+
+# ------------------------------------------------------------------------------------------------ the reference itself
+T_GRID = [10, 170, 330, 490, 650, 810, 970, 980, 980, 990]  # a skip-1-style tail: t = 980 twice
+
+
+def _write_run(tmp_path, seed, model="fashionmnist_synth"):
+    """results_*.csv files shaped like a reconstruction run's (t-start outer, image inner, pandas index column, a few
+    duplicated rows as the padded multi-GPU partition produces), plus the dense arrays they were made from."""
+    import pandas as pd
+
+    rng = np.random.default_rng(seed)
+    ood_dir = tmp_path / model / "ood"
+    ood_dir.mkdir(parents=True)
+    dense = {}
+    sets = [("val", "val", 40, 0.0), ("in", "in", 33, 0.0), ("MNIST", "out", 29, 0.6),
+            ("FashionMNIST_vflip", "out", 21, 0.3), ("FashionMNIST_hflip", "out", 25, 0.1)]
+    for name, typ, n, shift in sets:
+        a = {k: (rng.gamma(2.0, 0.01 * (1 + shift), size=(len(T_GRID), n)) * (1 + np.arange(len(T_GRID)))[:, None])
+             .astype(np.float32).astype(np.float64) for k in ("mse", "perceptual_difference")}
+        rows = [{"filename": f"{name}_{i:04d}", "type": typ, "t": T_GRID[k], "perceptual_difference":
+                 a["perceptual_difference"][k, i], "mse": a["mse"][k, i]} for k in range(len(T_GRID)) for i in range(n)]
+        rows += [dict(r) for r in rows[:3]]
+        pd.DataFrame(rows).to_csv(ood_dir / f"results_{name}.csv")
+        dense[name] = a
+    return model, dense
+
+
+def _oracle_aucs(dense, min_t, max_t, target="mse"):
+    from oracle import ood_scores
+
+    rows = ood_scores.select_t(T_GRID, min_t, max_t)
+    pick = lambda name: dense[name][target][rows]  # noqa: E731
+    return [ood_scores.ood_auc(pick("val"), pick("in"), pick(o)) for o in ("MNIST", "FashionMNIST_vflip", "FashionMNIST_hflip")]
+
+
+@pytest.mark.parametrize("min_t,max_t", [(0, 1000), (100, 985)])
+def test_oracle_against_the_reference_script_itself(tmp_path, monkeypatch, min_t, max_t):
+    """Executes /root/reference/ood_detection.py's own main() on synthetic CSVs (its third-party imports that are absent
+    here - generative's PNDMScheduler, monai's print_config / set_determinism, matplotlib - are stubbed; none of them
+    touches the score arithmetic) and compares every roc_auc_score it computes with oracle/ood_scores.py."""
+    import importlib.util
+    import sys
+    import types
+    from pathlib import Path
+
+    ref_path = Path("/root/reference/ood_detection.py")
+    if not ref_path.exists():
+        pytest.skip("reference tree not present (GPU box)")
+    from oracle.pndm import PNDMScheduler
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        monkeypatch.setitem(sys.modules, name, m)
+        return m
+
+    mod("generative"); mod("generative.networks")
+    mod("generative.networks.schedulers", PNDMScheduler=PNDMScheduler)
+    mod("monai"); mod("monai.config", print_config=lambda: None); mod("monai.utils", set_determinism=lambda seed=None: None)
+    plt = mod("matplotlib.pyplot", figure=lambda *a, **k: None, plot=lambda *a, **k: None, show=lambda *a, **k: None)
+    mod("matplotlib", pyplot=plt)
+    spec = importlib.util.spec_from_file_location("ref_ood_detection", ref_path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    seen = []
+    real = ref.roc_auc_score
+    monkeypatch.setattr(ref, "roc_auc_score", lambda y, s: seen.append(real(y, s)) or seen[-1])
+
+    model, dense = _write_run(tmp_path, seed=11)
+    ref.main(types.SimpleNamespace(seed=2, output_dir=str(tmp_path), model_name=model, max_t=max_t, min_t=min_t, t_skip=1))
+    want = _oracle_aucs(dense, min_t, max_t)
+    assert len(seen) == 3
+    for got, w in zip(seen, want):
+        assert abs(got - w) < 1e-12, (seen, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("min_t,max_t", [(0, 1000), (100, 985)])
+def test_root_ood_detection_cli_on_device(tmp_path, min_t, max_t):
+    """The repo's ood_detection.py (reference flags, device kernels) against the oracle on the same CSV files, including
+    the duplicated t = 980 column and the t filter."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+    import ood_detection as cli
+
+    model, dense = _write_run(tmp_path, seed=12)
+    res = cli.main(cli.parse_args(["--output_dir", str(tmp_path), "--model_name", model, "--min_t", str(min_t),
+                                   "--max_t", str(max_t)]))
+    want = _oracle_aucs(dense, min_t, max_t)
+    assert res["ood_data"] == ["MNIST", "FashionMNIST_vflip", "FashionMNIST_hflip"]
+    for got, w in zip(res["Zscore_mse"], want):
+        assert abs(got - w) < 2e-3, (res, want)  # fp32 z-scores: only near-tie pairs can flip
+
+
+@pytest.mark.gpu
+def test_device_ood_auc_dedupes_and_filters_t():
+    from ddpm_ood_b200 import ood
+    from oracle import ood_scores
+
+    rng = np.random.default_rng(5)
+    val, ins, outs = (rng.gamma(2.0, 0.01, size=(len(T_GRID), n)).astype(np.float32) for n in (40, 30, 20))
+    outs *= 1.5
+    rows = ood_scores.select_t(T_GRID, 100, 985)
+    assert [T_GRID[i] for i in rows] == [170, 330, 490, 650, 810, 970, 980]
+    want = ood_scores.ood_auc(val[rows].astype(np.float64), ins[rows].astype(np.float64), outs[rows].astype(np.float64))
+    got = ood.ood_auc(*(torch.from_numpy(a).cuda() for a in (val, ins, outs)), t=torch.tensor(T_GRID), min_t=100, max_t=985)
+    assert abs(got - want) < 2e-3

@@ -47,7 +47,7 @@ def test_oracle_against_live_reference_when_present():
     sys.path.insert(0, str(Path(__file__).parent / "golden"))
     from make_simplex_golden import import_reference
 
-    ref = import_reference()
+    ref = import_reference(stub_numba=False)  # the reference's kernels under the real numba JIT
     perm, pgi = ref._init(-31337)
     p, g = osx.tables(-31337)
     rng = np.random.default_rng(5)
