@@ -118,6 +118,7 @@ SIGNATURES = {
     "ddpm_conv_forward": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "ddpm_conv_stats_parts": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "ddpm_conv_halo_stats_parts": (C.c_int, [C.c_int, C.c_int]),
+    "ddpm_conv_halo_stats_parts3": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "ddpm_gn_finalize": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "ddpm_gn_silu": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
@@ -184,7 +185,7 @@ SIGNATURES = {
 }
 
 
-ABI_VERSION = 6  # must equal ddpm_abi_version() of the loaded library (include/ddpm_ood_b200.h DDPM_ABI_VERSION)
+ABI_VERSION = 7  # must equal ddpm_abi_version() of the loaded library (include/ddpm_ood_b200.h DDPM_ABI_VERSION)
 
 
 def _verify(L: C.CDLL) -> None:

@@ -169,6 +169,7 @@ int ddpm_conv_stats_parts(int spatial_dims, int Dout, int Hout, int Wout) {
 }
 
 int ddpm_conv_halo_stats_parts(int Hout, int Wout) { return ddpm::conv_halo_stats_parts(Hout, Wout); }
+int ddpm_conv_halo_stats_parts3(int Dout, int Hout, int Wout) { return ddpm::conv_halo_stats_parts(Hout, Wout, Dout); }
 
 int ddpm_gn_finalize(int C0, const float* st0, int parts0, int C1, const float* st1, int parts1, const float* gamma,
                      const float* beta, float* ab, int N, int S, int groups, float eps, void* stream) {

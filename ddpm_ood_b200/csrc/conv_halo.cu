@@ -163,7 +163,8 @@ __device__ __forceinline__ void xform_row(int tid, int i, bool halo, int& row, i
 template <int BN, int MT, bool PAIR>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     conv_halo_kernel(const __grid_constant__ ConvHaloParams hp) {
-    static_assert(!PAIR || MT == 1, "pair tiles: one M tile per CTA");
+    // PAIR with MT == 2 is the 3-D configuration for 128 output channels: a CTA's two pair tiles are four consecutive depth
+    // slabs of ONE image (the host requires D % 4 == 0), so both share the image's scale/shift and addend rows
     using C = HCfg<BN, MT>;
     const ConvGemmParams& p = hp.g;
     extern __shared__ uint8_t smem_raw[];
@@ -238,8 +239,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 const int t = (m_group * 2 + static_cast<int>(rank)) * MT + mt;  // past-the-end tiles read zeros
-                if (PAIR) {
-                    w0[mt] = 0; h0[mt] = 0; n0[mt] = 2 * t;
+                if (PAIR) {  // w0: image of a 3-D slab pair (0 in 2-D), n0: first slab of the pair inside its image
+                    w0[mt] = hp.slabs > 1 ? (2 * t) / hp.slabs : 0; h0[mt] = 0;
+                    n0[mt] = hp.slabs > 1 ? (2 * t) % hp.slabs : 2 * t;
                 } else {
                     const int n = t / tiles_per_img;
                     const int r = t - n * tiles_per_img;
@@ -252,6 +254,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             for (int st = 0; st < hp.n_stages; ++st) {  // (segment, 64-channel chunk) in the host's schedule order
                 const int seg = hp.sched_seg[st], chunk = hp.sched_chunk[st];
                 const int halo = hp.seg_taps[seg] > 1 ? 1 : 0;
+                const int dd = (PAIR && halo && hp.slabs > 1) ? static_cast<int>(hp.sched_kd[st]) - 1 : 0;  // depth tap
                 const uint32_t bytes = (halo ? (PAIR ? kHaloRowsPair : kHaloRowsRegion) : kTileW * kTileH) * 128u;
                 const CUtensorMap* ma = seg == 0 ? &p.tmA[0] : (seg == 1 ? &p.tmA[1] : &p.tmA[2]);
                 {
@@ -282,8 +285,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 #pragma unroll
                         for (int mt = 0; mt < MT; ++mt) {
                             uint8_t* dst = smem_a + off_bytes + mt * tile_bytes;
-                            if (PAIR)  // tensor map dims (C, W, N, H, 1)
-                                ptx::tma_load_5d(dst, ma, &a_full[slot], chunk * kBlockK, -halo, n0[mt], -halo, 0);
+                            if (PAIR)  // tensor map dims (C, W, N, H, 1), 3-D: (C, W, D, H, N) - a slab out of range is zeros
+                                ptx::tma_load_5d(dst, ma, &a_full[slot], chunk * kBlockK, -halo, n0[mt] + dd, -halo, w0[mt]);
                             else               // tensor map dims (C, W, H, 1, N)
                                 ptx::tma_load_5d(dst, ma, &a_full[slot], chunk * kBlockK, w0[mt] - halo, h0[mt] - halo, 0,
                                                  n0[mt]);
@@ -306,7 +309,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 const int seg = hp.sched_seg[st], chunk = hp.sched_chunk[st];
                 const int taps = hp.seg_taps[seg];
                 {
-                    const int kc = hp.seg_kcol0[seg] + chunk * kBlockK;
+                    const int kc = hp.seg_kcol0[seg] + chunk * kBlockK + static_cast<int>(hp.sched_kd[st]) * 9 * hp.seg_cin[seg];
                     for (int tap = 0; tap < taps; ++tap) {
                         ptx::mbar_wait(&b_empty[sb], pb ^ 1);
                         if (ptx::elect_one()) {
@@ -447,7 +450,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                     if (PAIR) n = 2 * ((m_group * 2 + static_cast<int>(rank)) * MT) + slot;
                     else n = slot < MT ? ((m_group * 2 + static_cast<int>(rank)) * MT + slot) / tiles_per_img : p.N;
                     if (n >= p.N) continue;  // uniform across the transform warps
-                    if (!PAIR && slot == 1 && n == ((m_group * 2 + static_cast<int>(rank)) * MT) / tiles_per_img) {
+                    if (PAIR && hp.slabs > 1) n /= hp.slabs;  // 3-D: slab -> image (both slabs of a pair: the same image)
+                    const bool same_as_slot0 =
+                        PAIR ? hp.slabs > 1 : n == ((m_group * 2 + static_cast<int>(rank)) * MT) / tiles_per_img;
+                    if (slot == 1 && same_as_slot0) {
                         // both tiles lie in the same image: copy slot 0 instead of reducing the statistics twice
                         xsync();
                         for (int c = tid; c < hp.ab_C; c += kXformWarps * 32) s_ab[kMaxGnChannels + c] = s_ab[c];
@@ -482,6 +488,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                         for (int mt = 0; mt < MT; ++mt) {
                             uint32_t off[kRowIters];
                             uint32_t m = halo ? mask_halo[mt] : 0u;
+                            if (PAIR && halo && hp.slabs > 1) {  // 3-D: the depth tap's input slab outside the volume is padding
+                                const int d = tn[mt] % hp.slabs + static_cast<int>(hp.sched_kd[st]) - 1;
+                                if (d < 0 || d >= hp.slabs) m = 0u;
+                            }
 #pragma unroll
                             for (int i = 0; i < kRowIters; ++i) {
                                 int row, hh, ww;
@@ -555,6 +565,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 const int t = (m_group_ * 2 + static_cast<int>(rank)) * MT + (PAIR ? 0 : slot);
                 int n = PAIR ? 2 * t + slot : t / tiles_per_img;
                 if (n >= p.N) n = 0;
+                if (PAIR && hp.slabs > 1) n /= hp.slabs;  // 3-D: slab -> image
 #pragma unroll
                 for (int j = 0; j < BN / 128; ++j) {
                     const int i = et + 128 * j;
@@ -607,7 +618,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 static bool pair_tiles(const ConvProblem& q) { return q.H <= 8 && q.W <= 8; }
 
 bool conv_halo_supported(const ConvProblem& q) {
-    if (q.spatial_dims != 2 || q.D != 1 || q.stride != 1 || q.mode != EPI_STORE || q.b_rows_per_mtile) return false;
+    if (q.stride != 1 || q.mode != EPI_STORE || q.b_rows_per_mtile) return false;
+    if (q.spatial_dims == 3) {
+        // volumes of 8 x 8 slabs: pair tiles of two consecutive depth slabs; a CTA's slabs must lie in one image
+        if (q.H != 8 || q.W != 8 || q.upsample2 || q.Cout % 128 != 0) return false;
+        if (q.D % (q.Cout % 256 == 0 ? 2 : 4) != 0) return false;
+    } else if (q.spatial_dims != 2 || q.D != 1) {
+        return false;
+    }
     if (q.n_seg < 1 || q.n_seg > kMaxSeg) return false;
     if (q.upsample2) {  // nearest x2 + 3x3 conv as four sub-pixel 2x2 phases over the low-resolution tile
         if (q.n_seg != 1 || q.seg[0].ksize != 2 || q.seg[0].channels % kBlockK != 0 || q.residual) return false;
@@ -620,12 +638,12 @@ bool conv_halo_supported(const ConvProblem& q) {
     if (q.Cout % 128 != 0) return false;
     // images up to 8 x 8: a tile is two whole images (one M tile per CTA: 256-wide N tiles only);
     // larger images: a tile is an 8 x 16 region of one image
-    if (pair_tiles(q)) return q.Cout % 256 == 0;
+    if (q.spatial_dims == 2 && pair_tiles(q)) return q.Cout % 256 == 0;
     return true;
 }
 
-int conv_halo_stats_parts(int H, int W) {
-    if (H <= 8 && W <= 8) return 4;
+int conv_halo_stats_parts(int H, int W, int D) {
+    if (H <= 8 && W <= 8) return 4 * (D > 1 ? D : 1);  // one part per epilogue warp of a slab (3-D) / image (2-D)
     return ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH) * 4;
 }
 
@@ -649,15 +667,18 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_cha
         }
     }
     const bool pair = pair_tiles(q);
+    const bool vol = q.spatial_dims == 3;  // pair tiles over the depth slabs of a volume; p.N counts slabs
+    const int kdn = vol ? 3 : 1;           // depth taps of a 3x3(x3) segment
     hp.pair_mode = pair ? 1 : 0;
+    hp.slabs = vol ? q.D : 1;
     p.pair_rows = pair ? 1 : 0;
-    p.N = q.N; p.D = 1; p.H = q.H; p.W = q.W;
+    p.N = vol ? q.N * q.D : q.N; p.D = 1; p.H = q.H; p.W = q.W;
     p.stride = 1;
     p.bw = kTileW; p.bh = kTileH; p.bd = 1; p.bn = 1;
     p.tiles_w = pair ? 1 : (q.W + kTileW - 1) / kTileW;
     p.tiles_h = pair ? 1 : (q.H + kTileH - 1) / kTileH;
     p.tiles_d = 1;
-    p.tiles_n = pair ? (q.N + 1) / 2 : q.N;
+    p.tiles_n = pair ? (p.N + 1) / 2 : q.N;
     p.num_m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     const int BN = (q.Cout % 256 == 0) ? 256 : 128;
     out->block_n = BN;
@@ -673,6 +694,7 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_cha
     p.num_phases = q.upsample2 ? 4 : 1;
     p.phase3d = 0;
     p.stats_out = q.stats_out;
+    // pair tiles: 4 parts per slab / image in the epilogue's indexing ([slab][4] == [image][4 D] in memory)
     p.stats_parts = q.stats_out ? conv_halo_stats_parts(q.H, q.W) * p.num_phases : 0;
     p.n_seg = q.n_seg;
     int kcol = 0, ab_off = 0, kb = 0, c3_off = 0;
@@ -692,17 +714,17 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_cha
         p.seg_chunks[s] = g.channels / kBlockK;
         p.seg_kw[s] = p.seg_kh[s] = g.ksize;
         p.seg_kd[s] = 1;
-        kb += taps * p.seg_chunks[s];
+        kb += taps * (taps == 9 ? kdn : 1) * p.seg_chunks[s];
         p.seg_kb_end[s] = kb;
-        hp.seg_taps[s] = taps;
+        hp.seg_taps[s] = taps;  // in-plane taps of one stage; a 3x3x3 segment has kdn stages per chunk
         if (q.concat3x3 && taps == 9) {
             hp.seg_cin[s] = total3;     // tap stride along K
             hp.seg_kcol0[s] = c3_off;   // channel offset inside the concatenation
-            kcol = 9 * total3;          // 1x1 segments follow the whole 3x3 block
+            kcol = 9 * kdn * total3;    // 1x1 segments follow the whole 3x3(x3) block
         } else {
             hp.seg_cin[s] = g.channels;
             hp.seg_kcol0[s] = kcol;
-            kcol += taps * g.channels;
+            kcol += taps * (taps == 9 ? kdn : 1) * g.channels;
         }
         const bool normalised = gn_ab && (taps == 9 || (gn_on_1x1 && s == 0));
         hp.seg_gn[s] = normalised ? (q.gn_silu ? 1 : 2) : 0;
@@ -713,7 +735,12 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_cha
         const cuuint64_t row_bytes = static_cast<cuuint64_t>(g.channels) * 2;
         cuuint64_t gdim[5], gstr[4];
         cuuint32_t box[5];
-        if (pair) {  // (C, W, N, H, 1): the box interleaves the rows of two images
+        if (vol) {   // (C, W, D, H, N): the box interleaves the rows of two depth slabs; slabs outside [0, D) read zeros
+            gdim[0] = g.channels; gdim[1] = q.W; gdim[2] = q.D; gdim[3] = q.H; gdim[4] = q.N;
+            gstr[0] = row_bytes; gstr[1] = row_bytes * q.W * q.H; gstr[2] = row_bytes * q.W;
+            gstr[3] = row_bytes * q.W * q.H * q.D;
+            box[0] = kBlockK; box[1] = 8 + halo; box[2] = 2; box[3] = 8 + halo; box[4] = 1;
+        } else if (pair) {  // (C, W, N, H, 1): the box interleaves the rows of two images
             gdim[0] = g.channels; gdim[1] = q.W; gdim[2] = q.N; gdim[3] = q.H; gdim[4] = 1;
             gstr[0] = row_bytes; gstr[1] = row_bytes * q.W * q.H; gstr[2] = row_bytes * q.W;
             gstr[3] = row_bytes * q.W * q.H * q.N;
@@ -735,15 +762,21 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_cha
     // them starves the MMA warp (measured: 42 % of the kernel waiting on a_ready with the 1x1 skip segments at the end);
     // spreading them between the heavy chunks lets every refill hide behind 9 taps of work.
     {
-        int heavy_seg[64], heavy_chunk[64], light_seg[64], light_chunk[64], nh = 0, nl = 0;
+        int heavy_seg[64], heavy_chunk[64], heavy_kd[64], light_seg[64], light_chunk[64], nh = 0, nl = 0;
         for (int s = 0; s < q.n_seg; ++s)
-            for (int c = 0; c < p.seg_chunks[s]; ++c) {
-                if (nh + nl >= kMaxStagesPerItem) { set_error("conv_halo: more than %d K stages per item", kMaxStagesPerItem); return 2; }
-                if (hp.seg_taps[s] > 1) { heavy_seg[nh] = s; heavy_chunk[nh++] = c; }
-                else { light_seg[nl] = s; light_chunk[nl++] = c; }
-            }
+            for (int c = 0; c < p.seg_chunks[s]; ++c)
+                for (int kd = 0; kd < (hp.seg_taps[s] == 9 ? kdn : 1); ++kd) {
+                    if (nh + nl >= kMaxStagesPerItem || nh >= 64 || nl >= 64) {
+                        set_error("conv_halo: more than %d K stages per item", kMaxStagesPerItem);
+                        return 2;
+                    }
+                    if (hp.seg_taps[s] > 1) { heavy_seg[nh] = s; heavy_chunk[nh] = c; heavy_kd[nh++] = kd; }
+                    else { light_seg[nl] = s; light_chunk[nl++] = c; }
+                }
+        memset(hp.sched_kd, 0, sizeof(hp.sched_kd));
         int n = 0, li = 0;
         for (int h = 0; h < nh; ++h) {
+            hp.sched_kd[n] = static_cast<uint8_t>(heavy_kd[h]);
             hp.sched_seg[n] = static_cast<uint8_t>(heavy_seg[h]); hp.sched_chunk[n++] = static_cast<uint8_t>(heavy_chunk[h]);
             const int take = (nl - li + (nh - h) - 1) / (nh - h);  // spread the remaining lights over the remaining heavies
             for (int t = 0; t < take; ++t, ++li) {
@@ -811,7 +844,9 @@ int conv_halo_launch(const ConvHaloLaunch& l, cudaStream_t stream) {
                                               HCfg<128, 2>::kSmemBytes);
         cudaError_t e3 = cudaFuncSetAttribute(conv_halo_kernel<256, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               HCfg<256, 1>::kSmemBytes);
-        const cudaError_t es[3] = {e1, e2, e3};
+        cudaError_t e4 = cudaFuncSetAttribute(conv_halo_kernel<128, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              HCfg<128, 2>::kSmemBytes);
+        const cudaError_t es[4] = {e1, e2, e3, e4};
         for (cudaError_t e : es) {
             if (e != cudaSuccess) {
                 set_error("conv_halo: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -821,7 +856,9 @@ int conv_halo_launch(const ConvHaloLaunch& l, cudaStream_t stream) {
         attr_set = true;
     }
     cudaError_t e;
-    if (l.p.pair_mode)
+    if (l.p.pair_mode && l.block_n == 128)  // 3-D volumes, 128 output channels
+        e = launch_pdl(conv_halo_kernel<128, 2, true>, dim3(l.grid), dim3(kThreads), HCfg<128, 2>::kSmemBytes, stream, l.p);
+    else if (l.p.pair_mode)
         e = launch_pdl(conv_halo_kernel<256, 1, true>, dim3(l.grid), dim3(kThreads), HCfg<256, 1>::kSmemBytes, stream, l.p);
     else if (l.block_n == 256)
         e = launch_pdl(conv_halo_kernel<256, 1, false>, dim3(l.grid), dim3(kThreads), HCfg<256, 1>::kSmemBytes, stream, l.p);

@@ -43,6 +43,9 @@ struct ConvHaloParams {
     ConvGemmParams g;         // geometry, K schedule, epilogue, tmA[seg] (haloed / plain boxes), tmB (half weight tile)
     int n_stages;             // K-loop schedule: stage i stages chunk sched_chunk[i] of segment sched_seg[i]
     uint8_t sched_seg[kMaxStagesPerItem], sched_chunk[kMaxStagesPerItem];
+    uint8_t sched_kd[kMaxStagesPerItem];  // 3-D: depth tap (0..2) of a 3x3x3 segment's stage (9 in-plane taps each); else 0
+    int slabs;                // 3-D volumes of 8 x 8 slabs: depth D of an image (a pair tile = two consecutive depth slabs
+                              // of one image, g.N counts slabs); 1 for 2-D problems
     int seg_taps[kMaxSeg];    // 9 or 1
     int seg_cin[kMaxSeg];     // channels of the segment (tap stride along K)
     int seg_kcol0[kMaxSeg];   // first K column of the segment in the weight matrix
@@ -66,10 +69,12 @@ struct ConvHaloLaunch {
     int grid;
 };
 
-// stride-1 2-D problems of 3x3 / 1x1 segments, store epilogue; images of up to 8 x 8 pixels need Cout % 256 == 0
+// stride-1 problems of 3x3 / 1x1 segments, store epilogue. 2-D: any size (images of up to 8 x 8 pixels need
+// Cout % 256 == 0). 3-D: volumes of 8 x 8 slabs (H == W == 8) with D % 4 == 0 (D % 2 == 0 when Cout % 256 == 0): a 3x3x3
+// segment runs as three depth-tap stages per 64 channels, each the nine in-plane taps of one haloed pair tile.
 bool conv_halo_supported(const ConvProblem& q);
-// GroupNorm-statistics parts per image emitted by this kernel's epilogue for an H x W output
-int conv_halo_stats_parts(int H, int W);
+// GroupNorm-statistics parts per image emitted by this kernel's epilogue for a (D x) H x W output
+int conv_halo_stats_parts(int H, int W, int D = 1);
 // gn_ab: null, or the (scale, shift) table [N][gn_ab_channels] applied to the 3x3 segments (channels concatenated in
 // segment order)
 // gn_src (optional, instead of gn_ab): compute the table inside the kernel from producer statistics.

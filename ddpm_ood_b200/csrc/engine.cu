@@ -187,7 +187,7 @@ int UNet::init() {
     if (const char* e = getenv("DDPM_HALO_GN_IN_KERNEL")) halo_gn_in_kernel_ = atoi(e) != 0;  // A/B switch for tests
     if (const char* e = getenv("DDPM_ID_RESIDUAL_MMA")) id_residual_mma_ = atoi(e) != 0;     // A/B switch for tests
     if (const char* e = getenv("DDPM_ATTN_FUSED")) use_attn_fused_ = atoi(e) != 0;            // A/B switch for tests
-    use_halo_ = use_halo_ && fuse_gn_stats_ && c.spatial_dims == 2;
+    use_halo_ = use_halo_ && fuse_gn_stats_;  // 2-D: every stride-1 3x3 conv; 3-D: the levels whose maps are 8 x 8 slabs
     in_gemm_ = (c.in_channels % 64 == 0);
     out_gemm_ = (c.out_channels % 128 == 0);
     if (!in_gemm_ && c.in_channels > 8) { set_error("unet: in_channels=%d unsupported (<=8 or multiple of 64)", c.in_channels); return 2; }
@@ -576,7 +576,7 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
                 if (ch > max_h) max_h = ch;
                 return shape_act(r.cout, h.D, h.H, h.W);
             }
-            const int parts = conv_halo_stats_parts(h.H, h.W);
+            const int parts = conv_halo_stats_parts(h.H, h.W, h.D);
             // GroupNorm statistics are finalised inside the consuming kernel (halo_gn_in_kernel_) or by a tiny launch
             float* ab1 = halo_gn_in_kernel_ ? nullptr : lay.take<float>(static_cast<size_t>(N) * cin * 2);
             float* ab2 = halo_gn_in_kernel_ ? nullptr : lay.take<float>(static_cast<size_t>(N) * r.cout * 2);

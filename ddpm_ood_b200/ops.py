@@ -117,8 +117,10 @@ def conv_stats_parts(spatial_dims: int, d: int, h: int, w: int) -> int:
     return int(lib().ddpm_conv_stats_parts(spatial_dims, d, h, w))
 
 
-def conv_halo_stats_parts(h: int, w: int) -> int:
-    """Parts per image emitted by conv_forward(impl=3, stats_out=...) for an h x w output."""
+def conv_halo_stats_parts(h: int, w: int, d: int = 1) -> int:
+    """Parts per image emitted by conv_forward(impl=3, stats_out=...) for a (d x) h x w output."""
+    if d > 1:
+        return int(lib().ddpm_conv_halo_stats_parts3(d, h, w))
     return int(lib().ddpm_conv_halo_stats_parts(h, w))
 
 

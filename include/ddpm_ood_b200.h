@@ -29,7 +29,7 @@ extern "C" {
 DDPM_API const char* ddpm_last_error(void);
 /* ABI version, bumped on any signature or struct-layout change; the Python binding refuses a library whose version or
  * struct sizes (ddpm_struct_sizes) differ from its own. */
-#define DDPM_ABI_VERSION 6
+#define DDPM_ABI_VERSION 7
 DDPM_API int ddpm_abi_version(void);
 
 /* ------------------------------------------------------------------------------------------------ building block
@@ -89,6 +89,8 @@ DDPM_API int ddpm_conv_forward(const ddpm_conv_args* args, void* stream);
 /* Parts per image that ddpm_conv_forward emits for an output of this geometry (0: unsupported, use ddpm_gn_silu). */
 DDPM_API int ddpm_conv_stats_parts(int spatial_dims, int Dout, int Hout, int Wout);
 DDPM_API int ddpm_conv_halo_stats_parts(int Hout, int Wout);
+/* 3-D volumes of 8 x 8 slabs on the halo kernel (impl 3, spatial_dims 3): parts for a Dout x Hout x Wout output */
+DDPM_API int ddpm_conv_halo_stats_parts3(int Dout, int Hout, int Wout);
 
 /* GroupNorm(groups, eps) (+ SiLU) over the channel concatenation of up to two channels-last fp16 tensors
  * src0 [N,S,C0], src1 [N,S,C1] (or NULL) -> out [N,S,C0+C1] fp16: the norm in front of every conv of

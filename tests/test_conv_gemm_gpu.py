@@ -64,7 +64,8 @@ def _run_case(sd, n, sp, segs, cout, stride=1, use_bias=True, use_cadd=False, us
         ref = ref + _to_ncx(res16)
     st = None
     if stats:
-        st = torch.full((n, ops.conv_halo_stats_parts(sp[0], sp[1]), cout // 4, 2), float("nan"), device=dev)
+        parts = ops.conv_halo_stats_parts(sp[0], sp[1]) if sd == 2 else ops.conv_halo_stats_parts(sp[1], sp[2], sp[0])
+        st = torch.full((n, parts, cout // 4, 2), float("nan"), device=dev)
     out = ops.conv_forward(xs, [k for _, k in segs], wp, cout, stride=stride, bias=bias, chan_add=cadd,
                            residual=res16, impl=impl, stats_out=st,
                            gn_scale_shift=torch.cat(abs_, dim=1).contiguous() if abs_ else None)
@@ -144,6 +145,21 @@ HALO_CASES = {
     "halo_pair_many_items": dict(sd=2, n=333, sp=(8, 8), segs=[(256, 3)], cout=256, use_cadd=True),
     "halo_14px_one_partial_tile_row": dict(sd=2, n=3, sp=(14, 14), segs=[(256, 3)], cout=256),
 }
+
+
+# 3-D volumes of 8 x 8 slabs on the halo kernel: a pair tile is two consecutive depth slabs of one image, a 3x3x3 segment
+# runs as three depth-tap stages per 64 channels (slabs outside the volume are TMA zero fill and stay zero under the
+# on-the-fly GroupNorm). 128 output channels: conv_halo_kernel<128, 2, true> (four slabs per CTA, D % 4 == 0);
+# 256: <256, 1, true> (D % 2 == 0).
+HALO_CASES.update({
+    "halo3d_8vox_128to128": dict(sd=3, n=2, sp=(8, 8, 8), segs=[(128, 3)], cout=128),
+    "halo3d_8vox_odd_n_temb_res": dict(sd=3, n=3, sp=(8, 8, 8), segs=[(128, 3)], cout=128, use_cadd=True, use_res=True),
+    "halo3d_two_3x3x3_inputs_384to128": dict(sd=3, n=2, sp=(8, 8, 8), segs=[(256, 3), (128, 3)], cout=128, use_cadd=True),
+    "halo3d_conv2_plus_1x1_skip": dict(sd=3, n=3, sp=(8, 8, 8), segs=[(128, 3), (256, 1), (128, 1)], cout=128),
+    "halo3d_depth4": dict(sd=3, n=5, sp=(4, 8, 8), segs=[(128, 3)], cout=128, use_res=True),
+    "halo3d_256_out_depth6": dict(sd=3, n=3, sp=(6, 8, 8), segs=[(128, 3)], cout=256, use_cadd=True),
+    "halo3d_many_items": dict(sd=3, n=85, sp=(8, 8, 8), segs=[(128, 3)], cout=128, use_cadd=True),
+})
 
 
 @pytest.mark.parametrize("gn", [False, True], ids=["raw", "gn_silu_on_the_fly"])
