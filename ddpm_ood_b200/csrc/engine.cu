@@ -761,20 +761,23 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
                     q.mode = EPI_STORE;
                     q.bias = L.samp.bias;
                     q.upsample2 = 1;
-                    // (the halo-tile kernel can run this too - all four phases' taps are views of one staged low-resolution
-                    // tile - but measured slower in the chain: with 4 taps per staged tile its items are short and
-                    // epilogue-bound; the im2col-tile kernel runs it. tests/test_conv_gemm_gpu.py still covers that mode.)
+                    // 2-D: on the halo-tile kernel (the four taps of a phase are views of ONE staged low-resolution tile:
+                    // a quarter of the im2col kernel's A traffic). Round 1 measured this slower (short 4-tap items were
+                    // epilogue-bound); with 256-bit epilogue stores and prefetched addends it is +1.7 % on the same box.
+                    static const bool up_halo = !(getenv("DDPM_UPCONV_HALO") && atoi(getenv("DDPM_UPCONV_HALO")) == 0);  // A/B switch
+                    const bool on_halo = up_halo && use_halo_ && conv_halo_supported(q);
                     Act o = shape_act(h.C, h.D * fd, h.H * 2, h.W * 2);
                     if (!measure) {
                         o = new_act(h.C, h.D * fd, h.H * 2, h.W * 2, false);
                         if (fuse_gn_stats_) {
-                            o.parts = conv_stats_parts(sd, h.D, h.H, h.W) * (1 << sd);
+                            o.parts = on_halo ? conv_halo_stats_parts(h.H, h.W) * 4 : conv_stats_parts(sd, h.D, h.H, h.W) * (1 << sd);
                             o.stats = take_stats(h.C, o.parts);
                         }
                     }
                     q.out = o.p;
                     q.stats_out = o.stats;
-                    gemm(q, -1);
+                    if (on_halo && !measure) halo_conv(q, nullptr, 0, -1);
+                    else gemm(q, -1);
                     h = o;
                 } else {
                     const size_t cnt = static_cast<size_t>(N) * (h.D * fd) * (h.H * 2) * (h.W * 2) * h.C;
