@@ -691,7 +691,16 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
         };
 
         // ---- walk
-        Act h = measure ? shape_act(c.num_channels[0], D, H, W) : new_act(c.num_channels[0], D, H, W, in_gemm_);
+        ConvProblem qin{};  // conv_in of wide-channel inputs (latents): one 3x3(x3) conv over the NDHWC fp16 copy of x
+        qin.spatial_dims = sd; qin.N = N; qin.D = D; qin.H = H; qin.W = W; qin.stride = 1; qin.n_seg = 1;
+        qin.seg[0] = {nullptr, c.in_channels, 3};
+        qin.Cout = c.num_channels[0]; qin.mode = EPI_STORE;
+        const bool in_halo = in_gemm_ && use_halo_ && c.in_channels <= 512 && conv_halo_supported(qin);
+        Act h = measure ? shape_act(c.num_channels[0], D, H, W) : new_act(c.num_channels[0], D, H, W, in_gemm_ && !in_halo);
+        if (!measure && in_halo) {
+            h.parts = conv_halo_stats_parts(H, W, D);
+            h.stats = take_stats(c.num_channels[0], h.parts);
+        }
         if (!measure && !in_gemm_ && fuse_gn_stats_ && conv_in_has_stats(c.in_channels, c.num_channels[0], sd)) {
             h.parts = conv_in_stats_parts(D, H, W);
             h.stats = take_stats(c.num_channels[0], h.parts);
@@ -703,14 +712,14 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             op.st0 = h.stats;
             op.flops = 2.0 * N * D * H * W * c.num_channels[0] * (sd == 3 ? 27.0 : 9.0) * c.in_channels;
             op.bytes = static_cast<double>(N) * D * H * W * (4.0 * c.in_channels + 2.0 * c.num_channels[0]);
+            op.on_halo = in_halo;
             if (in_gemm_ && !dry) {
-                ConvProblem q{};
-                q.spatial_dims = sd; q.N = N; q.D = D; q.H = H; q.W = W; q.stride = 1; q.n_seg = 1;
-                q.seg[0] = {plan.x_half, c.in_channels, 3};
-                q.weights = conv_in_wp_; q.w_rows = c.num_channels[0]; q.Cout = c.num_channels[0];
-                q.mode = EPI_STORE; q.bias = conv_in_b_; q.out = h.p;
+                ConvProblem q = qin;
+                q.seg[0].ptr = plan.x_half;
+                q.weights = conv_in_wp_; q.w_rows = c.num_channels[0];
+                q.bias = conv_in_b_; q.out = h.p;
                 q.stats_out = h.stats;
-                int r = conv_prepare(q, sms, &op.conv);
+                int r = in_halo ? conv_halo_prepare(q, nullptr, 0, sms, &op.halo) : conv_prepare(q, sms, &op.conv);
                 if (r && !rc) rc = r;
             }
             plan.ops.push_back(op);
@@ -809,9 +818,13 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             op.dtaps = dtaps;
             op.bytes = static_cast<double>(N) * h.S() * (2.0 * h.C + 36.0 * c.out_channels);
             plan.ops.push_back(op);
-        } else {
-            gn(h, nullptr, out_g_, out_b_, zA, true);
         }
+        ConvProblem qout{};  // conv_out of wide-channel outputs: on the halo kernel the out-norm is applied in shared memory
+        qout.spatial_dims = sd; qout.N = N; qout.D = D; qout.H = H; qout.W = W; qout.stride = 1; qout.n_seg = 1;
+        qout.seg[0] = {nullptr, h.C, 3};
+        qout.Cout = c.out_channels; qout.mode = EPI_STORE;
+        const bool out_halo = out_gemm_ && use_halo_ && h.parts > 0 && h.C <= 512 && conv_halo_supported(qout);
+        if (!out_taps && !out_halo) gn(h, nullptr, out_g_, out_b_, zA, true);
         if (!measure) {
             plan.z_out = zA;
             Op op{};
@@ -820,13 +833,15 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             op.src0 = zA; op.D = D; op.H = H; op.W = W; op.C = h.C;
             op.flops = 2.0 * N * D * H * W * c.out_channels * (sd == 3 ? 27.0 : 9.0) * h.C;
             op.bytes = static_cast<double>(N) * D * H * W * (2.0 * h.C + 4.0 * c.out_channels);
+            op.on_halo = out_halo;
             if (out_gemm_ && !dry) {
-                ConvProblem q{};
-                q.spatial_dims = sd; q.N = N; q.D = D; q.H = H; q.W = W; q.stride = 1; q.n_seg = 1;
-                q.seg[0] = {zA, h.C, 3};
-                q.weights = conv_out_wp_; q.w_rows = c.out_channels; q.Cout = c.out_channels;
-                q.mode = EPI_STORE; q.bias = conv_out_b_; q.out = plan.y_half;
-                int r = conv_prepare(q, sms, &op.conv);
+                ConvProblem q = qout;
+                q.seg[0].ptr = out_halo ? h.p : zA;
+                q.weights = conv_out_wp_; q.w_rows = c.out_channels;
+                q.bias = conv_out_b_; q.out = plan.y_half;
+                q.gn_silu = 1;
+                const HaloGnSource src = gn_source(h, nullptr, out_g_, out_b_);
+                int r = out_halo ? conv_halo_prepare(q, nullptr, h.C, sms, &op.halo, &src) : conv_prepare(q, sms, &op.conv);
                 if (r && !rc) rc = r;
             }
             plan.ops.push_back(op);
@@ -907,7 +922,7 @@ int UNet::forward(const float* x, const long long* timesteps, int t_uniform, flo
                 break;
             case Op::CONV_IN_GEMM:
                 rc = nchw_to_nhwc_half(x, plan.x_half, N, c.in_channels, S, stream);
-                if (!rc) rc = conv_launch(op.conv, stream);
+                if (!rc) rc = op.on_halo ? conv_halo_launch(op.halo, stream) : conv_launch(op.conv, stream);
                 ++launches_;
                 break;
             case Op::GN:
@@ -959,7 +974,7 @@ int UNet::forward(const float* x, const long long* timesteps, int t_uniform, flo
                                     c.spatial_dims, plms, ring, stash, sample, stream);
                 break;
             case Op::CONV_OUT_GEMM: {
-                rc = conv_launch(op.conv, stream);
+                rc = op.on_halo ? conv_halo_launch(op.halo, stream) : conv_launch(op.conv, stream);
                 if (rc) break;
                 float* eps = out ? out
                                  : (plms && !plms->push) ? plan.eps_tmp

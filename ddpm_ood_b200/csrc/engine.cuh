@@ -90,7 +90,8 @@ struct Op {
     float* ab;  // GN_FINALIZE: destination table [N][C0 + C1][2]
     // GEMM
     ConvLaunch conv;
-    ConvHaloLaunch halo;  // CONV_HALO
+    ConvHaloLaunch halo;  // CONV_HALO; CONV_IN_GEMM / CONV_OUT_GEMM with on_halo
+    bool on_halo;         // CONV_IN_GEMM / CONV_OUT_GEMM: `halo` instead of `conv` (wide-channel 3-D latents at 8 x 8 slabs)
     bool uses_temb;
     int temb_off;
     // ATTN

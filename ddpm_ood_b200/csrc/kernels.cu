@@ -337,13 +337,17 @@ int time_proj_all(const float* act, int R, int K, const float* wcat, const float
 }
 
 // ------------------------------------------------------------------------------------------------ attention core
-// Generic-T attention on CUDA cores (fp32 math, fp16 I/O): one CTA per (16 queries, image*head). The score row lives
-// in shared memory, K and V stream through a 64-key staging tile. Head dim fixed at 256 (num_head_channels=256 in both
-// reference configurations, src/trainers/base.py:73,84).
-constexpr int kHD = 256, kQT = 16, kKT = 64, kPadHD = kHD + 8;
+// Generic-T attention on CUDA cores (fp32 math, fp16 I/O): one CTA per (4 * QPG queries, image*head). The score rows
+// live in shared memory, K and V stream through a 64-key staging tile. Head dim fixed at 256 (num_head_channels=256 in
+// both reference configurations, src/trainers/base.py:73,84). QPG = 4 (16 queries per CTA) up to T = 2816 tokens; fewer
+// queries per CTA (QPG 2 / 1) keep the fp32 score rows inside shared memory for the 4096-token level-0 attention of
+// `--model_type big` on 64 x 64 images (T <= 5632 / 11264).
+constexpr int kHD = 256, kKT = 64, kPadHD = kHD + 8;
 
+template <int QPG>
 __global__ void __launch_bounds__(256) attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int T,
                                                         int C, int heads, float scale) {
+    constexpr int kQT = 4 * QPG;
     extern __shared__ __align__(16) uint8_t smem_att[];
     __half* q_s = reinterpret_cast<__half*>(smem_att);                 // [kQT][kPadHD]
     __half* kv_s = q_s + kQT * kPadHD;                                 // [kKT][kPadHD]
@@ -375,22 +379,24 @@ __global__ void __launch_bounds__(256) attention_kernel(const __half* __restrict
             *reinterpret_cast<uint4*>(kv_s + r * kPadHD + cv * 8) = val;
         }
         __syncthreads();
-        const int j = tid % kKT, qg = tid / kKT;  // 4 query groups x 4 queries
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const int j = tid % kKT, qg = tid / kKT;  // 4 query groups x QPG queries
+        float acc[QPG];
+#pragma unroll
+        for (int qq = 0; qq < QPG; ++qq) acc[qq] = 0.f;
         for (int d = 0; d < kHD; d += 8) {
             float kf[8];
             unpack8(*reinterpret_cast<const uint4*>(kv_s + j * kPadHD + d), kf);
 #pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
+            for (int qq = 0; qq < QPG; ++qq) {
                 float qf[8];
-                unpack8(*reinterpret_cast<const uint4*>(q_s + (qg * 4 + qq) * kPadHD + d), qf);
+                unpack8(*reinterpret_cast<const uint4*>(q_s + (qg * QPG + qq) * kPadHD + d), qf);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) acc[qq] += qf[e] * kf[e];
             }
         }
         if (k0 + j < T) {
 #pragma unroll
-            for (int qq = 0; qq < 4; ++qq) s_s[(qg * 4 + qq) * Tp + k0 + j] = acc[qq] * scale;
+            for (int qq = 0; qq < QPG; ++qq) s_s[(qg * QPG + qq) * Tp + k0 + j] = acc[qq] * scale;
         }
     }
     __syncthreads();
@@ -415,11 +421,12 @@ __global__ void __launch_bounds__(256) attention_kernel(const __half* __restrict
             for (int jx = lane; jx < T; jx += 32) row[jx] *= inv;
         }
     }
-    // phase 3: O = P V ; thread -> 2 channels x 8 queries
+    // phase 3: O = P V ; thread -> 2 channels x (2 * QPG) queries
+    constexpr int kQ3 = 2 * QPG;
     const int c2 = tid % (kHD / 2), qg2 = tid / (kHD / 2);
-    float o_acc[8][2];
+    float o_acc[kQ3][2];
 #pragma unroll
-    for (int qq = 0; qq < 8; ++qq) { o_acc[qq][0] = 0.f; o_acc[qq][1] = 0.f; }
+    for (int qq = 0; qq < kQ3; ++qq) { o_acc[qq][0] = 0.f; o_acc[qq][1] = 0.f; }
     for (int k0 = 0; k0 < T; k0 += kKT) {
         __syncthreads();
         for (int i = tid; i < kKT * (kHD / 8); i += blockDim.x) {
@@ -433,16 +440,16 @@ __global__ void __launch_bounds__(256) attention_kernel(const __half* __restrict
         for (int jx = 0; jx < kmax; ++jx) {
             const float2 vv = __half22float2(*reinterpret_cast<const __half2*>(kv_s + jx * kPadHD + 2 * c2));
 #pragma unroll
-            for (int qq = 0; qq < 8; ++qq) {
-                const float pj = s_s[(qg2 * 8 + qq) * Tp + k0 + jx];
+            for (int qq = 0; qq < kQ3; ++qq) {
+                const float pj = s_s[(qg2 * kQ3 + qq) * Tp + k0 + jx];
                 o_acc[qq][0] += pj * vv.x;
                 o_acc[qq][1] += pj * vv.y;
             }
         }
     }
 #pragma unroll
-    for (int qq = 0; qq < 8; ++qq) {
-        const int qrow = q0 + qg2 * 8 + qq;
+    for (int qq = 0; qq < kQ3; ++qq) {
+        const int qrow = q0 + qg2 * kQ3 + qq;
         if (qrow < T) {
             __half2 hv = __floats2half2_rn(o_acc[qq][0], o_acc[qq][1]);
             *reinterpret_cast<__half2*>(out + (static_cast<size_t>(n) * T + qrow) * C + head * kHD + 2 * c2) = hv;
@@ -453,17 +460,22 @@ __global__ void __launch_bounds__(256) attention_kernel(const __half* __restrict
 int attention_core(const __half* qkv, __half* out, int N, int T, int C, int heads, float scale, cudaStream_t stream) {
     if (C != heads * kHD) { set_error("attention_core: head dim %d unsupported (need 256)", heads ? C / heads : 0); return 2; }
     const int Tp = (T + 3) & ~3;
-    const size_t smem = static_cast<size_t>(kQT + kKT) * kPadHD * sizeof(__half) + static_cast<size_t>(kQT) * Tp * sizeof(float);
-    if (smem > 220 * 1024) { set_error("attention_core: T=%d too large", T); return 2; }
-    static size_t smem_set_dev[kMaxDevices] = {};
-    size_t& smem_set = smem_set_dev[device_slot()];
+    auto smem_for = [&](int qt) {
+        return static_cast<size_t>(qt + kKT) * kPadHD * sizeof(__half) + static_cast<size_t>(qt) * Tp * sizeof(float);
+    };
+    const int qpg = smem_for(16) <= 220 * 1024 ? 4 : (smem_for(8) <= 220 * 1024 ? 2 : 1);
+    const size_t smem = smem_for(4 * qpg);
+    if (smem > 220 * 1024) { set_error("attention_core: T=%d tokens exceed the %d this kernel holds score rows for", T, 11264); return 2; }
+    static size_t smem_set_dev[3][kMaxDevices] = {};
+    size_t& smem_set = smem_set_dev[qpg == 4 ? 0 : (qpg == 2 ? 1 : 2)][device_slot()];
+    auto kernel = qpg == 4 ? attention_kernel<4> : (qpg == 2 ? attention_kernel<2> : attention_kernel<1>);
     if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) { set_error("attention_core: %s", cudaGetErrorString(e)); return 4; }
         smem_set = smem;
     }
-    dim3 grid((T + kQT - 1) / kQT, N * heads);
-    attention_kernel<<<grid, 256, smem, stream>>>(qkv, out, T, C, heads, scale);
+    dim3 grid((T + 4 * qpg - 1) / (4 * qpg), N * heads);
+    kernel<<<grid, 256, smem, stream>>>(qkv, out, T, C, heads, scale);
     DDPM_CHECK_LAUNCH("attention_core");
     return 0;
 }

@@ -32,6 +32,20 @@ def test_attention_matches_torch(n, t, heads, impl):
     assert err < 4e-3, (n, t, heads, impl, err)
 
 
+@pytest.mark.parametrize("t", [1000, 4096])
+def test_attention_generic_kernel_large_token_counts(t):
+    """The CUDA-core fallback beyond the tcgen05 kernels' shapes: T = 4096 is the level-0 attention of `--model_type big`
+    (attention at every level, src/trainers/base.py:77-86) on 64 x 64 images; fewer queries per CTA keep the fp32 score
+    rows in shared memory."""
+    from ddpm_ood_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(t)
+    qkv = (torch.randn((2 * t, 3 * 256), generator=g, device="cuda") * 1.2).half()
+    got = ops.attention(qkv, 2, t, 1, 1.0 / 256 ** 0.5, 1).float()
+    err = (got - _ref(qkv, 2, t, 1)).abs().max().item()
+    assert err < 4e-3, (t, err)
+
+
 # ------------------------------------------------------------------------------------------------ fused AttentionBlock
 def _block_ref(h, n, t, gamma, beta, wqkv, bqkv, wproj, bproj, eps=1e-6):
     """fp32 PyTorch AttentionBlock on the same fp16 inputs / weights (oracle/unet.py:AttentionBlock, one head)."""
