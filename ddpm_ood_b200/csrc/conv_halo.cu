@@ -247,7 +247,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     // back (L2 hits)
     const int total_items = gpp * p.num_phases * p.num_n_tiles;
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-    const int tiles_per_img = p.tiles_w * p.tiles_h;
+    const int tiles_per_slab = p.tiles_w * p.tiles_h;
+    const int tiles_per_img = tiles_per_slab * p.tiles_d;  // region tiles of a 3-D volume: tile order (w, h, depth slab, image)
 
     if (warp == kWarpA) {
         HALO_REG_DEC();
@@ -257,16 +258,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         long long cyc_prod = 0;
         for (int item = cluster_id; item < total_items; item += num_clusters) {
             const int m_group = item / (p.num_n_tiles * p.num_phases);
-            int w0[MT], h0[MT], n0[MT];
+            int w0[MT], h0[MT], n0[MT], d0[MT];
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 const int t = (m_group * 2 + static_cast<int>(rank)) * MT + mt;  // past-the-end tiles read zeros
+                d0[mt] = 0;
                 if (PAIR) {  // w0: image of a 3-D slab pair (0 in 2-D), n0: first slab of the pair inside its image
                     w0[mt] = hp.slabs > 1 ? (2 * t) / hp.slabs : 0; h0[mt] = 0;
                     n0[mt] = hp.slabs > 1 ? (2 * t) % hp.slabs : 2 * t;
                 } else {
                     const int n = t / tiles_per_img;
-                    const int r = t - n * tiles_per_img;
+                    int r = t - n * tiles_per_img;
+                    d0[mt] = r / tiles_per_slab;
+                    r -= d0[mt] * tiles_per_slab;
                     const int th = r / p.tiles_w;
                     w0[mt] = (r - th * p.tiles_w) * kTileW;
                     h0[mt] = th * kTileH;
@@ -276,7 +280,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             for (int st = 0; st < hp.n_stages; ++st) {  // (segment, 64-channel chunk) in the host's schedule order
                 const int seg = hp.sched_seg[st], chunk = hp.sched_chunk[st];
                 const int halo = hp.seg_taps[seg] > 1 ? 1 : 0;
-                const int dd = (PAIR && halo && hp.slabs > 1) ? static_cast<int>(hp.sched_kd[st]) - 1 : 0;  // depth tap
+                const int dd = (halo && hp.slabs > 1) ? static_cast<int>(hp.sched_kd[st]) - 1 : 0;  // depth tap
                 const uint32_t bytes = (halo ? (PAIR ? kHaloRowsPair : kHaloRowsRegion) : kTileW * kTileH) * 128u;
                 const CUtensorMap* ma = seg == 0 ? &p.tmA[0] : (seg == 1 ? &p.tmA[1] : &p.tmA[2]);
                 {
@@ -309,9 +313,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                             uint8_t* dst = smem_a + off_bytes + mt * tile_bytes;
                             if (PAIR)  // tensor map dims (C, W, N, H, 1), 3-D: (C, W, D, H, N) - a slab out of range is zeros
                                 ptx::tma_load_5d(dst, ma, &a_full[slot], chunk * kBlockK, -halo, n0[mt] + dd, -halo, w0[mt]);
-                            else               // tensor map dims (C, W, H, 1, N)
-                                ptx::tma_load_5d(dst, ma, &a_full[slot], chunk * kBlockK, w0[mt] - halo, h0[mt] - halo, 0,
-                                                 n0[mt]);
+                            else               // tensor map dims (C, W, H, D, N) (D == 1 in 2-D)
+                                ptx::tma_load_5d(dst, ma, &a_full[slot], chunk * kBlockK, w0[mt] - halo, h0[mt] - halo,
+                                                 d0[mt] + dd, n0[mt]);
                         }
                     }
                     __syncwarp();
@@ -440,15 +444,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             const int m_group = item / (p.num_n_tiles * p.num_phases);
             // validity of this thread's rows of a HALOED tile (zero padding must stay zero), per M tile
             uint32_t mask_halo[MT];
-            int tn[MT], th0[MT], tw0[MT];
+            int tn[MT], th0[MT], tw0[MT], td0[MT];
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 const int t = (m_group * 2 + static_cast<int>(rank)) * MT + mt;
+                td0[mt] = 0;
                 if (PAIR) {
                     tn[mt] = 2 * t + (tid >> 7); th0[mt] = 0; tw0[mt] = 0;
                 } else {
                     const int n = t / tiles_per_img;
-                    const int r = t - n * tiles_per_img;
+                    int r = t - n * tiles_per_img;
+                    td0[mt] = r / tiles_per_slab;
+                    r -= td0[mt] * tiles_per_slab;
                     const int th = r / p.tiles_w;
                     tn[mt] = n; th0[mt] = th * kTileH; tw0[mt] = (r - th * p.tiles_w) * kTileW;
                 }
@@ -515,8 +522,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                         for (int mt = 0; mt < MT; ++mt) {
                             uint32_t off[kRowIters];
                             uint32_t m = halo ? mask_halo[mt] : 0u;
-                            if (PAIR && halo && hp.slabs > 1) {  // 3-D: the depth tap's input slab outside the volume is padding
-                                const int d = tn[mt] % hp.slabs + static_cast<int>(hp.sched_kd[st]) - 1;
+                            if (halo && hp.slabs > 1) {  // 3-D: the depth tap's input slab outside the volume is padding
+                                const int d = (PAIR ? tn[mt] % hp.slabs : td0[mt]) + static_cast<int>(hp.sched_kd[st]) - 1;
                                 if (d < 0 || d >= hp.slabs) m = 0u;
                             }
 #pragma unroll
@@ -656,9 +663,13 @@ static bool pair_tiles(const ConvProblem& q) { return q.H <= 8 && q.W <= 8; }
 bool conv_halo_supported(const ConvProblem& q) {
     if (q.stride != 1 || q.mode != EPI_STORE || q.b_rows_per_mtile) return false;
     if (q.spatial_dims == 3) {
-        // volumes of 8 x 8 slabs: pair tiles of two consecutive depth slabs; a CTA's slabs must lie in one image
-        if (q.H != 8 || q.W != 8 || q.upsample2 || q.Cout % 128 != 0) return false;
-        if (q.D % (q.Cout % 256 == 0 ? 2 : 4) != 0) return false;
+        if (q.upsample2 || q.Cout % 128 != 0) return false;
+        if (q.H == 8 && q.W == 8) {
+            // volumes of 8 x 8 slabs: pair tiles of two consecutive depth slabs; a CTA's slabs must lie in one image
+            if (q.D % (q.Cout % 256 == 0 ? 2 : 4) != 0) return false;
+        } else if (q.H <= 8 && q.W <= 8) {
+            return false;  // smaller slabs would leave most rows of a pair tile empty: the im2col-tile kernel runs them
+        }                  // larger slabs: 8 x 16 region tiles of one depth slab
     } else if (q.spatial_dims != 2 || q.D != 1) {
         return false;
     }
@@ -680,7 +691,7 @@ bool conv_halo_supported(const ConvProblem& q) {
 
 int conv_halo_stats_parts(int H, int W, int D) {
     if (H <= 8 && W <= 8) return 4 * (D > 1 ? D : 1);  // one part per epilogue warp of a slab (3-D) / image (2-D)
-    return ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH) * 4;
+    return ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH) * 4 * (D > 1 ? D : 1);
 }
 
 int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_channels, int num_sms, ConvHaloLaunch* out,
@@ -708,14 +719,15 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_cha
     hp.pair_mode = pair ? 1 : 0;
     hp.slabs = vol ? q.D : 1;
     p.pair_rows = pair ? 1 : 0;
-    p.N = vol ? q.N * q.D : q.N; p.D = 1; p.H = q.H; p.W = q.W;
+    const bool vol_pair = vol && pair;     // pair tiles index depth slabs as images (p.N counts slabs)
+    p.N = vol_pair ? q.N * q.D : q.N; p.D = vol_pair ? 1 : q.D; p.H = q.H; p.W = q.W;
     p.stride = 1;
     p.bw = kTileW; p.bh = kTileH; p.bd = 1; p.bn = 1;
     p.tiles_w = pair ? 1 : (q.W + kTileW - 1) / kTileW;
     p.tiles_h = pair ? 1 : (q.H + kTileH - 1) / kTileH;
-    p.tiles_d = 1;
+    p.tiles_d = p.D;  // region tiles of a volume: one depth slab per tile
     p.tiles_n = pair ? (p.N + 1) / 2 : q.N;
-    p.num_m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    p.num_m_tiles = p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
     const int BN = (q.Cout % 256 == 0) ? 256 : 128;
     out->block_n = BN;
     out->m_tiles_per_cta = BN == 256 ? 1 : 2;
@@ -726,12 +738,15 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_cha
     p.chan_add = q.chan_add;
     p.chan_add_stride = q.chan_add_stride;
     p.residual = static_cast<const __half*>(q.residual);
+    p.relu = q.relu;                                            // VQ-VAE convs: ReLU after bias / residual
+    p.out_lo = static_cast<__half*>(q.out_lo);                  // split-precision activations (VQ-VAE encoder)
+    p.residual_lo = static_cast<const __half*>(q.residual_lo);
     p.out = static_cast<__half*>(q.out);
     p.num_phases = q.upsample2 ? 4 : 1;
     p.phase3d = 0;
     p.stats_out = q.stats_out;
     // pair tiles: 4 parts per slab / image in the epilogue's indexing ([slab][4] == [image][4 D] in memory)
-    p.stats_parts = q.stats_out ? conv_halo_stats_parts(q.H, q.W) * p.num_phases : 0;
+    p.stats_parts = q.stats_out ? conv_halo_stats_parts(q.H, q.W, vol_pair ? 1 : q.D) * p.num_phases : 0;
     p.n_seg = q.n_seg;
     int kcol = 0, ab_off = 0, kb = 0, c3_off = 0;
     int total3 = 0;  // channels of all 3x3 segments
@@ -771,7 +786,7 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_cha
         const cuuint64_t row_bytes = static_cast<cuuint64_t>(g.channels) * 2;
         cuuint64_t gdim[5], gstr[4];
         cuuint32_t box[5];
-        if (vol) {   // (C, W, D, H, N): the box interleaves the rows of two depth slabs; slabs outside [0, D) read zeros
+        if (vol_pair) {   // (C, W, D, H, N): the box interleaves the rows of two depth slabs; slabs outside [0, D) read zeros
             gdim[0] = g.channels; gdim[1] = q.W; gdim[2] = q.D; gdim[3] = q.H; gdim[4] = q.N;
             gstr[0] = row_bytes; gstr[1] = row_bytes * q.W * q.H; gstr[2] = row_bytes * q.W;
             gstr[3] = row_bytes * q.W * q.H * q.D;
@@ -781,9 +796,9 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_cha
             gstr[0] = row_bytes; gstr[1] = row_bytes * q.W * q.H; gstr[2] = row_bytes * q.W;
             gstr[3] = row_bytes * q.W * q.H * q.N;
             box[0] = kBlockK; box[1] = 8 + halo; box[2] = 2; box[3] = 8 + halo; box[4] = 1;
-        } else {     // (C, W, H, 1, N)
-            gdim[0] = g.channels; gdim[1] = q.W; gdim[2] = q.H; gdim[3] = 1; gdim[4] = q.N;
-            gstr[0] = row_bytes; gstr[1] = row_bytes * q.W; gstr[2] = row_bytes * q.W * q.H; gstr[3] = gstr[2];
+        } else {     // (C, W, H, D, N), D == 1 in 2-D; a depth slab outside [0, D) reads zeros
+            gdim[0] = g.channels; gdim[1] = q.W; gdim[2] = q.H; gdim[3] = q.D; gdim[4] = q.N;
+            gstr[0] = row_bytes; gstr[1] = row_bytes * q.W; gstr[2] = row_bytes * q.W * q.H; gstr[3] = gstr[2] * q.D;
             box[0] = kBlockK; box[1] = kTileW + halo; box[2] = kTileH + halo; box[3] = 1; box[4] = 1;
         }
         cuuint32_t estr[5] = {1, 1, 1, 1, 1};

@@ -1,6 +1,7 @@
 // VQ-VAE encode / quantise / decode engine. See vqvae.cuh.
 #include "vqvae.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include "launch.cuh"
@@ -473,11 +474,20 @@ int VqVae::build(Plan& plan, bool decode, int N, int D, int H, int W, void* ws, 
     const int sms = num_sms();
     int rc = 0;
     plan.ops.clear();
+    static const bool halo_off = getenv("DDPM_VQ_HALO") && atoi(getenv("DDPM_VQ_HALO")) == 0;  // A/B switch for tests
     auto gemm = [&](ConvProblem q) {
         Op op{};
-        op.type = Op::GEMM;
-        int r = conv_prepare(q, sms, &op.conv);
-        if (r && !rc) rc = r;
+        // stride-1 3x3(x3) convs (residual units, the latent-side convs): the halo-tile kernel stages each input tile once
+        // for all of its taps where it supports the geometry (2-D; 3-D slabs of 8 x 8 or larger); no GroupNorm here
+        bool all3 = q.stride == 1 && !q.upsample2 && q.mode == EPI_STORE;
+        for (int i = 0; i < q.n_seg; ++i) all3 = all3 && q.seg[i].ksize == 3;
+        if (all3 && !halo_off && conv_halo_supported(q) && conv_halo_prepare(q, nullptr, 0, sms, &op.halo) == 0) {
+            op.type = Op::HALO;  // (a geometry the kernel cannot stage - too many K stages per item - takes the GEMM path)
+        } else {
+            op.type = Op::GEMM;
+            int r = conv_prepare(q, sms, &op.conv);
+            if (r && !rc) rc = r;
+        }
         plan.ops.push_back(op);
     };
     // in_lo != null: split-precision operands, K segments [in | in_lo | in] against weight rows [hi | hi | lo]
@@ -611,6 +621,9 @@ int VqVae::run(const Plan& plan, cudaStream_t stream) {
             }
             case Op::GEMM:
                 rc = conv_launch(op.conv, stream);
+                break;
+            case Op::HALO:
+                rc = conv_halo_launch(op.halo, stream);
                 break;
             case Op::QUANT_HALF:
             case Op::QUANT_ROWS_F32: {

@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "conv_gemm.cuh"
+#include "conv_halo.cuh"
 
 namespace ddpm {
 
@@ -67,8 +68,9 @@ class VqVae {
     struct EncLevel { __half* w; float* b; int Cin, Cout; std::vector<Res> res; };
     struct DecLevel { std::vector<Res> res; __half* w; float* b; int Cin, Cout; bool last; };
     struct Op {
-        enum Type { IM2COL, GEMM, QUANT_HALF, QUANT_ROWS_F32, QUANT_NCHW, GATHER } type;
+        enum Type { IM2COL, GEMM, HALO, QUANT_HALF, QUANT_ROWS_F32, QUANT_NCHW, GATHER } type;
         ConvLaunch conv;
+        ConvHaloLaunch halo;  // HALO: stride-1 3x3(x3) convs on the halo-tile kernel where it supports the geometry
         // IM2COL / GATHER / QUANT geometry
         const void* src; void* dst; void* dst2; int* idx;
         int N, C, D, H, W, K;

@@ -159,6 +159,10 @@ HALO_CASES.update({
     "halo3d_depth4": dict(sd=3, n=5, sp=(4, 8, 8), segs=[(128, 3)], cout=128, use_res=True),
     "halo3d_256_out_depth6": dict(sd=3, n=3, sp=(6, 8, 8), segs=[(128, 3)], cout=256, use_cadd=True),
     "halo3d_many_items": dict(sd=3, n=85, sp=(8, 8, 8), segs=[(128, 3)], cout=128, use_cadd=True),
+    # slabs larger than 8 x 8: 8 x 16 region tiles of one depth slab (the VQ-VAE's residual units, larger latents)
+    "halo3d_region_16px_slabs": dict(sd=3, n=2, sp=(4, 16, 16), segs=[(128, 3)], cout=256, use_cadd=True, use_res=True),
+    "halo3d_region_ragged_20x12": dict(sd=3, n=3, sp=(3, 20, 12), segs=[(128, 3), (64, 3)], cout=128),
+    "halo3d_region_plus_1x1_skip": dict(sd=3, n=2, sp=(5, 16, 16), segs=[(128, 3), (128, 1)], cout=128, use_res=True),
 })
 
 

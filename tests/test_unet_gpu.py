@@ -70,11 +70,14 @@ def test_forward_big_model_matches_oracle(shape):
     assert rel < 4e-3, rel
 
 
-def test_forward_3d_latent():
+@pytest.mark.parametrize("shape", [(2, 128, 8, 8, 8), (1, 128, 4, 16, 16)])
+def test_forward_3d_latent(shape):
+    """3-D latent UNet: 8 x 8 x 8 (BASELINE config 5's latent: the first level runs on pair tiles of two depth slabs) and
+    a 4 x 16 x 16 latent (region tiles of one 16 x 16 slab at the first level, pair tiles of 8 x 8 slabs at the second)."""
     ref, ours = _pair(3, 128, seed=3)
     g = torch.Generator().manual_seed(11)
-    x = torch.randn((2, 128, 8, 8, 8), generator=g)
-    t = torch.tensor([10, 900])
+    x = torch.randn(shape, generator=g)
+    t = torch.tensor([10, 900])[:shape[0]]
     with torch.no_grad():
         want = ref(x, t)
     got = ours(x.cuda(), timesteps=t.cuda()).cpu()
