@@ -49,6 +49,16 @@ WORKLOADS = {
                      label="CelebA-shaped 3x64x64 (BASELINE configs[3])"),
     "brats_latent": dict(sd=3, ch=128, size=(8, 8, 8), steps=100, skip=4, run_skip=4, batch=592,
                          label="BraTS LDM latent 128x8x8x8, 3-D UNet (BASELINE configs[4], latent side)"),
+    # config 5 from IMAGES: VQ-VAE encode once per batch, 3-D latent chains, VQ-VAE decode + MSE + per-item 2.5-D LPIPS per
+    # t-start (src/trainers/reconstruct.py:124,166,181-187). The VQ-VAE is the reference's README configuration
+    # (README.md:153-159); 128^3 volumes give the 8^3 latent of the config (its 160x160x128 crops need --latent_pad).
+    "brats_ldm": dict(sd=3, ch=128, size=(8, 8, 8), steps=100, skip=4, run_skip=4, batch=4, image_ch=1,
+                      image_size=(128, 128, 128),
+                      vqvae=dict(spatial_dims=3, in_channels=1, out_channels=1, num_channels=[256] * 4, num_res_layers=3,
+                                 num_res_channels=[256] * 4, downsample_parameters=[[2, 4, 1, 1]] * 4,
+                                 upsample_parameters=[[2, 4, 1, 1, 0]] * 4, num_embeddings=2048, embedding_dim=128),
+                      label="BraTS-shaped 1x128x128x128 volumes through the README VQ-VAE to 128x8x8x8 latents "
+                            "(BASELINE configs[4] from images)"),
 }
 
 
@@ -279,15 +289,22 @@ def run_ours(args):
     model = model.to(dev).eval()
     import warnings
 
+    vq = None
+    if w.get("vqvae"):
+        from ddpm_ood_b200.vqvae import VQVAE
+
+        torch.manual_seed(0)
+        vq = VQVAE(**w["vqvae"]).to(dev).eval()
+    img_ch, img_size = w.get("image_ch", w["ch"]), tuple(w.get("image_size", w["size"]))
     pl = None  # a 128-channel latent is not an LPIPS input: the latent workload scores MSE only
-    if w["ch"] <= 3:
+    if img_ch <= 3:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             pl = PerceptualLoss(dimensions=w["sd"], include_pixel_loss=False, is_fake_3d=(w["sd"] == 3),
                                 lpips_normalize=True, spatial=False, allow_synthetic_weights=True).to(dev)
     cfg = ReconConfig(beta_schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0195,
                       plms_state=args.plms_state, num_inference_steps=w["steps"], spatial_dimension=w["sd"])
-    eng = BatchReconstructor(model, pl, cfg, dev)
+    eng = BatchReconstructor(model, pl, cfg, dev, vqvae_model=vq)
     B = args.batch
     chains = _chains(args)
     n_t = len(chains)
@@ -295,7 +312,7 @@ def run_ours(args):
     # images sharded (weak scaling): every rank its own batch; t-starts sharded (strong): ONE global batch of B images
     recon_per_step = B * n_t * (1 if t_shard else world)
     g = torch.Generator().manual_seed(1234 + (0 if t_shard else rank))
-    host_images = torch.rand((B, w["ch"]) + tuple(w["size"]), generator=g).pin_memory()
+    host_images = torch.rand((B, img_ch) + img_size, generator=g).pin_memory()
     dev_images = host_images.to(dev)
     gathered = torch.empty((world * n_t, B, 2), dtype=torch.float32, device=dev) if world > 1 and not t_shard else None
     parts = partition_t_starts(chains, world) if t_shard else None
