@@ -46,19 +46,20 @@ __global__ void lpips_scale_kernel(const float* __restrict__ in0, const float* _
 
 // Convolution + bias + ReLU as a shared-memory tiled fp32 GEMM (NCHW in, NCHW out):
 //   out[(n, p), co] = relu(bias[co] + sum_k patch[(n, p), k] * w[co, k]),   k = (ci, kh, kw)
-// A CTA owns a 64 (image, pixel) x 64 output-channel tile; the patch matrix is gathered on the fly (zero padding), the
-// filter rows are read once per 64 rows instead of once per (image, channel, pixel block). 16 x 16 threads, 4 x 4
-// outputs each, K in steps of 16. fp32 CUDA-core math on purpose: the reference computes LPIPS in fp32
-// (src/losses/perceptual_loss.py:107-108) and the score tolerance is 2e-4.
+// A CTA owns a 128 (image, pixel) x 64 output-channel tile; the patch matrix is gathered on the fly (zero padding), the
+// filter rows are read once per 128 rows. 16 x 16 threads, 8 x 4 outputs each, K in steps of 16; the global loads of
+// step i + 1 are in registers while step i's FMAs run. fp32 CUDA-core math on purpose: the reference computes LPIPS in
+// fp32 (src/losses/perceptual_loss.py:107-108) and the score tolerance is 2e-4.
 // CENTER: a 3x3 / pad 1 conv over a 1x1 map only ever sees its centre tap (AlexNet's last three convs on 32x32 images):
 // the reduction runs over Cin with the centre weights, 1/9 of the work.
+constexpr int kLpBM = 128, kLpBN = 64, kLpBK = 16;
 template <int K, int STRIDE, int PAD, bool CENTER = false>
 __global__ void __launch_bounds__(256) lpips_conv_relu_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                               const float* __restrict__ bias, float* __restrict__ out,
                                                               int NB, int Cin, int H, int W, int Cout, int Ho, int Wo) {
-    constexpr int BM = 64, BN = 64, BK = 16;
-    __shared__ float As[BK][BM + 4];
-    __shared__ float Ws[BK][BN + 4];
+    constexpr int BM = kLpBM, BN = kLpBN, BK = kLpBK;
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Ws[BK][BN + 4];
     const int npix = Ho * Wo;
     const long long M = static_cast<long long>(NB) * npix;
     const int red = CENTER ? Cin : Cin * K * K;
@@ -66,61 +67,73 @@ __global__ void __launch_bounds__(256) lpips_conv_relu_kernel(const float* __res
     const int n0 = blockIdx.y * BN;
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
-    // loader mapping: row/col = tid % 64, k = tid / 64 + 4 j
-    const int lrow = tid & 63, lk = tid >> 6;
-    const long long am = m0 + lrow;
+    // loader mapping. A: row = tid % 128, k = 8 * (tid / 128) + j (j < 8). W: column = tid % 64, k = 4 * (tid / 64) + j
+    const int arow = tid & 127, ak = (tid >> 7) * 8;
+    const long long am = m0 + arow;
     const bool a_ok = am < M;
     const long long an = a_ok ? am / npix : 0;
     const int ap = a_ok ? static_cast<int>(am - an * npix) : 0;
     const int aho = ap / Wo, awo = ap - aho * Wo;
     const float* img = in + an * Cin * H * W;
-    const int wco = n0 + lrow;
+    const int wcol = tid & 63, wk = (tid >> 6) * 4;
+    const int wco = n0 + wcol;
     const bool w_ok = wco < Cout;
     const float* wrow = w + static_cast<long long>(w_ok ? wco : 0) * Cin * K * K;
-    float acc[4][4];
+    float ra[8], rw[4];
+    auto gload = [&](int k0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < red; k0 += BK) {
+        for (int j = 0; j < 8; ++j) {
+            const int k = k0 + ak + j;
+            float av = 0.f;
+            if (k < red && a_ok) {
+                if (CENTER) {
+                    av = __ldg(img + k);
+                } else {
+                    const int ci = k / (K * K);
+                    const int rem = k - ci * (K * K);
+                    const int kh = rem / K, kw = rem - kh * K;
+                    const int hi = aho * STRIDE + kh - PAD, wi = awo * STRIDE + kw - PAD;
+                    if (hi >= 0 && hi < H && wi >= 0 && wi < W) av = __ldg(img + (ci * H + hi) * W + wi);
+                }
+            }
+            ra[j] = av;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int kk = lk + 4 * j;
-            const int k = k0 + kk;
-            float av = 0.f, wv = 0.f;
-            if (CENTER) {
-                if (k < red) {
-                    if (a_ok) av = __ldg(img + k);
-                    if (w_ok) wv = __ldg(wrow + k * (K * K) + (K * K) / 2);
-                }
-            } else if (k < red) {
-                const int ci = k / (K * K);
-                const int rem = k - ci * (K * K);
-                const int kh = rem / K, kw = rem - kh * K;
-                const int hi = aho * STRIDE + kh - PAD, wi = awo * STRIDE + kw - PAD;
-                if (a_ok && hi >= 0 && hi < H && wi >= 0 && wi < W) av = __ldg(img + (ci * H + hi) * W + wi);
-                if (w_ok) wv = __ldg(wrow + k);
-            }
-            As[kk][lrow] = av;
-            Ws[kk][lrow] = wv;
+            const int k = k0 + wk + j;
+            rw[j] = (k < red && w_ok) ? __ldg(CENTER ? wrow + k * (K * K) + (K * K) / 2 : wrow + k) : 0.f;
         }
+    };
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    gload(0);
+    for (int k0 = 0; k0 < red; k0 += BK) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) As[ak + j][arow] = ra[j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Ws[wk + j][wcol] = rw[j];
         __syncthreads();
+        if (k0 + BK < red) gload(k0 + BK);  // in flight during this step's FMAs
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
-            const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
             const float4 b4 = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
-            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             const float b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const long long m = m0 + ty * 4 + i;
+    for (int i = 0; i < 8; ++i) {
+        const long long m = m0 + ty * 8 + i;
         if (m >= M) continue;
         const long long n = m / npix;
         const int pp = static_cast<int>(m - n * npix);
@@ -300,7 +313,7 @@ int Lpips::forward(const float* in0, const float* in1, float* out, int B, int C,
             cur = pool; ch = oh; cw = ow;
         }
         const long long M = static_cast<long long>(NB) * h[k] * w[k];
-        dim3 grid(static_cast<unsigned>((M + 63) / 64), static_cast<unsigned>((kChn[k] + 63) / 64));
+        dim3 grid(static_cast<unsigned>((M + kLpBM - 1) / kLpBM), static_cast<unsigned>((kChn[k] + kLpBN - 1) / kLpBN));
         if (k == 0)
             lpips_conv_relu_kernel<11, 4, 2><<<grid, 256, 0, stream>>>(cur, w_[k], b_[k], f[k], NB, kCin[k], ch, cw, kChn[k],
                                                                       h[k], w[k]);
