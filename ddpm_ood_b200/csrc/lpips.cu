@@ -7,9 +7,14 @@
 
 #include <string.h>
 
-#include "conv_gemm.cuh"  // set_error
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "conv_gemm.cuh"  // set_error, the tcgen05 implicit-GEMM conv
 
 namespace ddpm {
+
+int num_sms();  // api.cu
 
 #define LP_CHECK(name)                                                             \
     do {                                                                           \
@@ -164,10 +169,60 @@ __global__ void lpips_maxpool_kernel(const float* __restrict__ in, float* __rest
 }
 
 struct LpipsFeat {
-    const float* f[5];  // [2B, C_k, npix_k]
+    const float* f[5];  // [2B, C_k, npix_k] fp32, or null when the layer's features are channels-last halves:
+    const __half* fh[5];  // [2B, npix_k, C_k] fp16 hi
+    const __half* fl[5];  // [2B, npix_k, C_k] fp16 lo (value = hi + lo)
     const float* lin[5];
     int npix[5];
 };
+
+// ---- tensor-core path of conv3 / conv4 / conv5 (3x3, pad 1, 192 -> 384 -> 256 -> 256) for large maps ------------------
+// 2.5-D LPIPS of a 3-D volume pushes 2 x 128 slices of 128 x 128 through AlexNet per item (src/trainers/reconstruct.py:
+// 181-187): ~50 GFLOP in these three layers, 2 ms on the CUDA-core kernel above. They run instead on the tcgen05
+// implicit-GEMM conv (conv_gemm.cu) with SPLIT-PRECISION operands - activations and weights as fp16 hi + lo halves, K
+// segments [a_hi | a_lo | a_hi] x [w_hi | w_hi | w_lo], fp32 accumulation - which keeps ~22 mantissa bits per product:
+// the fp32 semantics of the reference at tensor-core speed. Features stay channels-last hi / lo halves for the distance
+// kernel.
+__global__ void lpips_split_nhwc_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo, int NB,
+                                        int C, int npix) {
+    // in [NB][C][npix] fp32 -> hi / lo [NB][npix][C] fp16, via a 32 x 32 shared-memory transpose
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, pp = p0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && pp < npix) ? in[(static_cast<long long>(n) * C + c) * npix + pp] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int pp = p0 + i, c = c0 + threadIdx.x;
+        if (pp < npix && c < C) {
+            const float v = tile[threadIdx.x][i];
+            const __half h = __float2half_rn(v);
+            const long long o = (static_cast<long long>(n) * npix + pp) * C + c;
+            hi[o] = h;
+            lo[o] = __float2half_rn(v - __half2float(h));
+        }
+    }
+}
+
+// fp32 [Cout][Cin][9] -> fp16 [Cout][3 * 9 * Cin]: K = segment * 9 Cin + tap * Cin + ci, segments hi | hi | lo
+__global__ void lpips_pack_split_kernel(const float* __restrict__ w, int Cout, int Cin, __half* __restrict__ dst) {
+    const long long total = static_cast<long long>(Cout) * Cin * 9;
+    const long long ktot = 9LL * Cin;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ci = static_cast<int>(i % Cin);
+        const long long r = i / Cin;
+        const int tap = static_cast<int>(r % 9);
+        const int co = static_cast<int>(r / 9);
+        const float v = w[(static_cast<long long>(co) * Cin + ci) * 9 + tap];
+        const __half h = __float2half_rn(v);
+        const long long k = co * 3 * ktot + static_cast<long long>(tap) * Cin + ci;
+        dst[k] = h;
+        dst[k + ktot] = h;
+        dst[k + 2 * ktot] = __float2half_rn(v - __half2float(h));
+    }
+}
 
 // One CTA per image pair: sum_k mean_p sum_c lin_k[c] * (f0/(|f0|+eps) - f1/(|f1|+eps))^2
 __global__ void __launch_bounds__(256) lpips_distance_kernel(LpipsFeat F, int B, float* __restrict__ out) {
@@ -180,13 +235,20 @@ __global__ void __launch_bounds__(256) lpips_distance_kernel(LpipsFeat F, int B,
     for (int k = 0; k < 5; ++k) {
         const int Ck = (k == 0) ? 64 : (k == 1 ? 192 : (k == 2 ? 384 : 256));
         const int np = F.npix[k];
-        const float* f0 = F.f[k] + static_cast<long long>(b) * Ck * np;
-        const float* f1 = F.f[k] + static_cast<long long>(b + B) * Ck * np;
+        const bool halves = F.f[k] == nullptr;  // channels-last hi / lo halves (tensor-core path)
+        const float* f0 = halves ? nullptr : F.f[k] + static_cast<long long>(b) * Ck * np;
+        const float* f1 = halves ? nullptr : F.f[k] + static_cast<long long>(b + B) * Ck * np;
+        const long long h0 = static_cast<long long>(b) * np * Ck, h1 = static_cast<long long>(b + B) * np * Ck;
+        auto feat = [&](int which, int c, int p) -> float {
+            if (!halves) return (which ? f1 : f0)[c * np + p];
+            const long long o = (which ? h1 : h0) + static_cast<long long>(p) * Ck + c;
+            return __half2float(F.fh[k][o]) + __half2float(F.fl[k][o]);
+        };
         float layer = 0.f;  // per-warp partial over its pixels
         for (int p = warp; p < np; p += 8) {
             float n0 = 0.f, n1 = 0.f;
             for (int c = lane; c < Ck; c += 32) {
-                const float a = f0[c * np + p], d = f1[c * np + p];
+                const float a = feat(0, c, p), d = feat(1, c, p);
                 n0 += a * a;
                 n1 += d * d;
             }
@@ -198,7 +260,7 @@ __global__ void __launch_bounds__(256) lpips_distance_kernel(LpipsFeat F, int B,
             const float i0 = 1.0f / (sqrtf(n0) + 1e-10f), i1 = 1.0f / (sqrtf(n1) + 1e-10f);
             float acc = 0.f;
             for (int c = lane; c < Ck; c += 32) {
-                const float d = f0[c * np + p] * i0 - f1[c * np + p] * i1;
+                const float d = feat(0, c, p) * i0 - feat(1, c, p) * i1;
                 acc += F.lin[k][c] * d * d;
             }
 #pragma unroll
@@ -221,7 +283,12 @@ __global__ void __launch_bounds__(256) lpips_distance_kernel(LpipsFeat F, int B,
 Lpips::Lpips() {}
 Lpips::~Lpips() {
     if (arena_) cudaFree(arena_);
+    if (wsplit_) cudaFree(wsplit_);
 }
+
+// rows of the three 3x3 layers from which the tensor-core path is used (below, the CUDA-core kernel's few blocks are faster
+// than three conv_prepare calls)
+static bool lpips_use_tc(int NB, int h2, int w2) { return h2 * w2 > 1 && static_cast<long long>(NB) * h2 * w2 >= 4096; }
 
 int Lpips::init() {
     size_t total = 0;
@@ -275,7 +342,10 @@ size_t Lpips::workspace_bytes(int B, int H, int W) const {
     size_t fl = static_cast<size_t>(2) * B * 3 * H * W;
     for (int k = 0; k < 5; ++k) fl += static_cast<size_t>(2) * B * kChn[k] * h[k] * w[k];
     fl += static_cast<size_t>(2) * B * 64 * ph[0] * pw[0] + static_cast<size_t>(2) * B * 192 * ph[1] * pw[1];
-    return fl * sizeof(float) + 16 * 256;
+    size_t extra = 0;
+    if (lpips_use_tc(2 * B, h[2], w[2]))  // hi / lo halves of the pooled input and of the three feature maps
+        extra = static_cast<size_t>(2) * B * h[2] * w[2] * (192 + 384 + 256 + 256) * 2 * sizeof(__half) + 16 * 1024;
+    return fl * sizeof(float) + 16 * 256 + extra;
 }
 
 int Lpips::forward(const float* in0, const float* in1, float* out, int B, int C, int H, int W, bool normalize, void* ws,
@@ -295,6 +365,31 @@ int Lpips::forward(const float* in0, const float* in1, float* out, int B, int C,
     for (int k = 0; k < 5; ++k) f[k] = take(static_cast<size_t>(NB) * kChn[k] * h[k] * w[k]);
     float* p0 = take(static_cast<size_t>(NB) * 64 * ph[0] * pw[0]);
     float* p1 = take(static_cast<size_t>(NB) * 192 * ph[1] * pw[1]);
+    const bool use_tc = lpips_use_tc(NB, h[2], w[2]);
+    __half *p1_hi = nullptr, *p1_lo = nullptr, *fh[5] = {}, *fl[5] = {};
+    if (use_tc) {
+        const size_t rows = static_cast<size_t>(NB) * h[2] * w[2];
+        __half* hp = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
+        auto take_h = [&](size_t n) { __half* r = hp; hp += (n + 511) & ~size_t(511); return r; };
+        p1_hi = take_h(rows * 192); p1_lo = take_h(rows * 192);
+        for (int k = 2; k < 5; ++k) { fh[k] = take_h(rows * kChn[k]); fl[k] = take_h(rows * kChn[k]); }
+        if (!wsplit_ready_) {  // one-time: split-precision weight matrices of conv3 / conv4 / conv5
+            size_t total = 0;
+            for (int k = 2; k < 5; ++k) total += static_cast<size_t>(kChn[k]) * 27 * kCin[k];
+            if (!wsplit_ && cudaMalloc(&wsplit_, total * sizeof(__half)) != cudaSuccess) {
+                set_error("lpips: cudaMalloc of the split-precision weights failed");
+                return 6;
+            }
+            __half* wp = static_cast<__half*>(wsplit_);
+            for (int k = 2; k < 5; ++k) {
+                wsplit_k_[k] = wp;
+                lpips_pack_split_kernel<<<592, 256, 0, stream>>>(w_[k], kChn[k], kCin[k], wp);
+                LP_CHECK("lpips_pack_split");
+                wp += static_cast<size_t>(kChn[k]) * 27 * kCin[k];
+            }
+            wsplit_ready_ = true;
+        }
+    }
 
     auto blocks_for = [](long long n) { long long b = (n + 255) / 256; return static_cast<int>(b > 148 * 16 ? 148 * 16 : b); };
     lpips_scale_kernel<<<blocks_for(static_cast<long long>(NB) * 3 * H * W), 256, 0, stream>>>(
@@ -313,6 +408,30 @@ int Lpips::forward(const float* in0, const float* in1, float* out, int B, int C,
             cur = pool; ch = oh; cw = ow;
         }
         const long long M = static_cast<long long>(NB) * h[k] * w[k];
+        if (k >= 2 && use_tc) {
+            const __half* in_hi = k == 2 ? p1_hi : fh[k - 1];
+            const __half* in_lo = k == 2 ? p1_lo : fl[k - 1];
+            if (k == 2) {
+                dim3 g((h[2] * w[2] + 31) / 32, (192 + 31) / 32, NB);
+                lpips_split_nhwc_kernel<<<g, dim3(32, 8), 0, stream>>>(cur, p1_hi, p1_lo, NB, 192, h[2] * w[2]);
+                LP_CHECK("lpips_split_nhwc");
+            }
+            ConvProblem q{};
+            q.spatial_dims = 2; q.N = NB; q.D = 1; q.H = h[k]; q.W = w[k]; q.stride = 1;
+            q.n_seg = 3;
+            q.seg[0] = {in_hi, kCin[k], 3};
+            q.seg[1] = {in_lo, kCin[k], 3};
+            q.seg[2] = {in_hi, kCin[k], 3};
+            q.weights = wsplit_k_[k]; q.w_rows = kChn[k]; q.Cout = kChn[k];
+            q.mode = EPI_STORE; q.bias = b_[k]; q.relu = 1;
+            q.out = fh[k]; q.out_lo = fl[k];
+            ConvLaunch l;
+            int rc = conv_prepare(q, num_sms(), &l);
+            if (!rc) rc = conv_launch(l, stream);
+            if (rc) return rc;
+            cur = nullptr; ch = h[k]; cw = w[k];
+            continue;
+        }
         dim3 grid(static_cast<unsigned>((M + kLpBM - 1) / kLpBM), static_cast<unsigned>((kChn[k] + kLpBN - 1) / kLpBN));
         if (k == 0)
             lpips_conv_relu_kernel<11, 4, 2><<<grid, 256, 0, stream>>>(cur, w_[k], b_[k], f[k], NB, kCin[k], ch, cw, kChn[k],
@@ -330,10 +449,14 @@ int Lpips::forward(const float* in0, const float* in1, float* out, int B, int C,
         cur = f[k]; ch = h[k]; cw = w[k];
     }
     LpipsFeat F;
-    for (int k = 0; k < 5; ++k) { F.f[k] = f[k]; F.lin[k] = lin_[k]; F.npix[k] = h[k] * w[k]; }
+    for (int k = 0; k < 5; ++k) {
+        const bool halves = use_tc && k >= 2;
+        F.f[k] = halves ? nullptr : f[k]; F.fh[k] = fh[k]; F.fl[k] = fl[k];
+        F.lin[k] = lin_[k]; F.npix[k] = h[k] * w[k];
+    }
     lpips_distance_kernel<<<B, 256, 0, stream>>>(F, B, out);
     LP_CHECK("lpips_distance");
-    launches_ += 9;
+    launches_ += use_tc ? 10 : 9;
     return 0;
 }
 

@@ -25,6 +25,11 @@ class Lpips {
     struct Slot { float* dst; long long numel; bool set; };
     float* arena_ = nullptr;
     float *w_[5], *b_[5], *lin_[5];
+    // tensor-core path of the three 3x3 convs (large maps: 3-D volumes scored slice by slice): split-precision weights
+    // [Cout][hi | hi | lo] fp16 (see lpips.cu), packed on the first forward that needs them
+    void* wsplit_ = nullptr;
+    void* wsplit_k_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool wsplit_ready_ = false;
     std::map<std::string, Slot> slots_;
     bool ready_ = false;
     long long launches_ = 0;
