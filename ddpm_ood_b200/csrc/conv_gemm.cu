@@ -510,7 +510,7 @@ int conv_prepare(const ConvProblem& q, int num_sms, ConvLaunch* out) {
     for (int s = 0; s < q.n_seg; ++s) {
         const ConvSegment& g = q.seg[s];
         if (g.channels % kBlockK != 0) { set_error("conv: segment channels %d not a multiple of 64", g.channels); return 2; }
-        if (g.ksize != 1 && g.ksize != 3 && !(g.ksize == 2 && q.upsample2) && !(g.ksize == 4 && q.stride == 2)) {
+        if (g.ksize != 1 && g.ksize != 3 && g.ksize != 5 && !(g.ksize == 2 && q.upsample2) && !(g.ksize == 4 && q.stride == 2)) {
             set_error("conv: ksize %d unsupported", g.ksize);
             return 2;
         }

@@ -89,7 +89,7 @@ struct ConvLaunch {
 struct ConvSegment {
     const void* ptr;  // NDHWC fp16
     int channels;     // multiple of 64
-    int ksize;        // 1 or 3 (per spatial dim); 2 only with ConvProblem::upsample2; 4 with stride 2 and pad 1
+    int ksize;        // 1, 3 or 5 (per spatial dim, "same" padding); 2 only with ConvProblem::upsample2; 4 with stride 2 and pad 1
 };
 
 struct ConvProblem {

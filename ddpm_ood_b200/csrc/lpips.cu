@@ -174,9 +174,13 @@ struct LpipsFeat {
     const __half* fl[5];  // [2B, npix_k, C_k] fp16 lo (value = hi + lo)
     const float* lin[5];
     int npix[5];
+    int cstride[5];       // channels per row of the halves (conv2's 192 channels live in rows of 256)
 };
 
-// ---- tensor-core path of conv3 / conv4 / conv5 (3x3, pad 1, 192 -> 384 -> 256 -> 256) for large maps ------------------
+// ---- tensor-core path of conv2 (5x5, pad 2, 64 -> 192) and conv3 / conv4 / conv5 (3x3, pad 1, 192 -> 384 -> 256 -> 256)
+// for large maps. conv2's 192 output channels are padded to 256 (zero weight rows, zero bias: relu(0) = 0), the second
+// max-pool runs on the channels-last halves. conv1 (11x11 stride 4 over 3 channels, 10 % of the FLOPs) stays on the
+// CUDA-core kernel.
 // 2.5-D LPIPS of a 3-D volume pushes 2 x 128 slices of 128 x 128 through AlexNet per item (src/trainers/reconstruct.py:
 // 181-187): ~50 GFLOP in these three layers, 2 ms on the CUDA-core kernel above. They run instead on the tcgen05
 // implicit-GEMM conv (conv_gemm.cu) with SPLIT-PRECISION operands - activations and weights as fp16 hi + lo halves, K
@@ -205,22 +209,50 @@ __global__ void lpips_split_nhwc_kernel(const float* __restrict__ in, __half* __
     }
 }
 
-// fp32 [Cout][Cin][9] -> fp16 [Cout][3 * 9 * Cin]: K = segment * 9 Cin + tap * Cin + ci, segments hi | hi | lo
-__global__ void lpips_pack_split_kernel(const float* __restrict__ w, int Cout, int Cin, __half* __restrict__ dst) {
-    const long long total = static_cast<long long>(Cout) * Cin * 9;
-    const long long ktot = 9LL * Cin;
+// fp32 [Cout][Cin][taps] -> fp16 [Cout][3 * taps * Cin]: K = segment * taps Cin + tap * Cin + ci, segments hi | hi | lo
+__global__ void lpips_pack_split_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, __half* __restrict__ dst) {
+    const long long total = static_cast<long long>(Cout) * Cin * taps;
+    const long long ktot = static_cast<long long>(taps) * Cin;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int ci = static_cast<int>(i % Cin);
         const long long r = i / Cin;
-        const int tap = static_cast<int>(r % 9);
-        const int co = static_cast<int>(r / 9);
-        const float v = w[(static_cast<long long>(co) * Cin + ci) * 9 + tap];
+        const int tap = static_cast<int>(r % taps);
+        const int co = static_cast<int>(r / taps);
+        const float v = w[(static_cast<long long>(co) * Cin + ci) * taps + tap];
         const __half h = __float2half_rn(v);
         const long long k = co * 3 * ktot + static_cast<long long>(tap) * Cin + ci;
         dst[k] = h;
         dst[k + ktot] = h;
         dst[k + 2 * ktot] = __float2half_rn(v - __half2float(h));
+    }
+}
+
+// 3x3 / stride 2 max-pool on channels-last halves: in [NB][H][W][Cs] (C real channels of a row of Cs), out [NB][Ho][Wo][C].
+// The maximum of hi + lo is one of the inputs: its two halves are copied, nothing is re-rounded.
+__global__ void lpips_maxpool_halves_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, __half* __restrict__ ohi,
+                                            __half* __restrict__ olo, int NB, int H, int W, int Cs, int C, int Ho, int Wo) {
+    const long long total = static_cast<long long>(NB) * Ho * Wo * C;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C);
+        long long r = i / C;
+        const int wo = static_cast<int>(r % Wo); r /= Wo;
+        const int ho = static_cast<int>(r % Ho);
+        const long long n = r / Ho;
+        float best = -INFINITY;
+        __half bh = __float2half(0.f), bl = __float2half(0.f);
+        for (int dy = 0; dy < 3; ++dy)
+            for (int dx = 0; dx < 3; ++dx) {
+                const int y = 2 * ho + dy, x = 2 * wo + dx;
+                if (y >= H || x >= W) continue;
+                const long long o = ((n * H + y) * W + x) * Cs + c;
+                const __half a = hi[o], b = lo[o];
+                const float v = __half2float(a) + __half2float(b);
+                if (v > best) { best = v; bh = a; bl = b; }
+            }
+        ohi[i] = bh;
+        olo[i] = bl;
     }
 }
 
@@ -238,10 +270,11 @@ __global__ void __launch_bounds__(256) lpips_distance_kernel(LpipsFeat F, int B,
         const bool halves = F.f[k] == nullptr;  // channels-last hi / lo halves (tensor-core path)
         const float* f0 = halves ? nullptr : F.f[k] + static_cast<long long>(b) * Ck * np;
         const float* f1 = halves ? nullptr : F.f[k] + static_cast<long long>(b + B) * Ck * np;
-        const long long h0 = static_cast<long long>(b) * np * Ck, h1 = static_cast<long long>(b + B) * np * Ck;
+        const int Cs = F.cstride[k];
+        const long long h0 = static_cast<long long>(b) * np * Cs, h1 = static_cast<long long>(b + B) * np * Cs;
         auto feat = [&](int which, int c, int p) -> float {
             if (!halves) return (which ? f1 : f0)[c * np + p];
-            const long long o = (which ? h1 : h0) + static_cast<long long>(p) * Ck + c;
+            const long long o = (which ? h1 : h0) + static_cast<long long>(p) * Cs + c;
             return __half2float(F.fh[k][o]) + __half2float(F.fl[k][o]);
         };
         float layer = 0.f;  // per-warp partial over its pixels
@@ -344,7 +377,8 @@ size_t Lpips::workspace_bytes(int B, int H, int W) const {
     fl += static_cast<size_t>(2) * B * 64 * ph[0] * pw[0] + static_cast<size_t>(2) * B * 192 * ph[1] * pw[1];
     size_t extra = 0;
     if (lpips_use_tc(2 * B, h[2], w[2]))  // hi / lo halves of the pooled input and of the three feature maps
-        extra = static_cast<size_t>(2) * B * h[2] * w[2] * (192 + 384 + 256 + 256) * 2 * sizeof(__half) + 16 * 1024;
+        extra = (static_cast<size_t>(2) * B * h[2] * w[2] * (192 + 384 + 256 + 256) +
+                 static_cast<size_t>(2) * B * h[1] * w[1] * (64 + 256)) * 2 * sizeof(__half) + 32 * 1024;
     return fl * sizeof(float) + 16 * 256 + extra;
 }
 
@@ -366,27 +400,36 @@ int Lpips::forward(const float* in0, const float* in1, float* out, int B, int C,
     float* p0 = take(static_cast<size_t>(NB) * 64 * ph[0] * pw[0]);
     float* p1 = take(static_cast<size_t>(NB) * 192 * ph[1] * pw[1]);
     const bool use_tc = lpips_use_tc(NB, h[2], w[2]);
-    __half *p1_hi = nullptr, *p1_lo = nullptr, *fh[5] = {}, *fl[5] = {};
+    constexpr int kC1Pad = 256;  // conv2's 192 output channels in rows of 256 (two 128-wide N tiles)
+    __half *p0_hi = nullptr, *p0_lo = nullptr, *p1_hi = nullptr, *p1_lo = nullptr, *fh[5] = {}, *fl[5] = {};
     if (use_tc) {
         const size_t rows = static_cast<size_t>(NB) * h[2] * w[2];
         __half* hp = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
         auto take_h = [&](size_t n) { __half* r = hp; hp += (n + 511) & ~size_t(511); return r; };
+        const size_t rows1 = static_cast<size_t>(NB) * h[1] * w[1];
+        p0_hi = take_h(rows1 * 64); p0_lo = take_h(rows1 * 64);
+        fh[1] = take_h(rows1 * kC1Pad); fl[1] = take_h(rows1 * kC1Pad);
         p1_hi = take_h(rows * 192); p1_lo = take_h(rows * 192);
         for (int k = 2; k < 5; ++k) { fh[k] = take_h(rows * kChn[k]); fl[k] = take_h(rows * kChn[k]); }
-        if (!wsplit_ready_) {  // one-time: split-precision weight matrices of conv3 / conv4 / conv5
-            size_t total = 0;
+        if (!wsplit_ready_) {  // one-time: split-precision weight matrices of conv2 (rows padded to 256) .. conv5
+            size_t total = static_cast<size_t>(kC1Pad) * 3 * 25 * kCin[1];
             for (int k = 2; k < 5; ++k) total += static_cast<size_t>(kChn[k]) * 27 * kCin[k];
-            if (!wsplit_ && cudaMalloc(&wsplit_, total * sizeof(__half)) != cudaSuccess) {
+            const size_t bytes = total * sizeof(__half) + kC1Pad * sizeof(float);
+            if (!wsplit_ && cudaMalloc(&wsplit_, bytes) != cudaSuccess) {
                 set_error("lpips: cudaMalloc of the split-precision weights failed");
                 return 6;
             }
+            cudaMemsetAsync(wsplit_, 0, bytes, stream);
             __half* wp = static_cast<__half*>(wsplit_);
-            for (int k = 2; k < 5; ++k) {
+            for (int k = 1; k < 5; ++k) {
+                const int taps = kK[k] * kK[k];
                 wsplit_k_[k] = wp;
-                lpips_pack_split_kernel<<<592, 256, 0, stream>>>(w_[k], kChn[k], kCin[k], wp);
+                lpips_pack_split_kernel<<<592, 256, 0, stream>>>(w_[k], kChn[k], kCin[k], taps, wp);
                 LP_CHECK("lpips_pack_split");
-                wp += static_cast<size_t>(kChn[k]) * 27 * kCin[k];
+                wp += static_cast<size_t>(k == 1 ? kC1Pad : kChn[k]) * 3 * taps * kCin[k];
             }
+            bias1_pad_ = reinterpret_cast<float*>(wp);
+            cudaMemcpyAsync(bias1_pad_, b_[1], kChn[1] * sizeof(float), cudaMemcpyDeviceToDevice, stream);
             wsplit_ready_ = true;
         }
     }
@@ -399,7 +442,12 @@ int Lpips::forward(const float* in0, const float* in1, float* out, int B, int C,
     const float* cur = x;
     int ch = H, cw = W;
     for (int k = 0; k < 5; ++k) {
-        if (k == 1 || k == 2) {
+        if (k == 2 && use_tc) {  // second max-pool on the channels-last halves of conv2's output
+            lpips_maxpool_halves_kernel<<<blocks_for(static_cast<long long>(NB) * ph[1] * pw[1] * 192), 256, 0, stream>>>(
+                fh[1], fl[1], p1_hi, p1_lo, NB, h[1], w[1], kC1Pad, 192, ph[1], pw[1]);
+            LP_CHECK("lpips_maxpool_halves");
+            ch = ph[1]; cw = pw[1];
+        } else if (k == 1 || k == 2) {
             float* pool = (k == 1) ? p0 : p1;
             const int oh = ph[k - 1], ow = pw[k - 1];
             lpips_maxpool_kernel<<<blocks_for(static_cast<long long>(NB) * kCin[k] * oh * ow), 256, 0, stream>>>(
@@ -408,22 +456,23 @@ int Lpips::forward(const float* in0, const float* in1, float* out, int B, int C,
             cur = pool; ch = oh; cw = ow;
         }
         const long long M = static_cast<long long>(NB) * h[k] * w[k];
-        if (k >= 2 && use_tc) {
-            const __half* in_hi = k == 2 ? p1_hi : fh[k - 1];
-            const __half* in_lo = k == 2 ? p1_lo : fl[k - 1];
-            if (k == 2) {
-                dim3 g((h[2] * w[2] + 31) / 32, (192 + 31) / 32, NB);
-                lpips_split_nhwc_kernel<<<g, dim3(32, 8), 0, stream>>>(cur, p1_hi, p1_lo, NB, 192, h[2] * w[2]);
+        if (k >= 1 && use_tc) {
+            const __half* in_hi = k == 1 ? p0_hi : (k == 2 ? p1_hi : fh[k - 1]);
+            const __half* in_lo = k == 1 ? p0_lo : (k == 2 ? p1_lo : fl[k - 1]);
+            if (k == 1) {  // the pooled conv1 features (NCHW fp32) -> channels-last halves
+                dim3 g((h[1] * w[1] + 31) / 32, (64 + 31) / 32, NB);
+                lpips_split_nhwc_kernel<<<g, dim3(32, 8), 0, stream>>>(cur, p0_hi, p0_lo, NB, 64, h[1] * w[1]);
                 LP_CHECK("lpips_split_nhwc");
             }
+            const int cout = k == 1 ? kC1Pad : kChn[k];
             ConvProblem q{};
             q.spatial_dims = 2; q.N = NB; q.D = 1; q.H = h[k]; q.W = w[k]; q.stride = 1;
             q.n_seg = 3;
-            q.seg[0] = {in_hi, kCin[k], 3};
-            q.seg[1] = {in_lo, kCin[k], 3};
-            q.seg[2] = {in_hi, kCin[k], 3};
-            q.weights = wsplit_k_[k]; q.w_rows = kChn[k]; q.Cout = kChn[k];
-            q.mode = EPI_STORE; q.bias = b_[k]; q.relu = 1;
+            q.seg[0] = {in_hi, kCin[k], kK[k]};
+            q.seg[1] = {in_lo, kCin[k], kK[k]};
+            q.seg[2] = {in_hi, kCin[k], kK[k]};
+            q.weights = wsplit_k_[k]; q.w_rows = cout; q.Cout = cout;
+            q.mode = EPI_STORE; q.bias = k == 1 ? bias1_pad_ : b_[k]; q.relu = 1;
             q.out = fh[k]; q.out_lo = fl[k];
             ConvLaunch l;
             int rc = conv_prepare(q, num_sms(), &l);
@@ -450,13 +499,14 @@ int Lpips::forward(const float* in0, const float* in1, float* out, int B, int C,
     }
     LpipsFeat F;
     for (int k = 0; k < 5; ++k) {
-        const bool halves = use_tc && k >= 2;
+        const bool halves = use_tc && k >= 1;
         F.f[k] = halves ? nullptr : f[k]; F.fh[k] = fh[k]; F.fl[k] = fl[k];
+        F.cstride[k] = (use_tc && k == 1) ? kC1Pad : kChn[k];
         F.lin[k] = lin_[k]; F.npix[k] = h[k] * w[k];
     }
     lpips_distance_kernel<<<B, 256, 0, stream>>>(F, B, out);
     LP_CHECK("lpips_distance");
-    launches_ += use_tc ? 10 : 9;
+    launches_ += use_tc ? 11 : 9;
     return 0;
 }
 

@@ -29,6 +29,7 @@ class Lpips {
     // [Cout][hi | hi | lo] fp16 (see lpips.cu), packed on the first forward that needs them
     void* wsplit_ = nullptr;
     void* wsplit_k_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float* bias1_pad_ = nullptr;  // conv2's bias padded from 192 to 256 output channels (two 128-wide N tiles)
     bool wsplit_ready_ = false;
     std::map<std::string, Slot> slots_;
     bool ready_ = false;
