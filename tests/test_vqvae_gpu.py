@@ -176,3 +176,24 @@ def test_ldm_route_against_golden():
     assert flips <= total // 100, flips
     for key, rel in worst.items():
         assert rel < tol, (key, rel, flips)
+
+
+def test_wide_3d_model_falls_back_to_the_im2col_kernel_where_the_halo_kernel_cannot_stage():
+    """512-channel 3-D residual units with split-precision operands need 72 K stages per work item, more than the halo
+    kernel schedules: those convs take the im2col-tile kernel, the others (decoder, 3 x 8 x 3 = ... <= 48 stages) stay on
+    the halo kernel. Same parity bars as the narrow models."""
+    cfg = dict(spatial_dims=3, in_channels=1, out_channels=1, num_channels=(512,), num_res_layers=1,
+               num_res_channels=(512,), downsample_parameters=((2, 4, 1, 1),), upsample_parameters=((2, 4, 1, 1, 0),),
+               num_embeddings=64, embedding_dim=128)
+    ref, ours = _pair(cfg)
+    x = _image(cfg, 2, 16)
+    with torch.no_grad():
+        want_idx = ref.index_quantize(x)
+        ties = _tie_mask(ref, ref.encode(x), rel=2e-5)
+        want_img = ref.decode_samples(want_idx)
+    got_idx = ours.index_quantize(x.cuda()).cpu()
+    differ = got_idx != want_idx
+    assert not bool((differ & ~ties).any()), int((differ & ~ties).sum())
+    got_img = ours.decode_samples(want_idx.cuda()).cpu()
+    rel = ((got_img - want_img).norm() / want_img.norm()).item()
+    assert rel < 3e-3, rel
