@@ -216,6 +216,30 @@ class PerceptualLoss(nn.Module):
             ys, ps = ys[idx], ps[idx]
         return torch.mean(self.perceptual_function(ys, ps, normalize=self.lpips_normalize))
 
+    @torch.no_grad()
+    def per_item(self, y: torch.Tensor, y_pred: torch.Tensor, max_slices: int = 4096) -> torch.Tensor:
+        """[B] scores, one per batch item: what the reference's 3-D scoring loop computes by calling the loss once per
+        item (`self.perceptual_loss(images_original[b, None, ...], reconstructions[b, None, ...])`,
+        src/trainers/reconstruct.py:181-187), with the slices of several items in ONE LPIPS launch sequence
+        (`max_slices` slice pairs per call) and the mean taken per item."""
+        B = y.shape[0]
+        if not (self.dimensions == 3 and self.fake_3D_views and self.keep_ratio == 1):
+            return torch.stack([self(y[b:b + 1], y_pred[b:b + 1]).reshape(()) for b in range(B)])
+        permute_dims, view_dims = self.fake_3D_views[-1]  # the reference keeps the last view's value
+        y, y_pred = y.float(), y_pred.float()
+        slices = y.shape[permute_dims[1]]
+        step = max(1, max_slices // slices)
+        out = []
+        for b0 in range(0, B, step):
+            ys = y[b0:b0 + step].permute(*permute_dims).contiguous()
+            ps = y_pred[b0:b0 + step].permute(*permute_dims).contiguous()
+            n = ys.shape[0]
+            ys = ys.view(-1, ys.shape[2], ys.shape[3], ys.shape[4])
+            ps = ps.view(-1, ps.shape[2], ps.shape[3], ps.shape[4])
+            d = self.perceptual_function(ys, ps, normalize=self.lpips_normalize)
+            out.append(d.reshape(n, slices).mean(dim=1) * self.perceptual_factor)
+        return torch.cat(out)
+
     def get_perceptual_factor(self) -> float:
         return self.perceptual_factor
 

@@ -187,6 +187,10 @@ class BatchReconstructor:
                 else:
                     pd = self.pl(images_original, recon)
                 pd_all[i] = pd.reshape(B)
+            elif hasattr(self.pl, "per_item"):
+                # one score per item, as the reference's 3-D loop produces (trainers/reconstruct.py:181-187), with the
+                # slices of several items per LPIPS call
+                pd_all[i] = self.pl.per_item(images_original, recon).reshape(B)
             else:
                 for b in range(B):  # per item, as the reference does in 3-D (trainers/reconstruct.py:181-187)
                     pd_all[i, b] = self.pl(images_original[b, None, ...], recon[b, None, ...])

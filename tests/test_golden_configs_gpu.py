@@ -102,6 +102,10 @@ def test_lpips_3d_per_item():
     a, b = gold["a"].float().cuda(), gold["b"].float().cuda()
     got = torch.stack([pl(a[i, None], b[i, None]).reshape(()) for i in range(a.shape[0])]).cpu()
     assert torch.allclose(got, gold["pd"], rtol=2e-4, atol=1e-8), (got, gold["pd"])
+    # the batched form the engine uses: all items' slices in one LPIPS call, mean per item
+    batched = pl.per_item(a, b).cpu()
+    assert torch.allclose(batched, got, rtol=1e-5, atol=1e-9), (batched, got)
+    assert torch.allclose(pl.per_item(a, b, max_slices=1).cpu(), got, rtol=1e-5, atol=1e-9)  # one item per call
 
 
 @pytest.mark.parametrize("key", ["1x32x32", "3x32x32", "3x64x64", "1x28x28", "128x8x8x8"])
