@@ -3,9 +3,9 @@ fp32 oracle): the exact grids of the BASELINE.json configurations, which the ora
 
 Tolerance (north_star): 1e-3 relative on the scores, t grid bit-exact. Per-forward eps tolerance: the CUDA path computes
 with fp16 operands / fp32 accumulation through ~40 layers, the oracle in fp32 throughout: an eps element differs by up
-to ~1e-2 of the eps range at the noisiest timestep (fp16 has 11 bits; 40 layers of rounding), so the per-forward bound
-is stated on the relative L2 error (3e-3) and on max|diff| / max|eps| (1.5e-2); what the metric reads - the scores after
-a whole chain - is held to 1e-3.
+to ~1e-3 of the eps range (fp16 has 11 bits; 40 layers of rounding): measured relative L2 error 0.86e-3 .. 1.04e-3 and
+max|diff| / max|eps| 0.83e-3 .. 1.28e-3 over the five BASELINE shapes, asserted at 1.5e-3 / 3e-3; what the metric
+reads - the scores after a whole chain - is held to 1e-3 (measured 2e-5 .. 1.9e-4 on the committed grids).
 """
 from pathlib import Path
 
@@ -119,8 +119,9 @@ def test_unet_eps_per_forward(key):
     rel_l2 = ((y - want).norm() / want.norm()).item()
     max_rel = ((y - want).abs().max() / want.abs().max()).item()
     print(key, "rel-L2", rel_l2, "max|diff|/max|eps|", max_rel)
-    assert rel_l2 < 3e-3, (key, rel_l2)
-    assert max_rel < 1.5e-2, (key, max_rel)
+    # measured on B200 (round 2): rel-L2 0.86e-3 .. 1.04e-3, max|diff| / max|eps| 0.83e-3 .. 1.28e-3 over the five shapes
+    assert rel_l2 < 1.5e-3, (key, rel_l2)
+    assert max_rel < 3e-3, (key, max_rel)
 
 
 def test_t_start_shards_union_equals_full_grid():
