@@ -143,7 +143,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint
                         if (!s_add && cadd) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(cadd + col0 + j));
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(cadd + (p.chan_mod ? col0 % p.chan_mod : col0) + j));
                                 f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
                             }
                         }

@@ -483,6 +483,8 @@ int conv_prepare(const ConvProblem& q, int num_sms, ConvLaunch* out) {
     p.bias = q.bias;
     p.chan_add = q.chan_add;
     p.chan_add_stride = q.chan_add_stride;
+    p.chan_mod = q.chan_mod;
+    if (q.chan_mod && (q.chan_mod % 32 != 0 || q.Cout % q.chan_mod != 0)) { set_error("conv: chan_mod=%d unsupported", q.chan_mod); return 2; }
     p.residual = static_cast<const __half*>(q.residual);
     p.out = static_cast<__half*>(q.out);
     p.out_lo = static_cast<__half*>(q.out_lo);

@@ -52,6 +52,8 @@ struct ConvGemmParams {
     const float* bias;        // [Cout] or null
     const float* chan_add;    // per-image channel offsets (timestep embedding) or null: chan_add[n*chan_add_stride + c]
     long long chan_add_stride;  // row pitch in floats (0 = one shared row)
+    int chan_mod;             // 0, or: chan_add holds chan_mod values per row, output column c reads entry c % chan_mod (the
+                              // dense 2x2x2 form of a 3-D conv: columns are (voxel, channel))
     const __half* residual;   // same layout as out, or null
     __half* out;
     float scale;              // EPI_SOFTMAX_BD: logits scale
@@ -106,6 +108,7 @@ struct ConvProblem {
     const float* bias;
     const float* chan_add;
     long long chan_add_stride;
+    int chan_mod;  // see ConvGemmParams::chan_mod (multiple of 32; needs impl-independent general epilogue: set with chan_add)
     const void* residual;
     void* out;
     float scale;

@@ -16,6 +16,35 @@ __global__ void add_vec_kernel(const float* a, const float* b, float* out, int n
 
 // conv2's packed weights widened by an identity block: out = W z + I x puts the ResnetBlock's identity residual on the
 // tensor pipe (fp16 x times 1.0 is exact in the fp32 accumulator) instead of latency-bound loads in the epilogue.
+// Dense form of a padded 3x3x3 conv on a 2 x 2 x 2 volume (voxel v = (z * 2 + y) * 2 + x): output voxel vo reads input voxel
+// vi through tap (vi - vo + 1) per axis. w: packed fp16 [cout][... | 27 taps x cin at column kcol0 | ...] (row pitch ksrc);
+// dst[(vo * cout + co)][kdst0 + vi * cin + ci] = w[co][kcol0 + tap(vo, vi) * cin + ci].
+// diag: a 1x1 conv (the ResnetBlock skip conv): dst[(vo, co)][kdst0 + vi * cin + ci] = vi == vo ? w[co][kcol0 + ci] : 0.
+__global__ void dense2_pack_kernel(const __half* __restrict__ w, int cout, int cin, long long ksrc, long long kcol0,
+                                   __half* __restrict__ dst, long long kdst, long long kdst0, int diag) {
+    const long long total = 64LL * cout * cin;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ci = static_cast<int>(i % cin);
+        long long r = i / cin;
+        const int vi = static_cast<int>(r % 8); r /= 8;
+        const int co = static_cast<int>(r % cout);
+        const int vo = static_cast<int>(r / cout);
+        __half v = __float2half(0.f);
+        if (diag) {
+            if (vi == vo) v = w[co * ksrc + kcol0 + ci];
+        } else {
+            const int dz = (vi >> 2) - (vo >> 2) + 1, dy = ((vi >> 1) & 1) - ((vo >> 1) & 1) + 1, dx = (vi & 1) - (vo & 1) + 1;
+            v = w[co * ksrc + kcol0 + static_cast<long long>((dz * 3 + dy) * 3 + dx) * cin + ci];
+        }
+        dst[(static_cast<long long>(vo) * cout + co) * kdst + kdst0 + static_cast<long long>(vi) * cin + ci] = v;
+    }
+}
+__global__ void tile_vec_kernel(const float* __restrict__ src, int n, int reps, float* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n * reps) dst[i] = src[i % n];
+}
+
 __global__ void widen_with_identity_kernel(const __half* __restrict__ w, int cout, long long k, __half* __restrict__ dst) {
     const long long kw = k + cout;
     const long long total = static_cast<long long>(cout) * kw;
@@ -63,6 +92,7 @@ UNet::UNet(const UNetConfig& cfg) : cfg_(cfg), E_(cfg.num_channels[0]) {}
 
 UNet::~UNet() {
     for (auto& kv : chain_graphs_) cudaGraphExecDestroy(kv.second.exec);
+    for (void* q : dense2_allocs_) cudaFree(q);
     if (temb_table_) cudaFree(temb_table_);
     if (temb_table_act_) cudaFree(temb_table_act_);
     if (f32_arena_) cudaFree(f32_arena_);
@@ -365,10 +395,45 @@ int UNet::finalize(cudaStream_t stream) {
             widen_with_identity_kernel<<<148 * 4, 256, 0, stream>>>(r.w2, r.cout, k2, r.w2_id);
         }
     };
-    for (auto& L : down_) for (auto& r : L.res) fold_and_widen(r);
-    fold_and_widen(mid1_);
-    fold_and_widen(mid2_);
-    for (auto& L : up_) for (auto& r : L.res) fold_and_widen(r);
+    // 3-D models: dense-form weights for whichever ResnetBlocks end up on 2 x 2 x 2 maps (the third level of an 8^3
+    // latent); built for every block (<= 25 MB each) because the level sizes depend on the input, not on the weights
+    int drc = 0;
+    auto dense2 = [&](ResW& r) {
+        if (cfg_.spatial_dims != 3 || drc) return;
+        const int cin = r.c0 + r.c1;
+        const long long k1 = 8LL * cin, k2 = 8LL * r.cout + (r.skip_conv ? 8LL * cin : 0);
+        const long long ksrc1 = 27LL * cin, ksrc2 = 27LL * r.cout + (r.skip_conv ? cin : 0);
+        if (!r.w1d) {
+            void* q[4] = {nullptr, nullptr, nullptr, nullptr};
+            if (cudaMalloc(&q[0], 8 * r.cout * k1 * sizeof(__half)) != cudaSuccess ||
+                cudaMalloc(&q[1], 8 * r.cout * k2 * sizeof(__half)) != cudaSuccess ||
+                cudaMalloc(&q[2], 8 * r.cout * sizeof(float)) != cudaSuccess ||
+                cudaMalloc(&q[3], 8 * r.cout * sizeof(float)) != cudaSuccess) {
+                set_error("unet: cudaMalloc of the dense 2x2x2 weights failed");
+                drc = 6;
+                return;
+            }
+            for (void* x : q) dense2_allocs_.push_back(x);
+            r.w1d = static_cast<__half*>(q[0]); r.w2d = static_cast<__half*>(q[1]);
+            r.bias1d = static_cast<float*>(q[2]); r.bias2d = static_cast<float*>(q[3]);
+        }
+        dense2_pack_kernel<<<148 * 8, 256, 0, stream>>>(r.w1, r.cout, cin, ksrc1, 0, r.w1d, k1, 0, 0);
+        dense2_pack_kernel<<<148 * 8, 256, 0, stream>>>(r.w2, r.cout, r.cout, ksrc2, 0, r.w2d, k2, 0, 0);
+        if (r.skip_conv) {  // the 1x1 skip conv over cat(h, skip): two block-diagonal K segments after conv2's
+            dense2_pack_kernel<<<148 * 8, 256, 0, stream>>>(r.w2, r.cout, r.c0, ksrc2, 27LL * r.cout, r.w2d, k2, 8LL * r.cout, 1);
+            if (r.c1)
+                dense2_pack_kernel<<<148 * 8, 256, 0, stream>>>(r.w2, r.cout, r.c1, ksrc2, 27LL * r.cout + r.c0, r.w2d, k2,
+                                                                8LL * r.cout + 8LL * r.c0, 1);
+        }
+        tile_vec_kernel<<<(8 * r.cout + 255) / 256, 256, 0, stream>>>(r.bias1, r.cout, 8, r.bias1d);
+        tile_vec_kernel<<<(8 * r.cout + 255) / 256, 256, 0, stream>>>(r.bias2_total, r.cout, 8, r.bias2d);
+    };
+    auto per_block = [&](ResW& r) { fold_and_widen(r); dense2(r); };
+    for (auto& L : down_) for (auto& r : L.res) per_block(r);
+    per_block(mid1_);
+    per_block(mid2_);
+    for (auto& L : up_) for (auto& r : L.res) per_block(r);
+    if (drc) return drc;
     // timestep-embedding table: row t = all time_emb_proj outputs for timestep t (depends on weights only)
     if (!temb_table_) {
         if (cudaMalloc(&temb_table_, static_cast<size_t>(temb_rows_) * P_ * sizeof(float)) != cudaSuccess ||
@@ -619,6 +684,31 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
             halo_conv(q2, ab2, r.cout, -1, halo_gn_in_kernel_ ? &src2 : nullptr, flops2);
             return out;
         };
+        // a ResnetBlock conv on a 2 x 2 x 2 map as ONE linear layer over (voxel, channel): rows = images, K = 8 x channels of
+        // each input tensor, N = 8 cout (see ResW::w1d). 8 / 27 of the im2col form's MACs and plain 2-D GEMM tiles instead
+        // of 128-row boxes gathered from 16 tiny volumes.
+        auto dense2_conv = [&](const __half* z, int zc, const Act* raw0, const Act* raw1, const __half* w, const float* bias,
+                               int cout, int temb_off, const __half* residual, __half* out, double flops) {
+            ConvProblem q{};
+            q.spatial_dims = 2; q.N = N; q.D = 1; q.H = 1; q.W = 1; q.stride = 1;
+            q.n_seg = 1;
+            q.seg[0] = {z, 8 * zc, 1};
+            if (raw0) q.seg[q.n_seg++] = {raw0->p, 8 * raw0->C, 1};
+            if (raw1) q.seg[q.n_seg++] = {raw1->p, 8 * raw1->C, 1};
+            q.weights = w; q.w_rows = 8 * cout; q.Cout = 8 * cout;
+            q.mode = EPI_STORE;
+            q.bias = bias; q.residual = residual; q.out = out;
+            if (temb_off >= 0 && plan.temb_all) { q.chan_add = plan.temb_all + temb_off; q.chan_add_stride = P_; q.chan_mod = cout; }
+            if (measure || dry) { gemm(q, temb_off); return; }
+            Op op{};
+            op.type = Op::GEMM;
+            op.uses_temb = temb_off >= 0;
+            op.temb_off = temb_off;
+            op.flops = flops;
+            int r_ = conv_prepare(q, sms, &op.conv);
+            if (r_ && !rc) rc = r_;
+            plan.ops.push_back(op);
+        };
         auto resblock = [&](const ResW& r, const Act& h, const Act* skip) -> Act {
             if (halo_ok(h, skip, r.cout, r.cout)) return resblock_halo(r, h, skip);
             const int cin = r.c0 + r.c1;
@@ -626,11 +716,22 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
                 const size_t ch = static_cast<size_t>(N) * h.S() * r.cout;
                 if (ch > max_h) max_h = ch;
             }
+            const bool dense2 = sd == 3 && h.D == 2 && h.H == 2 && h.W == 2 && r.w1d && cin % 8 == 0 && r.cout % 32 == 0;
             gn(h, skip, r.g1, r.b1, zA, true);
             Act h1{hB, r.cout, h.D, h.H, h.W, nullptr, 0};
-            if (!measure && fuse_gn_stats_) {
+            if (!measure && fuse_gn_stats_ && !dense2) {
                 h1.parts = conv_stats_parts(sd, h.D, h.H, h.W);
                 h1.stats = take_stats(r.cout, h1.parts);
+            }
+            if (dense2) {
+                const double f1 = 2.0 * N * 8.0 * r.cout * 27.0 * cin;
+                const double f2 = 2.0 * N * 8.0 * r.cout * (27.0 * r.cout + (r.skip_conv ? cin : 0));
+                dense2_conv(zA, cin, nullptr, nullptr, r.w1d, r.bias1d, r.cout, r.temb_off, nullptr, hB, f1);
+                gn(h1, nullptr, r.g2, r.b2, zB, true);
+                Act out = measure ? shape_act(r.cout, h.D, h.H, h.W) : new_act(r.cout, h.D, h.H, h.W, false);
+                dense2_conv(zB, r.cout, r.skip_conv ? &h : nullptr, r.skip_conv ? skip : nullptr, r.w2d, r.bias2d, r.cout, -1,
+                            r.skip_conv ? nullptr : h.p, out.p, f2);
+                return out;
             }
             conv3(h, zA, cin, r.w1, r.bias1, r.cout, 1, r.temb_off, nullptr, hB, nullptr, nullptr, h1.stats);
             gn(h1, nullptr, r.g2, r.b2, zB, true);

@@ -44,6 +44,11 @@ struct ResW {
     float *bias2, *bias_skip, *bias2_total;
     __half* w2_id;  // identity-residual blocks only: [cout][(taps + 1) * cout] = conv2 weights | I (residual as one more K segment)
     int temb_off;
+    // 3-D models: the dense form of both convs for 2 x 2 x 2 maps - under a padded 3x3x3 conv every output voxel sees every
+    // input voxel through a distinct tap, so the conv is a linear layer over (voxel, channel): w1d [8 cout][8 (c0 + c1)],
+    // w2d [8 cout][8 cout (+ 8 c0 + 8 c1: the 1x1 skip conv, block diagonal over voxels)], biases tiled over the voxels
+    __half *w1d = nullptr, *w2d = nullptr;
+    float *bias1d = nullptr, *bias2d = nullptr;
     std::string prefix;
 };
 struct AttnW {
@@ -183,6 +188,7 @@ class UNet {
     int temb_rows_ = 1000;                                      // num_train_timesteps of every reference scheduler
     struct Level { std::vector<ResW> res; std::vector<AttnW> attn; bool has_samp; SampW samp; };
     std::vector<Level> down_, up_;
+    std::vector<void*> dense2_allocs_;  // cudaMalloc'ed dense-form weights of the ResnetBlocks (3-D models)
     ResW mid1_, mid2_;
     AttnW mid_attn_;
     float *out_g_, *out_b_;
