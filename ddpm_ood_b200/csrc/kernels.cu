@@ -135,11 +135,84 @@ __global__ void __launch_bounds__(256) gn_silu_kernel(const __half* __restrict__
     }
 }
 
+// Tiny maps (S <= 8 pixels per image: the 2 x 2 x 2 level of the 3-D UNet): one THREAD per (image, group) keeps the
+// group's S x cpg values in registers - statistics, then scale / shift / SiLU, one read and one write per element. The
+// one-CTA-per-(image, group chunk) kernel above spends ~30 us on 4736 nearly empty CTAs for such a tensor.
+template <int V>  // uint4 vectors per pixel of one group: cpg = 8 V
+__global__ void __launch_bounds__(128) gn_silu_small_kernel(const __half* __restrict__ src0, int C0,
+                                                            const __half* __restrict__ src1, int C1,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            __half* __restrict__ out, int N, int S, int groups, float eps,
+                                                            int do_silu) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * groups) return;
+    const int n = idx / groups, g = idx - n * groups;
+    const int C = C0 + C1, c = g * 8 * V;
+    const __half* base;
+    int Cs;
+    if (c < C0) { base = src0 + static_cast<size_t>(n) * S * C0 + c; Cs = C0; }
+    else        { base = src1 + static_cast<size_t>(n) * S * C1 + (c - C0); Cs = C1; }
+    uint4 raw[8][V];
+    float sum = 0.f, sq = 0.f;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        if (p < S) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                raw[p][v] = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(p) * Cs + 8 * v);
+                float f[8];
+                unpack8(raw[p][v], f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { sum += f[i]; sq += f[i] * f[i]; }
+            }
+        }
+    }
+    const float inv_n = 1.0f / (static_cast<float>(8 * V) * static_cast<float>(S));
+    const float mean = sum * inv_n;
+    float var = sq * inv_n - mean * mean;
+    var = var < 0.f ? 0.f : var;
+    const float rstd = rsqrtf(var + eps);
+    float a[8 * V], b[8 * V];
+#pragma unroll
+    for (int i = 0; i < 8 * V; ++i) {
+        a[i] = gamma[c + i] * rstd;
+        b[i] = beta[c + i] - mean * a[i];
+    }
+    __half* obase = out + static_cast<size_t>(n) * S * C + c;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        if (p < S) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                float f[8];
+                unpack8(raw[p][v], f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float y = f[i] * a[8 * v + i] + b[8 * v + i];
+                    f[i] = do_silu ? silu_fast(y) : y;
+                }
+                *reinterpret_cast<uint4*>(obase + static_cast<size_t>(p) * C + 8 * v) = pack8(f);
+            }
+        }
+    }
+}
+
 int gn_silu(const __half* src0, int C0, const __half* src1, int C1, const float* gamma, const float* beta,
             __half* out, int N, int S, int groups, float eps, bool do_silu, cudaStream_t stream) {
     const int C = C0 + C1;
     if (C % groups != 0 || C0 % 8 != 0 || C1 % 8 != 0) { set_error("gn_silu: C=%d+%d groups=%d unsupported", C0, C1, groups); return 2; }
     const int cpg = C / groups;
+    if (S <= 8 && (cpg == 8 || cpg == 16) && C0 % cpg == 0) {  // a group never straddles the two concatenated tensors
+        const int total = N * groups;
+        if (cpg == 8)
+            gn_silu_small_kernel<1><<<(total + 127) / 128, 128, 0, stream>>>(src0, C0, src1, C1, gamma, beta, out, N, S, groups, eps,
+                                                                          do_silu ? 1 : 0);
+        else
+            gn_silu_small_kernel<2><<<(total + 127) / 128, 128, 0, stream>>>(src0, C0, src1, C1, gamma, beta, out, N, S, groups, eps,
+                                                                          do_silu ? 1 : 0);
+        DDPM_CHECK_LAUNCH("gn_silu_small");
+        return 0;
+    }
     int gpc = 0;
     for (int g = 1; g <= groups; g <<= 1) {
         if (groups % g == 0 && (g * cpg) % 8 == 0 && (g * cpg >= 32 || g == groups)) { gpc = g; break; }

@@ -131,3 +131,21 @@ def test_conv_in_matches_torch(n, cin, hw, cout):
     got = st.sum(dim=1)
     assert torch.allclose(got[..., 0], want_s, rtol=1e-5, atol=1e-2), (got[..., 0] - want_s).abs().max()
     assert torch.allclose(got[..., 1], want_q, rtol=1e-5, atol=1e-2), (got[..., 1] - want_q).abs().max()
+
+
+@pytest.mark.parametrize("n,sp,c0,c1", [(37, (2, 2, 2), 256, 0), (5, (2, 2, 2), 256, 256), (9, (2, 2), 256, 0),
+                                        (3, (1, 1), 512, 0), (600, (2, 2, 2), 256, 256)])
+def test_groupnorm_small_maps(n, sp, c0, c1):
+    """Maps of up to 8 pixels (the 2 x 2 x 2 level of the 3-D UNet): the one-thread-per-(image, group) kernel."""
+    from ddpm_ood_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(n)
+    xs = [(torch.randn((n,) + sp + (c,), generator=g, device="cuda") * 1.5 + 0.3).half() for c in (c0, c1) if c]
+    C = c0 + c1
+    gamma = 1 + 0.1 * torch.randn(C, generator=g, device="cuda")
+    beta = 0.1 * torch.randn(C, generator=g, device="cuda")
+    for silu in (True, False):
+        want = _ref_gn(xs, gamma, beta, 32, 1e-6, silu)
+        got = ops.gn_silu(xs[0], xs[1] if c1 else None, gamma, beta, 32, 1e-6, silu).float()
+        err = (got - want).abs().max().item()
+        assert err < 4e-3 * max(1.0, want.abs().max().item()), (silu, err)
