@@ -728,9 +728,17 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_cha
     p.tiles_d = p.D;  // region tiles of a volume: one depth slab per tile
     p.tiles_n = pair ? (p.N + 1) / 2 : q.N;
     p.num_m_tiles = p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_n;
-    const int BN = (q.Cout % 256 == 0) ? 256 : 128;
+    int BN = (q.Cout % 256 == 0) ? 256 : 128;
+    int MT = BN == 256 ? 1 : 2;
+    if (!vol) {
+        // Small batches (BASELINE configs[0]: 8 images): when the default tiling leaves at least half of the clusters without
+        // a work item, halve the items - 128-wide N tiles of one M tile per CTA - so twice as many clusters share the launch
+        // (a kernel's duration is then one item's latency, and that halves)
+        const int items_default = ((p.num_m_tiles + 2 * MT - 1) / (2 * MT)) * (q.Cout / BN) * (q.upsample2 ? 4 : 1);
+        if (2 * items_default <= num_sms / 2) { BN = 128; MT = 1; }
+    }
     out->block_n = BN;
-    out->m_tiles_per_cta = BN == 256 ? 1 : 2;
+    out->m_tiles_per_cta = MT;
     p.num_n_tiles = q.Cout / BN;
     p.Cout = q.Cout;
     p.mode = EPI_STORE;
@@ -897,7 +905,11 @@ int conv_halo_launch(const ConvHaloLaunch& l, cudaStream_t stream) {
                                               HCfg<256, 1>::kSmemBytes);
         cudaError_t e4 = cudaFuncSetAttribute(conv_halo_kernel<128, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               HCfg<128, 2>::kSmemBytes);
-        const cudaError_t es[4] = {e1, e2, e3, e4};
+        cudaError_t e5 = cudaFuncSetAttribute(conv_halo_kernel<128, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              HCfg<128, 1>::kSmemBytes);
+        cudaError_t e6 = cudaFuncSetAttribute(conv_halo_kernel<128, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              HCfg<128, 1>::kSmemBytes);
+        const cudaError_t es[6] = {e1, e2, e3, e4, e5, e6};
         for (cudaError_t e : es) {
             if (e != cudaSuccess) {
                 set_error("conv_halo: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -907,7 +919,11 @@ int conv_halo_launch(const ConvHaloLaunch& l, cudaStream_t stream) {
         attr_set = true;
     }
     cudaError_t e;
-    if (l.p.pair_mode && l.block_n == 128)  // 3-D volumes, 128 output channels
+    if (l.block_n == 128 && l.m_tiles_per_cta == 1 && l.p.pair_mode)  // small batches (fine tiling)
+        e = launch_pdl(conv_halo_kernel<128, 1, true>, dim3(l.grid), dim3(kThreads), HCfg<128, 1>::kSmemBytes, stream, l.p);
+    else if (l.block_n == 128 && l.m_tiles_per_cta == 1)
+        e = launch_pdl(conv_halo_kernel<128, 1, false>, dim3(l.grid), dim3(kThreads), HCfg<128, 1>::kSmemBytes, stream, l.p);
+    else if (l.p.pair_mode && l.block_n == 128)  // 3-D volumes, 128 output channels
         e = launch_pdl(conv_halo_kernel<128, 2, true>, dim3(l.grid), dim3(kThreads), HCfg<128, 2>::kSmemBytes, stream, l.p);
     else if (l.p.pair_mode)
         e = launch_pdl(conv_halo_kernel<256, 1, true>, dim3(l.grid), dim3(kThreads), HCfg<256, 1>::kSmemBytes, stream, l.p);
