@@ -13,59 +13,61 @@ Three extra, optional flags that the reference does not have:
 import argparse
 import ast
 
+# (flag, type, default, what it does) - names, types and defaults are the reference's (reconstruct.py:7-141); the wording is ours
+_lit = ast.literal_eval
 FLAGS = [
-    # name, kwargs
-    ("--seed", dict(type=int, default=2, help="Random seed to use.")),
-    ("--output_dir", dict(help="Location for models.")),
-    ("--model_name", dict(help="Name of model.")),
-    ("--validation_ids", dict(help="Location of file with validation ids.")),
-    ("--in_ids", dict(help="Location of file with inlier ids.")),
-    ("--out_ids", dict(help="List of location of file with outlier ids.")),
-    ("--spatial_dimension", dict(default=2, type=int, help="Dimension of images: 2d or 3d.")),
-    ("--image_size", dict(default=None, help="Resize images.")),
-    ("--image_roi", dict(default=None, type=ast.literal_eval,
-                         help="Central ROI crop of inputs, as a tuple, with -1 to not crop a dimension.")),
-    ("--latent_pad", dict(default=None, type=ast.literal_eval,
-                          help="Padding applied to a latent so the U-net's two downsamplings divide it; a tuple in "
-                               "torch.nn.functional.pad order.")),
-    ("--vqvae_checkpoint", dict(default=None, help="Path to a VQ-VAE checkpoint, to reconstruct with an LDM.")),
-    ("--ddpm_checkpoint_epoch", dict(default=None, help="Epoch of a specific checkpoint; default is the best one.")),
-    ("--prediction_type", dict(default="epsilon", help="Scheduler prediction type: epsilon, sample or v_prediction.")),
-    ("--model_type", dict(default="small", help="Small or big model.")),
-    ("--beta_schedule", dict(default="linear", help="Linear or scaled linear")),
-    ("--beta_start", dict(type=float, default=1e-4, help="Beta start.")),
-    ("--beta_end", dict(type=float, default=2e-2, help="Beta end.")),
-    ("--b_scale", dict(type=float, default=1, help="Scale the data by a factor b before noising.")),
-    ("--snr_shift", dict(type=float, default=1, help="Shift the SNR of the noise scheduler by a factor.")),
-    ("--simplex_noise", dict(type=int, default=0, help="Use simplex instead of Gaussian noise.")),
-    ("--batch_size", dict(type=int, default=256, help="Batch size.")),
-    ("--augmentation", dict(type=int, default=0, help="Use of augmentation, 1 (True) or 0 (False).")),
-    ("--cache_data", dict(type=int, default=1, help="Whether or not to cache data in dataloaders.")),
-    ("--num_workers", dict(type=int, default=8, help="Number of loader workers")),
-    ("--first_n_val", dict(default=None, help="Only run on the first n samples from the val dataset.")),
-    ("--first_n", dict(default=None, help="Only run on the first n samples from each dataset.")),
-    ("--eval_checkpoint", dict(default=None, help="Select a specific checkpoint to evaluate on.")),
-    ("--drop_last", dict(default=False, help="Drop last non-complete batch..")),
-    ("--is_grayscale", dict(type=int, default=0, help="Is data grayscale.")),
-    ("--run_val", dict(type=int, default=1, help="Run reconstructions on val set.")),
-    ("--run_in", dict(type=int, default=1, help="Run reconstructions on in set.")),
-    ("--run_out", dict(type=int, default=1, help="Run reconstructions on out set.")),
-    ("--num_inference_steps", dict(type=int, default=100, help="Number of inference steps to use with the PLMS sampler.")),
-    ("--inference_skip_factor", dict(type=int, default=1,
-                                     help="Perform fewer reconstructions by skipping some t-values as starting points.")),
-    # extensions (see module docstring)
-    ("--plms_state", dict(default="carry", choices=["carry", "reset"], help="PLMS history across t-starts.")),
-    ("--honour_num_inference_steps", dict(type=int, default=0, help="Make --num_inference_steps effective.")),
-    ("--shard", dict(default="images", choices=["images", "t_starts"],
-                     help="Under torchrun: split images over ranks (the reference) or the t-start grid (needs "
-                          "--plms_state reset).")),
+    ("seed", int, 2, "RNG seed"),
+    ("output_dir", None, None, "directory that holds the run directories"),
+    ("model_name", None, None, "run directory under --output_dir (checkpoint in, ood/results_*.csv out)"),
+    ("validation_ids", None, None, "csv with the validation image paths"),
+    ("in_ids", None, None, "csv with the in-distribution image paths"),
+    ("out_ids", None, None, "comma-separated csv files, one per out-of-distribution set (suffix _vflip / _hflip: flipped)"),
+    ("spatial_dimension", int, 2, "2 or 3"),
+    ("image_size", None, None, "resize every image to this edge length"),
+    ("image_roi", _lit, None, "centre crop, a tuple; -1 keeps a dimension whole"),
+    ("latent_pad", _lit, None, "F.pad tuple applied to the latent so that the UNet's downsamplings divide it"),
+    ("vqvae_checkpoint", None, None, "stage-1 checkpoint of a latent diffusion model (vqvae_config.json next to it)"),
+    ("ddpm_checkpoint_epoch", None, None, "use checkpoint_<epoch>.pth instead of checkpoint.pth"),
+    ("prediction_type", None, "epsilon", "epsilon | sample | v_prediction"),
+    ("model_type", None, "small", "small | big"),
+    ("beta_schedule", None, "linear", "linear | scaled_linear_beta"),
+    ("beta_start", float, 1e-4, "first beta"),
+    ("beta_end", float, 2e-2, "last beta"),
+    ("b_scale", float, 1, "data scale applied before noising"),
+    ("snr_shift", float, 1, "SNR shift of the noise schedule"),
+    ("simplex_noise", int, 0, "1: simplex noise instead of Gaussian"),
+    ("batch_size", int, 256, "images per batch"),
+    ("augmentation", int, 0, "accepted for launch-script compatibility (training only)"),
+    ("cache_data", int, 1, "accepted for launch-script compatibility"),
+    ("num_workers", int, 8, "accepted for launch-script compatibility"),
+    ("first_n_val", None, None, "only the first n validation images"),
+    ("first_n", None, None, "only the first n images of every other set"),
+    ("eval_checkpoint", None, None, "accepted for launch-script compatibility"),
+    ("drop_last", None, False, "drop a trailing partial batch"),
+    ("is_grayscale", int, 0, "1: single-channel images"),
+    ("run_val", int, 1, "score the validation set"),
+    ("run_in", int, 1, "score the in-distribution set"),
+    ("run_out", int, 1, "score the out-of-distribution sets"),
+    ("num_inference_steps", int, 100, "PLMS steps (ignored unless --honour_num_inference_steps 1, like the reference)"),
+    ("inference_skip_factor", int, 1, "use every k-th timestep as a reconstruction starting point"),
+]
+EXTENSIONS = [  # see the module docstring
+    ("plms_state", dict(default="carry", choices=["carry", "reset"], help="PLMS history across the t-starts of a batch")),
+    ("honour_num_inference_steps", dict(type=int, default=0, help="1: --num_inference_steps takes effect")),
+    ("shard", dict(default="images", choices=["images", "t_starts"],
+                   help="what torchrun ranks divide: images, or the t-start grid (needs --plms_state reset)")),
 ]
 
 
 def build_parser() -> argparse.ArgumentParser:
     parser = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
-    for name, kw in FLAGS:
-        parser.add_argument(name, **kw)
+    for name, typ, default, text in FLAGS:
+        kw = dict(default=default, help=text)
+        if typ is not None:
+            kw["type"] = typ
+        parser.add_argument("--" + name, **kw)
+    for name, kw in EXTENSIONS:
+        parser.add_argument("--" + name, **kw)
     return parser
 
 
