@@ -9,8 +9,9 @@ DiffusionModelUNet with random non-zero weights, scaled_linear_beta 0.0015->0.01
 inference_skip_factor=4 -> 25 t-starts, 1250 UNet evaluations per batch. A "step" is one batch of `--batch` images x 25
 t-starts. The batch size is the reference CLI's free `--batch_size` knob (default 256, reconstruct.py:89; BASELINE.json
 does not fix it): the default here is 1184 = 16 images per CTA pair of the 148-SM part, which makes every UNet level a
-whole number of waves and amortises each kernel's prologue over two work items at the 8-pixel level (measured: 2542
-reconstructions/s, 2490 at 592, 2250 at 256); `--batch 256` reproduces the reference default.
+whole number of waves and amortises each kernel's prologue over two work items at the 8-pixel level (round 2, builder-run:
+2670-2787 reconstructions/s depending on the box, ~2420 at 256); `--batch 256` reproduces the reference default, and the
+default run appends that batch and BASELINE configs[0] (batch 8, skip 16) as `secondary` lines measured on the same box.
 Under torchrun every rank processes its own batch (images are what the reference shards, SURVEY.md §8e; weak scaling);
 the only collective is the gather of the [25, B, 2] score tensor.
 """
@@ -79,6 +80,9 @@ def parse():
                          "ONE global batch, the t-start grid split over ranks (strong scaling, needs plms_state=reset)")
     ap.add_argument("--profile_every", type=int, default=50, help="event-profile every n-th UNet forward (0 = off)")
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_secondary", action="store_true",
+                    help="skip the secondary lines of the default run (batch 256 = the reference CLI's default, and "
+                         "BASELINE configs[0] = batch 8 / skip 16), which are measured after the headline on the same box")
     a = ap.parse_args()
     w = WORKLOADS[a.config]
     if a.batch is None:
@@ -254,6 +258,62 @@ class ClockSampler:
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ secondary lines
+def _secondary_line(torch, eng, model, pl, dev, w, B, skip, steps, warmup, profile_every, peak_tf, label):
+    """One more measurement of the SAME engine at another batch / grid (N = 1 only), in the headline's form: device-timed
+    `value`, `e2e` with host buffers (H2D + D2H inside the timed region) and the conv family's roofline fraction."""
+    import math
+
+    from ddpm_ood_b200.synthetic import chain_lengths
+
+    chains = chain_lengths(w["steps"], skip)
+    n_t = len(chains)
+    g = torch.Generator().manual_seed(4321)
+    host_images = torch.rand((B, w["ch"]) + tuple(w["size"]), generator=g).pin_memory()
+    dev_images = host_images.to(dev)
+
+    def step(images):
+        res = eng.score_batch(images, skip)
+        return torch.stack([res["perceptual_difference"], res["mse"]], dim=-1)
+
+    for _ in range(warmup):
+        step(dev_images)
+    torch.cuda.synchronize()
+    graph_mode = B * math.prod(w["size"]) <= 64 * 1024
+    if profile_every > 0 and not graph_mode:
+        model.set_profile(profile_every)
+        model.read_profile(reset=True)
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    e[0].record()
+    for _ in range(steps):
+        step(dev_images)
+    e[1].record()
+    torch.cuda.synchronize()
+    prof = model.read_profile(reset=True) if profile_every > 0 and not graph_mode else {}
+    model.set_profile(0)
+    e[2].record()
+    for _ in range(steps):
+        host_scores = step(host_images).cpu()
+    e[3].record()
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(host_scores).all())
+    ms, ms_e2e = e[0].elapsed_time(e[1]), e[2].elapsed_time(e[3])
+    total = B * n_t * steps
+    out = {"workload": f"{label}, skip_factor={skip} ({n_t} t-starts), batch={B}, plms_state=carry",
+           "value": total / (ms / 1000.0), "unit": UNIT, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+           "e2e": {"value": total / (ms_e2e / 1000.0), "unit": UNIT, "h2d_bytes_per_step": host_images.numel() * 4,
+                   "d2h_bytes_per_step": n_t * B * 2 * 4},
+           "chain_launch": "one CUDA graph per t-start chain" if graph_mode
+                           else "per-kernel launches with programmatic dependent launch"}
+    if prof and "conv_gemm" in prof:
+        cg = prof["conv_gemm"]
+        achieved = cg["flops"] / (cg["ms"] / 1000.0) / 1e12
+        out["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                           "frac": achieved / peak_tf, "launches_timed": cg["launches"]}
+        out["unet_fwd_ms"] = prof["_total"]["ms"] / max(prof["_total"]["forwards"], 1)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -475,6 +535,21 @@ def run_ours(args):
         "unet_frac_of_tensor_peak_whole_step": unet_tflops / (peak_tf * world),
         "breakdown": breakdown,
     }
+    if world == 1 and not args.no_secondary and args.config == "fmnist" and args.batch == w["batch"]:
+        # driver-visible secondary lines, same engine / weights / box, measured after the headline
+        line["secondary"] = [
+            _secondary_line(torch, eng, model, pl, dev, w, 256, args.skip, 2, 3, args.profile_every, peak_tf,
+                            w["label"] + " at the reference CLI's default batch"),
+            _secondary_line(torch, eng, model, pl, dev, w, WORKLOADS["fmnist_b8"]["batch"],
+                            WORKLOADS["fmnist_b8"]["run_skip"], 5, 3, args.profile_every, peak_tf,
+                            WORKLOADS["fmnist_b8"]["label"]),
+        ]
+        if not args.no_cpu_baseline:  # the CPU arm at the IDENTICAL batch and grid (BASELINE configs[0] is its own case)
+            a8 = argparse.Namespace(**{**vars(args), "config": "fmnist_b8", "batch": WORKLOADS["fmnist_b8"]["batch"],
+                                       "skip": WORKLOADS["fmnist_b8"]["run_skip"]})
+            rates8, cores8, sample8, _ = _cpu_sample(a8, budget_s=25.0, n_runs=1)
+            line["secondary"][1]["cpu_baseline"] = {"value": rates8[0], "unit": UNIT, "cores": cores8, "kind": "port",
+                                                    "sample": sample8}
     if world == 1 and not args.no_cpu_baseline:
         rates, cores, sample, _ = _cpu_sample(args, budget_s=25.0, n_runs=1)
         line["cpu_baseline"] = {"value": rates[0], "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}

@@ -145,14 +145,27 @@ int ddpm_conv_forward(const ddpm_conv_args* a, void* stream) {
         if (rc) return rc;
         rc = ddpm::conv_halo_launch(hl, static_cast<cudaStream_t>(stream));
         if (!rc && hl.p.dbg_cycles && getenv("DDPM_HALO_CYCLES_PRINT")) {  // experiment only
-            long long h[8 * 74];
-            if (!ddpm::conv_halo_read_cycles(hl, h, 8 * 74)) {
+            long long h[16 * 128];
+            if (!ddpm::conv_halo_read_cycles(hl, h, 16 * 128)) {
                 double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 const int nc = hl.grid / 2;
                 for (int i = 0; i < nc; ++i) for (int k = 0; k < 8; ++k) s[k] += static_cast<double>(h[8 * i + k]);
                 fprintf(stderr, "halo cycles (mean over %d clusters): total %.0f | MMA waits: tempty %.0f a_ready %.0f b_full %.0f | "
                         "A producer waits a_empty %.0f | transform: table %.0f wait a_full %.0f work %.0f\n",
                         nc, s[0] / nc, s[1] / nc, s[2] / nc, s[3] / nc, s[4] / nc, s[5] / nc, s[6] / nc, s[7] / nc);
+                // wall-clock timeline (ns after the earliest kernel entry): per stamp the min / max over the clusters
+                const long long* tl = h + 8 * 128;
+                long long t0 = tl[0];
+                for (int i = 0; i < nc; ++i) if (tl[8 * i] < t0) t0 = tl[8 * i];
+                static const char* names[8] = {"entry", "prologue done", "pdl_wait done", "first A ready", "MMA loop end",
+                                               "last acc full", "epilogue done", "exit"};
+                fprintf(stderr, "halo timeline ns (min..max over clusters):");
+                for (int k = 0; k < 8; ++k) {
+                    long long lo = tl[k] - t0, hi = lo;
+                    for (int i = 0; i < nc; ++i) { const long long v = tl[8 * i + k] - t0; if (v < lo) lo = v; if (v > hi) hi = v; }
+                    fprintf(stderr, " %s %lld..%lld |", names[k], lo, hi);
+                }
+                fprintf(stderr, "\n");
             }
         }
         return rc;

@@ -82,7 +82,7 @@ struct ConvGemmParams {
 // Host side: filled by conv_prepare(), launched by conv_launch().
 struct ConvLaunch {
     ConvGemmParams p;
-    int block_n;          // 128 or 256
+    int block_n;          // 128 or 256 (conv_halo, small batches: 64 too)
     int m_tiles_per_cta;  // 1, or 2 (block_n == 128 only): two 128-pixel tiles share each weight tile
     int cta_pair;         // 1: conv_gemm_2cta_kernel (clusters of 2, tcgen05 cta_group::2)
     int grid;

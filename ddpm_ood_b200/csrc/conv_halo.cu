@@ -77,14 +77,23 @@ struct HCfg {
     static constexpr int kARingUnits = MT == 2 ? 150 + (7 - HALO_B128) * 8 : HALO_A256 * 25;
     static constexpr int kARingBytes = kARingUnits * 1024;
     static constexpr int kBHalfBytes = (BN / 2) * kBlockK * 2;  // this CTA's half of a weight tile
-    static constexpr int kBStages = MT == 2 ? HALO_B128 : HALO_B256;
+    // The narrow tiles of the small-batch tilings (MT == 1, BN <= 128) group up to kTapGroup taps of a 3x3 segment into
+    // one weight stage: the MMA warp spends ~370 cycles per barrier hand-off (wait, elect, commit; measured with the MMAs
+    // skipped, profiles/r02_halo_small_batch_s26.md), which a wide tile hides behind 512 cycles of MMAs per tap and a
+    // narrow one (128-256 cycles per tap) does not.
+    static constexpr int kTapGroup = (MT == 1 && BN <= 128) ? 3 : 1;
+    static constexpr int kBStageBytes = kTapGroup * kBHalfBytes;
+    static constexpr int kBStages = MT == 2 ? HALO_B128 : (BN == 256 ? HALO_B256 : (BN == 128 ? 4 : 6));
     static constexpr int kAddBytes = 2 * BN * 4 * (MT == 2 ? 1 : 2);  // epilogue addend rows: [MT or 2 images][BN] fp32
+    // Measured dead end (profiles/r02_halo_small_batch_s26.md): rotating the K = 16 steps of a stage over two / four
+    // accumulators (summed in the epilogue) does not shorten the K loop of the narrow tiles - a cta_group::2 M = 256 MMA
+    // takes ~90 cycles at N = 64 with one accumulator or four, so it is not the accumulator dependency that paces them.
     static constexpr int kAccCols = MT * BN;
     static constexpr int kTmemCols = 2 * kAccCols;
     static constexpr int kAbBytes = 2 * kMaxGnChannels * 8;  // per-item (scale, shift) rows of the (up to 2) images
     static constexpr int kGnScratchBytes = (kMaxGnChannels / 4) * 8 + 256 * 8;  // statistics reduction scratch
     static constexpr int kSmemBytes =
-        kARingBytes + kBStages * kBHalfBytes + kAbBytes + kGnScratchBytes + kAddBytes + 1024 /*align*/ + 512 /*barriers*/;
+        kARingBytes + kBStages * kBStageBytes + kAbBytes + kGnScratchBytes + kAddBytes + 1024 /*align*/ + 512 /*barriers*/;
     static_assert(kTmemCols <= 512, "TMEM");
     static_assert(kSmemBytes <= 227 * 1024, "shared memory");
     static_assert((3 * kAFlight + 2 * kBStages + 4) * 8 + 8 <= 512, "barrier block");
@@ -181,6 +190,14 @@ __device__ __forceinline__ void xform_row(int tid, int i, bool halo, int& row, i
     }
 }
 
+__device__ __forceinline__ long long gtime_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// experiment only (DDPM_HALO_CYCLES): wall-clock stamps of one launch's phases, leader CTA of every cluster
+#define HALO_STAMP(k) do { if (hp.dbg_cycles && rank == 0) hp.dbg_cycles[8 * 128 + 8 * cluster_id_ + (k)] = gtime_ns(); } while (0)
+
 template <int BN, int MT, bool PAIR>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     conv_halo_kernel(const __grid_constant__ ConvHaloParams hp) {
@@ -192,11 +209,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     using Walk = AWalk<MT, PAIR, C::kARingUnits>;
     uint8_t* smem_a = smem;                                   // A ring (1 KB units, see AWalk)
-    uint8_t* smem_b = smem + C::kARingBytes;                  // [kBStages][BN/2 rows x 128 B]
-    float2* s_ab = reinterpret_cast<float2*>(smem_b + C::kBStages * C::kBHalfBytes);  // [2][kMaxGnChannels]
-    float* s_gn = reinterpret_cast<float*>(smem_b + C::kBStages * C::kBHalfBytes + C::kAbBytes);  // s_qs | s_qq | s_sub
+    uint8_t* smem_b = smem + C::kARingBytes;                  // [kBStages][kTapGroup][BN/2 rows x 128 B]
+    float2* s_ab = reinterpret_cast<float2*>(smem_b + C::kBStages * C::kBStageBytes);  // [2][kMaxGnChannels]
+    float* s_gn = reinterpret_cast<float*>(smem_b + C::kBStages * C::kBStageBytes + C::kAbBytes);  // s_qs | s_qq | s_sub
     float* s_add = s_gn + C::kGnScratchBytes / 4;  // [MT (region) | 2 images (pair)][BN]: bias + chan_add per column
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + C::kBStages * C::kBHalfBytes + C::kAbBytes + C::kGnScratchBytes +
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + C::kBStages * C::kBStageBytes + C::kAbBytes + C::kGnScratchBytes +
                                                  C::kAddBytes);
     uint64_t* a_full = bars;                      // per CTA: TMA -> transform warps
     uint64_t* a_ready = a_full + kAFlight;        // leader's copy: transform warps of both CTAs -> MMA
@@ -210,6 +227,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
+    const int cluster_id_ = blockIdx.x >> 1;
+    if (threadIdx.x == 0) HALO_STAMP(0);
     ptx::pdl_trigger();
 
     if (warp == kWarpA && lane == 0) {
@@ -238,7 +257,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     ptx::cluster_sync_all();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) HALO_STAMP(1);
     ptx::pdl_wait();  // everything above overlapped the previous kernel's tail
+    if (threadIdx.x == 0) HALO_STAMP(2);
 
     // work item = 2*MT consecutive M tiles (MT per CTA) x one N tile; N tiles of the same pixels run on neighbouring
     // clusters at the same time (the second read of the input hits L2).
@@ -337,12 +358,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 const int taps = hp.seg_taps[seg];
                 {
                     const int kc = hp.seg_kcol0[seg] + chunk * kBlockK + static_cast<int>(hp.sched_kd[st]) * 9 * hp.seg_cin[seg];
-                    for (int tap = 0; tap < taps; ++tap) {
+                    for (int tap0 = 0; tap0 < taps; tap0 += C::kTapGroup) {  // one weight stage = up to kTapGroup taps
+                        const int gt = taps - tap0 < C::kTapGroup ? taps - tap0 : C::kTapGroup;
                         ptx::mbar_wait(&b_empty[sb], pb ^ 1);
                         if (ptx::elect_one()) {
-                            if (rank == 0) ptx::mbar_arrive_expect_tx(&b_full[sb], 2 * C::kBHalfBytes);
-                            ptx::tma_load_2d_2cta(smem_b + sb * C::kBHalfBytes, &p.tmB, &b_full[sb],
-                                                  kc + tap * hp.seg_cin[seg], brow);
+                            if (rank == 0) ptx::mbar_arrive_expect_tx(&b_full[sb], 2 * gt * C::kBHalfBytes);
+                            for (int j = 0; j < gt; ++j)
+                                ptx::tma_load_2d_2cta(smem_b + sb * C::kBStageBytes + j * C::kBHalfBytes, &p.tmB, &b_full[sb],
+                                                      kc + (tap0 + j) * hp.seg_cin[seg], brow);
                         }
                         __syncwarp();
                         if (++sb == C::kBStages) { sb = 0; pb ^= 1; }
@@ -381,8 +404,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                         t0 = prof ? clock64() : 0;
                         ptx::mbar_wait(&a_ready[sa], pa);
                         if (prof) cyc_a += clock64() - t0;
+                        if (prof && lane == 0 && item == cluster_id && st == 0) HALO_STAMP(3);
                         ptx::tc_fence_after();
                         const uint32_t a_base = ptx::smem_u32(smem_a + a_off);
+                        if constexpr (C::kTapGroup == 1) {
                         for (int tap = 0; tap < taps; ++tap) {
                             // tap (dh, dw): rows (h + 1 + dh) * pitch + (w + 1 + dw) of the haloed tile
                             // taps == 4: sub-pixel phase (ph, pw) of an upsample conv, tap (a, b) reads low-res pixel
@@ -412,6 +437,72 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                             accumulate = 1;
                             if (++sb == C::kBStages) { sb = 0; pb ^= 1; }
                         }
+                        } else if (taps == 9) {
+                            // narrow tiles, 3x3 stage: one weight stage per tap ROW, its 12 MMAs fully unrolled with constant
+                            // descriptor offsets (the MMA warp's own instruction stream paces these kernels)
+                            const bool skip_mma = (hp.dbg & 4) != 0;
+#pragma unroll
+                            for (int g = 0; g < 3; ++g) {
+                                t0 = prof ? clock64() : 0;
+                                ptx::mbar_wait(&b_full[sb], pb);
+                                if (prof) cyc_b += clock64() - t0;
+                                ptx::tc_fence_after();
+                                if (ptx::elect_one()) {
+                                    const uint64_t da_row = desc_hi | ((a_base + g * (PAIR ? 2 : 1) * (kTileW + 2) * 128) >> 4);
+                                    const uint64_t db_s = ptx::make_desc_k128(ptx::smem_u32(smem_b + sb * C::kBStageBytes));
+                                    if (!skip_mma) {
+#pragma unroll
+                                        for (int j = 0; j < 3; ++j)
+#pragma unroll
+                                            for (int k = 0; k < kBlockK / 16; ++k)
+                                                ptx::umma_f16_2cta(d_tmem, da_row + (8 * j + 2 * k),
+                                                                   db_s + (j * (C::kBHalfBytes >> 4) + 2 * k), idesc,
+                                                                   accumulate | (g | j | k));
+                                    }
+                                    ptx::umma_commit_2cta(&b_empty[sb]);
+                                    if (g == 2) ptx::umma_commit_2cta(&a_empty[sa]);
+                                }
+                                __syncwarp();
+                                if (++sb == C::kBStages) { sb = 0; pb ^= 1; }
+                            }
+                            accumulate = 1;
+                        } else {
+                        for (int tap0 = 0; tap0 < taps; tap0 += C::kTapGroup) {  // one weight stage = up to kTapGroup taps
+                            const int gt = taps - tap0 < C::kTapGroup ? taps - tap0 : C::kTapGroup;
+                            t0 = prof ? clock64() : 0;
+                            ptx::mbar_wait(&b_full[sb], pb);
+                            if (prof) cyc_b += clock64() - t0;
+                            ptx::tc_fence_after();
+                            if (ptx::elect_one()) {
+                                for (int j = 0; j < gt; ++j) {
+                                    const int tap = tap0 + j;
+                                    // tap (dh, dw): rows (h + 1 + dh) * pitch + (w + 1 + dw) of the haloed tile
+                                    // taps == 4: sub-pixel phase (ph, pw) of an upsample conv, tap (a, b) reads low-res
+                                    // pixel (h + ph - 1 + a, w + pw - 1 + b): the same nine views, four per phase
+                                    const uint32_t th_ = taps == 9 ? tap / 3 : (taps == 4 ? ((phase >> 1) & 1) + (tap >> 1) : 0);
+                                    const uint32_t tw_ = taps == 9 ? tap % 3 : (taps == 4 ? (phase & 1) + (tap & 1) : 0);
+                                    const uint32_t row0 = th_ * (PAIR ? 2 * pitch : pitch) + tw_;
+                                    const uint64_t da0 = desc_hi | ((a_base + row0 * 128) >> 4);
+                                    const uint64_t db0 = ptx::make_desc_k128(
+                                        ptx::smem_u32(smem_b + sb * C::kBStageBytes + j * C::kBHalfBytes));
+#pragma unroll
+                                    for (int k = 0; k < kBlockK / 16; ++k) {
+                                        if (hp.dbg & 4) break;
+#pragma unroll
+                                        for (int mt = 0; mt < MT; ++mt)
+                                            ptx::umma_f16_2cta(d_tmem + mt * BN, da0 + (mt * (a_tile >> 4) + 2 * k),
+                                                               db0 + 2 * k, idesc, accumulate | k);
+                                    }
+                                    accumulate = 1;
+                                }
+                                ptx::umma_commit_2cta(&b_empty[sb]);
+                                if (tap0 + gt == taps) ptx::umma_commit_2cta(&a_empty[sa]);
+                            }
+                            __syncwarp();
+                            accumulate = 1;
+                            if (++sb == C::kBStages) { sb = 0; pb ^= 1; }
+                        }
+                        }
                     }
                 }
                 if (ptx::elect_one()) ptx::umma_commit_2cta(&tfull_bar[as]);
@@ -421,6 +512,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             if (prof && lane == 0) {
                 long long* o = hp.dbg_cycles + 8 * cluster_id;
                 o[0] = clock64() - t_begin; o[1] = cyc_t; o[2] = cyc_a; o[3] = cyc_b;
+                HALO_STAMP(4);
             }
         }
     } else if (warp == kWarpTmem) {
@@ -634,6 +726,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             }
             ptx::mbar_wait(&tfull_bar[as], pt);
             ptx::tc_fence_after();
+            if (threadIdx.x == 0 && item + num_clusters >= total_items) HALO_STAMP(5);
             if (!(hp.dbg & 2)) {
 #pragma unroll 1
                 for (int mt = 0; mt < MT; ++mt)
@@ -646,11 +739,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             if (lane == 0) ptx::mbar_arrive_leader(&tempty_bar[as]);
             if (++as == 2) { as = 0; pt ^= 1; }
         }
+        if (threadIdx.x == 0) HALO_STAMP(6);
     }
 
     ptx::tc_fence_before();
     __syncthreads();
     ptx::cluster_sync_all();
+    if (threadIdx.x == 0) HALO_STAMP(7);
     if (warp == kWarpTmem) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc_2cta<C::kTmemCols>(tmem_base);
@@ -733,9 +828,19 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_cha
     if (!vol) {
         // Small batches (BASELINE configs[0]: 8 images): when the default tiling leaves at least half of the clusters without
         // a work item, halve the items - 128-wide N tiles of one M tile per CTA - so twice as many clusters share the launch
-        // (a kernel's duration is then one item's latency, and that halves)
-        const int items_default = ((p.num_m_tiles + 2 * MT - 1) / (2 * MT)) * (q.Cout / BN) * (q.upsample2 ? 4 : 1);
-        if (2 * items_default <= num_sms / 2) { BN = 128; MT = 1; }
+        // (a kernel's duration is then one item's latency, and that halves); and once more - 64-wide N tiles - while the
+        // finer items still fit the clusters in one wave. DDPM_HALO_FINE (tests): 0 = default tiling only, 1 = down to
+        // 128-wide tiles, unset / 2 = down to 64-wide tiles.
+        const char* fe = getenv("DDPM_HALO_FINE");
+        const int fine_max = fe ? atoi(fe) : 2;
+        const int clusters = num_sms / 2;
+        const int phases = q.upsample2 ? 4 : 1;
+        const int items_default = ((p.num_m_tiles + 2 * MT - 1) / (2 * MT)) * (q.Cout / BN) * phases;
+        if (fine_max >= 1 && 2 * items_default <= clusters) {
+            BN = 128; MT = 1;
+            const int items_128 = ((p.num_m_tiles + 1) / 2) * (q.Cout / 128) * phases;
+            if (fine_max >= 2 && 2 * items_128 <= clusters) BN = 64;
+        }
     }
     out->block_n = BN;
     out->m_tiles_per_cta = MT;
@@ -865,7 +970,7 @@ int conv_halo_prepare(const ConvProblem& q, const float* gn_ab_in, int gn_ab_cha
         p.dbg = hp.dbg;
         static long long* cyc_buf = nullptr;  // experiment only: one buffer for the process, read back by the caller
         if (getenv("DDPM_HALO_CYCLES")) {
-            if (!cyc_buf) cudaMalloc(&cyc_buf, 8 * 128 * sizeof(long long));
+            if (!cyc_buf) cudaMalloc(&cyc_buf, 16 * 128 * sizeof(long long));
             hp.dbg_cycles = cyc_buf;
         }
     }
@@ -909,7 +1014,11 @@ int conv_halo_launch(const ConvHaloLaunch& l, cudaStream_t stream) {
                                               HCfg<128, 1>::kSmemBytes);
         cudaError_t e6 = cudaFuncSetAttribute(conv_halo_kernel<128, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               HCfg<128, 1>::kSmemBytes);
-        const cudaError_t es[6] = {e1, e2, e3, e4, e5, e6};
+        cudaError_t e7 = cudaFuncSetAttribute(conv_halo_kernel<64, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              HCfg<64, 1>::kSmemBytes);
+        cudaError_t e8 = cudaFuncSetAttribute(conv_halo_kernel<64, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              HCfg<64, 1>::kSmemBytes);
+        const cudaError_t es[8] = {e1, e2, e3, e4, e5, e6, e7, e8};
         for (cudaError_t e : es) {
             if (e != cudaSuccess) {
                 set_error("conv_halo: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -919,7 +1028,11 @@ int conv_halo_launch(const ConvHaloLaunch& l, cudaStream_t stream) {
         attr_set = true;
     }
     cudaError_t e;
-    if (l.block_n == 128 && l.m_tiles_per_cta == 1 && l.p.pair_mode)  // small batches (fine tiling)
+    if (l.block_n == 64 && l.p.pair_mode)  // small batches (finest tiling)
+        e = launch_pdl(conv_halo_kernel<64, 1, true>, dim3(l.grid), dim3(kThreads), HCfg<64, 1>::kSmemBytes, stream, l.p);
+    else if (l.block_n == 64)
+        e = launch_pdl(conv_halo_kernel<64, 1, false>, dim3(l.grid), dim3(kThreads), HCfg<64, 1>::kSmemBytes, stream, l.p);
+    else if (l.block_n == 128 && l.m_tiles_per_cta == 1 && l.p.pair_mode)  // small batches (fine tiling)
         e = launch_pdl(conv_halo_kernel<128, 1, true>, dim3(l.grid), dim3(kThreads), HCfg<128, 1>::kSmemBytes, stream, l.p);
     else if (l.block_n == 128 && l.m_tiles_per_cta == 1)
         e = launch_pdl(conv_halo_kernel<128, 1, false>, dim3(l.grid), dim3(kThreads), HCfg<128, 1>::kSmemBytes, stream, l.p);

@@ -174,6 +174,23 @@ def test_conv_halo_case(name, gn):
     assert mx < 3e-3, (name, rel, mx)
 
 
+# Small-batch tilings of the halo kernel: with few work items the host halves the items' N extent (128-, then 64-wide N
+# tiles of one M tile per CTA) so that more clusters share a launch. DDPM_HALO_FINE pins the finest level allowed, so the
+# same small problems run on every instantiation (0: <256,1> / <128,2>; 1: <128,1>; 2: <64,1>).
+FINE_CASES = ["halo_32px_128to128", "halo_16px_128to256_bias_temb_res", "halo_conv2_plus_1x1_skip_concat",
+              "halo_28px_ragged_tiles", "halo_512_out_channels", "halo_pair_8px_256to256_odd_n",
+              "halo_pair_8px_concat_plus_skip", "halo_pair_7px"]
+
+
+@pytest.mark.parametrize("fine", ["0", "1", "2"], ids=["default_tiles", "n128_tiles", "n64_tiles"])
+@pytest.mark.parametrize("name", FINE_CASES)
+def test_conv_halo_small_batch_tilings(name, fine, monkeypatch):
+    monkeypatch.setenv("DDPM_HALO_FINE", fine)
+    rel, mx = _run_case(**HALO_CASES[name], impl=3, gn=True, stats=True)
+    assert rel < 6e-4, (name, fine, rel, mx)
+    assert mx < 3e-3, (name, fine, rel, mx)
+
+
 @pytest.mark.parametrize("gn", [False, True], ids=["raw", "gn_silu_on_the_fly"])
 def test_conv_halo_concat_inputs_one_weight(gn):
     """conv3x3(cat(a, b)) + 1x1 skip conv over a third tensor with ONE torch-layout weight for the 3x3 part (K ordered
@@ -344,3 +361,11 @@ def test_upsample_conv_as_subpixel_phases(name, impl):
         o = out.float().reshape(n, -1, c // 4, 4)
         assert torch.allclose(st.sum(1)[..., 0], o.sum(dim=(1, 3)), rtol=1e-5, atol=1e-2)
         assert torch.allclose(st.sum(1)[..., 1], (o * o).sum(dim=(1, 3)), rtol=1e-5, atol=1e-2)
+
+
+@pytest.mark.parametrize("fine", ["0", "1"], ids=["default_tiles", "n128_tiles"])
+@pytest.mark.parametrize("name", ["up2d_8to16_256", "up2d_16to32_256_paired", "up2d_7to14_256"])
+def test_upsample_conv_halo_small_batch_tilings(name, fine, monkeypatch):
+    """The sub-pixel upsample conv on the coarser tilings too (the default, 64-wide N tiles, is the case above)."""
+    monkeypatch.setenv("DDPM_HALO_FINE", fine)
+    test_upsample_conv_as_subpixel_phases(name, 3)
