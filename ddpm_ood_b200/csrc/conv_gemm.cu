@@ -546,11 +546,8 @@ int conv_prepare(const ConvProblem& q, int num_sms, ConvLaunch* out) {
     }
     for (int s = q.n_seg; s < kMaxSeg; ++s) p.seg_kb_end[s] = kb;
     p.num_kb = kb;
-    static int allow_pair = -1;
-    if (allow_pair < 0) {
-        const char* e = getenv("DDPM_CONV_2CTA");
-        allow_pair = (e && atoi(e) == 0) ? 0 : 1;
-    }
+    const char* pair_env = getenv("DDPM_CONV_2CTA");  // tests: 0 = single-CTA tiles only (read at plan time)
+    const int allow_pair = (pair_env && atoi(pair_env) == 0) ? 0 : 1;
     const int tiles = p.num_m_tiles * p.num_phases;  // 128-pixel tiles per N tile
     out->m_tiles_per_cta = 1;
     out->cta_pair = 0;

@@ -874,7 +874,8 @@ int UNet::build_plan(Plan& plan, int N, int D, int H, int W, void* ws, size_t ws
                     // 2-D: on the halo-tile kernel (the four taps of a phase are views of ONE staged low-resolution tile:
                     // a quarter of the im2col kernel's A traffic). Round 1 measured this slower (short 4-tap items were
                     // epilogue-bound); with 256-bit epilogue stores and prefetched addends it is +1.7 % on the same box.
-                    static const bool up_halo = !(getenv("DDPM_UPCONV_HALO") && atoi(getenv("DDPM_UPCONV_HALO")) == 0);  // A/B switch
+                    const char* uh = getenv("DDPM_UPCONV_HALO");  // tests: 0 = the im2col-tile phases (read at plan time)
+                    const bool up_halo = !(uh && atoi(uh) == 0);
                     const bool on_halo = up_halo && use_halo_ && conv_halo_supported(q);
                     Act o = shape_act(h.C, h.D * fd, h.H * 2, h.W * 2);
                     if (!measure) {
@@ -1115,7 +1116,8 @@ int UNet::run_chain(int n_steps, const int* timesteps, const PlmsStep* steps, fl
     // configs[0]) a forward's ~45 kernels are shorter than their launch work. Policy: replay when one forward covers at
     // most kGraphPixels pixels; DDPM_CHAIN_GRAPH=0 / 1 forces it off / on.
     constexpr long long kGraphPixels = 64 * 1024;
-    static const int graph_env = getenv("DDPM_CHAIN_GRAPH") ? (atoi(getenv("DDPM_CHAIN_GRAPH")) != 0 ? 1 : 0) : -1;
+    const char* ge = getenv("DDPM_CHAIN_GRAPH");  // once per chain, not per launch
+    const int graph_env = ge ? (atoi(ge) != 0 ? 1 : 0) : -1;
     const bool want_graph = graph_env >= 0 ? graph_env == 1 : static_cast<long long>(N) * D * H * W <= kGraphPixels;
     if (!want_graph || !use_chain_graph_ || profile_every_ > 0 || !chain_warm_ || n_steps < 1) {
         int rc = run_plain();

@@ -918,7 +918,8 @@ __global__ void __launch_bounds__(256, CIN == 1 ? 2 : 1) conv_in_mma_kernel(cons
 }
 
 static bool conv_in_mma_ok(int Cin, int Cout, int H, int W, int kd) {
-    static const bool off = getenv("DDPM_CONV_IN_SCALAR") && atoi(getenv("DDPM_CONV_IN_SCALAR"));
+    const char* se = getenv("DDPM_CONV_IN_SCALAR");  // tests: 1 = the register-tile kernel for every shape
+    const bool off = se && atoi(se);
     return !off && kd == 1 && (Cin == 1 || Cin == 3) && Cout % 128 == 0 && W <= 128 && H >= 1;
 }
 
@@ -1418,7 +1419,8 @@ int gn_apply_taps(const __half* src, int C, const float* st, int parts, const fl
     dim3 grid((S + chunk - 1) / chunk, N);
     const int cpg = C / groups;
     cudaError_t e;
-    static const bool scalar = getenv("DDPM_TAPS_SCALAR") && atoi(getenv("DDPM_TAPS_SCALAR"));
+    const char* se = getenv("DDPM_TAPS_SCALAR");  // tests: 1 = the CUDA-core tap kernel
+    const bool scalar = se && atoi(se);
     if (scalar) {
         int ch = S;
         while (ch > 32 && static_cast<long long>(N) * ((S + ch - 1) / ch) < 2 * 148 && ch % 2 == 0) ch >>= 1;

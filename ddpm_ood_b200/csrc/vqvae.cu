@@ -474,7 +474,8 @@ int VqVae::build(Plan& plan, bool decode, int N, int D, int H, int W, void* ws, 
     const int sms = num_sms();
     int rc = 0;
     plan.ops.clear();
-    static const bool halo_off = getenv("DDPM_VQ_HALO") && atoi(getenv("DDPM_VQ_HALO")) == 0;  // A/B switch for tests
+    const char* vh = getenv("DDPM_VQ_HALO");  // tests: 0 = every conv on the im2col-tile kernel (read at plan time)
+    const bool halo_off = vh && atoi(vh) == 0;
     auto gemm = [&](ConvProblem q) {
         Op op{};
         // stride-1 3x3(x3) convs (residual units, the latent-side convs): the halo-tile kernel stages each input tile once

@@ -246,3 +246,60 @@ def test_identity_residual_on_the_tensor_pipe_equals_epilogue_add(name, monkeypa
     with torch.no_grad():
         want = ref(x.cpu(), t.cpu())
     assert _rel(outs["1"], want) < 4e-3 and _rel(outs["0"], want) < 4e-3
+
+
+# Every shape-dependent fallback of the engine is also reachable through an environment switch (read when a plan is
+# built), so the paths a large or odd shape would take are checked on the small parity shapes too: the im2col-tile conv
+# kernel instead of the halo-tile one, precomputed scale/shift tables, the stand-alone upsample + conv, the un-fused
+# attention chain with and without the tensor-core core, single-CTA conv tiles, the CUDA-core head / tail kernels, and
+# the coarser tilings of the halo kernel.
+ENGINE_SWITCHES = {
+    "im2col_convs": {"DDPM_CONV_HALO": "0"},
+    "scale_shift_tables": {"DDPM_HALO_GN_IN_KERNEL": "0"},
+    "upsample_then_conv": {"DDPM_UPCONV_PHASES": "0"},
+    "upsample_phases_im2col": {"DDPM_UPCONV_HALO": "0"},
+    "attention_unfused_tc": {"DDPM_ATTN_FUSED": "0"},
+    "attention_unfused_cuda_cores": {"DDPM_ATTN_FUSED": "0", "DDPM_ATTN_TC": "0"},
+    "single_cta_conv_tiles": {"DDPM_CONV_HALO": "0", "DDPM_CONV_2CTA": "0"},
+    "head_tail_cuda_cores": {"DDPM_CONV_IN_SCALAR": "1", "DDPM_TAPS_SCALAR": "1"},
+    "halo_default_tiles": {"DDPM_HALO_FINE": "0"},
+    "halo_n128_tiles": {"DDPM_HALO_FINE": "1"},
+}
+
+
+@pytest.mark.parametrize("switch", list(ENGINE_SWITCHES))
+@pytest.mark.parametrize("name", ["fashionmnist_1x32x32", "native_1x28x28"])
+def test_engine_fallback_paths_match_oracle(name, switch, monkeypatch):
+    case = FWD_CASES[name]
+    for k, v in ENGINE_SWITCHES[switch].items():
+        monkeypatch.setenv(k, v)
+    ref, ours = _pair(case["sd"], case["ch"])
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(case["shape"], generator=g)
+    t = torch.randint(0, 1000, (case["shape"][0],), generator=g)
+    with torch.no_grad():
+        want = ref(x, t)
+    got = ours(x.cuda(), timesteps=t.cuda()).cpu()
+    assert _rel(got, want) < 4e-3, (name, switch, _rel(got, want))
+
+
+def test_chain_graph_replay_equals_per_kernel_launches(monkeypatch):
+    """A PLMS chain replayed as one CUDA graph (the policy for launch-bound batches) runs the same kernels on the same
+    buffers as the per-kernel launch sequence: identical bits. An engine's first chain always runs un-captured, the
+    second is captured, the third replayed - so each variant runs the chain three times from the same start, in the
+    same buffer (the graph is keyed on the buffer addresses)."""
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("DDPM_CHAIN_GRAPH", flag)
+        _, ours = _pair(2, 1)
+        _, sched = _make_scheds()
+        g = torch.Generator().manual_seed(13)
+        x = torch.randn((2, 1, 32, 32), generator=g).cuda()
+        a = torch.empty_like(x)
+        for _ in range(3):
+            a.copy_(x)
+            sched.reset_chain()
+            sched.run_chain(ours, a, [40, 30, 20, 10])
+        outs[flag] = a.cpu()
+    assert bool(torch.isfinite(outs["0"]).all())
+    assert torch.equal(outs["0"], outs["1"])

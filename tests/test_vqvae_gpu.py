@@ -197,3 +197,18 @@ def test_wide_3d_model_falls_back_to_the_im2col_kernel_where_the_halo_kernel_can
     got_img = ours.decode_samples(want_idx.cuda()).cpu()
     rel = ((got_img - want_img).norm() / want_img.norm()).item()
     assert rel < 3e-3, rel
+
+
+@pytest.mark.parametrize("cfg,size", [(CFG3D, 8), (CFG2D, 16)])
+def test_decoder_on_the_im2col_kernel_only(cfg, size, monkeypatch):
+    """DDPM_VQ_HALO=0 keeps every VQ-VAE conv on the im2col-tile kernel (the route shapes the halo kernel cannot stage
+    take): same decoder parity bound as the default route."""
+    monkeypatch.setenv("DDPM_VQ_HALO", "0")
+    ref, ours = _pair(cfg)
+    g = torch.Generator().manual_seed(5)
+    idx = torch.randint(0, cfg["num_embeddings"], (2,) + (size,) * cfg["spatial_dims"], generator=g)
+    with torch.no_grad():
+        want = ref.decode_samples(idx)
+    got = ours.decode_samples(idx.cuda()).cpu()
+    rel = ((got - want).norm() / want.norm()).item()
+    assert rel < 3e-3, rel
