@@ -154,3 +154,46 @@ def test_t_start_shards_union_equals_full_grid():
                                                       beta_end=0.0195, plms_state="carry"), "cuda")
     with pytest.raises(ValueError):
         carry.score_batch(x0, skip, t_indices=[0])
+
+
+FULL_SIZE = {
+    # name: golden file, spatial dims, channels, batch bench.py runs the workload at, score keys
+    "config2_fmnist_b1184": ("recon_cfg2_skip4_carry.pt", 2, 1, 1184, ("mse", "perceptual_difference")),
+    "config4_celeba64_b296": ("recon_cfg4_skip1_first12.pt", 2, 3, 296, ("mse", "perceptual_difference")),
+    "config5_latent_b592": ("recon_cfg5_latent.pt", 3, 128, 592, ("mse",)),
+}
+
+
+@pytest.mark.parametrize("name", list(FULL_SIZE))
+def test_full_bench_batch_by_replication(name):
+    """The BASELINE configurations at the batch bench.py measures them at (every UNet level a whole number of waves of
+    the default tilings - kernels the small parity batches never launch). A chain only couples an image to itself, so
+    the golden's images tiled to the bench batch (noise tiled the same way) must give, for EVERY (image, t-start) pair of
+    the big batch, the oracle's score of the image it replicates: 1e-3 relative (north_star), the t grid bit-exact, and
+    the replicas of one image agree with each other to fp32 reduction noise. config 2 runs its whole benched grid
+    (25 t-starts, carry: 1250 UNet evaluations at batch 1184 - exactly one bench step)."""
+    from ddpm_ood_b200.reconstruction import BatchReconstructor, ReconConfig
+
+    fname, sd, ch, batch, keys = FULL_SIZE[name]
+    gold = torch.load(GOLDEN / fname)
+    base = gold["x0"].shape[0]
+    reps = batch // base
+    assert base * reps == batch
+    ours, pl = _models(sd, ch, gold["weight_seed"], with_pl=len(keys) > 1)
+    cfg = ReconConfig(beta_schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0195,
+                      plms_state=gold["plms_state"], num_inference_steps=gold["num_inference_steps"],
+                      spatial_dimension=sd)
+    eng = BatchReconstructor(ours, pl, cfg, "cuda")
+    tile = (reps,) + (1,) * (gold["x0"].dim() - 1)
+    x0 = gold["x0"].repeat(tile)  # image b of the big batch replicates golden image b % base
+    got = eng.score_batch(x0, gold["skip"], noise_fn=lambda i, t: gold["noise"][i].repeat(tile).cuda(),
+                          t_starts=gold["t_starts"])
+    assert torch.equal(got["t"], gold["t"])
+    n_t = len(gold["t"])
+    for key in keys:
+        g_ = got[key].cpu().reshape(n_t, reps, base)   # [t, replica, golden image]
+        w = gold[key].reshape(n_t, 1, base)
+        rel = ((g_ - w).abs() / w.abs().clamp_min(1e-12)).max().item()
+        assert rel < 1e-3, (name, key, rel)
+        spread = ((g_ - g_[:, :1]).abs() / g_[:, :1].abs().clamp_min(1e-12)).max().item()
+        assert spread < 1e-5, (name, key, spread)
