@@ -975,6 +975,7 @@ int UNet::forward(const float* x, const long long* timesteps, int t_uniform, flo
                   float* sample) {
     if (!finalized_) { set_error("unet: forward before finalize()"); return 10; }
     if (cfg_.spatial_dims == 2 && D != 1) { set_error("unet: 2-D model needs D == 1"); return 2; }
+    if (N < 1 || D < 1 || H < 1 || W < 1) { set_error("unet: empty input (N=%d, D=%d, H=%d, W=%d)", N, D, H, W); return 2; }
     auto key = std::make_tuple(N, D, H, W, ws);
     auto it = plans_.find(key);
     if (it == plans_.end()) {

@@ -279,6 +279,8 @@ class DiffusionModelUNet(nn.Module):
             raise ValueError("timesteps must have one entry per batch item")
         out_shape = (n, self.out_channels) + tuple(x.shape[2:])
         out = torch.empty(out_shape, dtype=torch.float32, device=x.device)
+        if n == 0:  # an empty batch is an empty result (what torch modules return), not a launch
+            return out
         with torch.cuda.device(x.device):
             ws = self._workspace(n, d, h, w, x.device)
             _lib.check(

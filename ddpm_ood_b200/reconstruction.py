@@ -151,6 +151,9 @@ class BatchReconstructor:
             grid_pos = [int(i) for i in t_indices]
             starts = starts[torch.tensor(grid_pos, dtype=torch.long)] if grid_pos else starts[:0]
         images_original = images_original.to(self.device, non_blocking=True).float().contiguous()
+        if images_original.shape[0] == 0:  # an empty batch scores nothing (the reference's loop would emit no rows)
+            empty = torch.empty((len(starts), 0), dtype=torch.float32, device=self.device)
+            return {"t": starts.clone(), "t_index": grid_pos, "perceptual_difference": empty, "mse": empty.clone()}
         images = images_original if self.vqvae_model is None else self.vqvae_model.encode_stage_2_inputs(images_original)
         if self.latent_pad:
             images = F.pad(input=images, pad=self.latent_pad, mode="constant", value=0)
