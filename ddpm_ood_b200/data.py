@@ -3,7 +3,7 @@
 The reference's loader (src/data/get_train_and_val_dataloader.py) is MONAI-based host I/O and is OUT OF SCOPE for the
 accelerated path; this module only restates enough of it for `reconstruct.py` to run end to end
 on the reference's own `.npy` datasets (src/data/get_computer_vision_datasets.py writes [H,W] uint8 for grayscale and
-[3,H,W] uint8 for colour) and to reproduce its multi-GPU image partition (get_train_and_val_dataloader.py:21-31).
+[3,H,W] uint8 for colour) and on single-file NIfTI-1 volumes (the 3-D medical datasets; `nifti.py`), and to reproduce its multi-GPU image partition (get_train_and_val_dataloader.py:21-31).
 Batches have the reference's structure: {"image": Tensor[B,C,...], "image_meta_dict": {"filename_or_obj": [...]}}.
 """
 from __future__ import annotations
@@ -58,8 +58,14 @@ def _load(path: str) -> np.ndarray:
         return np.load(path)
     if path.endswith(".pt"):
         return torch.load(path, map_location="cpu").numpy()
-    raise NotImplementedError(f"only .npy/.pt images are supported by the minimal loader (got {path}); NIfTI needs "
-                              f"nibabel, which is not part of this environment")
+    if path.endswith(".nii") or path.endswith(".nii.gz"):
+        # what monai's LoadImaged + EnsureChannelFirstd give for a NIfTI volume (get_train_and_val_dataloader.py:68-69):
+        # the file's own axis order, a 4th (modality) axis - BraTS stores four modalities in one file - moved first
+        from .nifti import read_nifti
+
+        arr = read_nifti(path)
+        return np.moveaxis(arr, -1, 0) if arr.ndim == 4 else arr
+    raise NotImplementedError(f"the minimal loader reads .npy / .pt / .nii / .nii.gz images (got {path})")
 
 
 def _transform(arr: np.ndarray, is_grayscale: bool, spatial_dimension: int, image_size, image_roi, add_vflip: bool,
