@@ -4,7 +4,9 @@ spatial=False)` (lpips==0.1.4, requirements.txt:1) and of the reference's wrappe
 PARITY UNPINNED for the third-party part: the `lpips` package and its pretrained AlexNet / linear-head weights are not
 available; weights here are synthetic and shared with the CUDA path. The wrapper part
 (PerceptualLoss) follows the reference file line by line, including the 2.5-D loop that overwrites instead of
-accumulating (perceptual_loss.py:113-122), so only the last view counts.
+accumulating (perceptual_loss.py:113-122), so only the last view counts; it IS pinned: the reference's own
+perceptual_loss.py, executed with this file's LPIPS in place of the absent package, gives the same values in 2-D and
+2.5-D (tests/test_reference_loop_pin_cpu.py).
 
 Parameter names mirror lpips' (`net.slice{1..5}.{idx}.weight`, `lin{k}.model.1.weight`) so real weights would load.
 """

@@ -2,8 +2,11 @@
 src/trainers/reconstruct.py:96-204, restated with injected noise (the reference draws `torch.randn_like` per t-start and
 never seeds it) and without the data loader / plotting.
 
-PARITY UNPINNED beyond the t-start grid: the UNet, scheduler and LPIPS arithmetic it calls are restatements
-(oracle/unet.py, oracle/pndm.py, oracle/lpips.py).
+THE LOOP IS PINNED: tests/test_reference_loop_pin_cpu.py loads the reference's own `Reconstruct.get_scores` from
+/root/reference (absent third-party imports replaced by the oracle's classes) and requires its CSV rows to equal this
+function's output bit for bit on the same model, images and noise (32 x 32 and 28 x 28, SNR shift, b_scale).
+PARITY UNPINNED for what the loop calls: the UNet, scheduler and LPIPS arithmetic are restatements (oracle/unet.py,
+oracle/pndm.py, oracle/lpips.py) of packages that are not available here.
 """
 from __future__ import annotations
 
