@@ -258,3 +258,67 @@ def test_reference_base_trainer_construction_equals_ours(monkeypatch, over):
         a, b = getattr(ref.scheduler, name), getattr(ours.scheduler, name)
         assert torch.equal(a, b), name  # the reference's own SNR-shift loop ran on the left-hand side
     assert ref.scheduler.prediction_type == ours.scheduler.prediction_type
+
+
+# ------------------------------------------------------------------------------------------------ Reconstruct.__init__ / reconstruct()
+def _recon_args(tmp, **over):
+    import argparse
+
+    base = dict(batch_size=7, validation_ids="/d/fmnist_val.csv", in_ids="/d/fmnist_test.csv",
+                out_ids="/d/mnist_test.csv,/d/fmnist_test_vflip.csv,/d/kmnist_test_hflip.csv", augmentation=1,
+                num_workers=3, cache_data=0, drop_last=0, first_n=None, first_n_val="5", is_grayscale=1,
+                spatial_dimension=2, image_roi=None, run_val=1, run_in=1, run_out=1, inference_skip_factor=8)
+    base.update(over)
+    return argparse.Namespace(**base)
+
+
+def _fake_rows(loader, dataset_name, skip):
+    return [{"filename": f"{dataset_name}{i}", "type": dataset_name, "t": 10 + 10 * skip * i,
+             "perceptual_difference": 0.125 * i + len(loader[1]["validation_ids"]), "mse": 0.5 ** i} for i in range(4)]
+
+
+def test_reference_reconstruct_orchestration_equals_ours(reference_modules, monkeypatch, tmp_path):
+    """`Reconstruct.__init__` and `Reconstruct.reconstruct` of the reference executed next to ours, both with a recording
+    loader factory and a canned `get_scores`: the same loader arguments for the val / in / out sets (flip variants
+    included), the same (dataset_name, skip) sequence, and byte-identical `ood/results_*.csv` files under the same names."""
+    _, rec_mod = reference_modules
+    import ddpm_ood_b200.trainers.reconstruct as ours_mod
+
+    outs = {}
+    for side, mod in (("ref", rec_mod), ("ours", ours_mod)):
+        calls, score_calls = [], []
+        run_dir = tmp_path / side
+        run_dir.mkdir()
+
+        def base_init(self, args, run_dir=run_dir):
+            self.found_checkpoint, self.run_dir, self.image_size = True, run_dir, None
+            self.device, self.do_latent_pad = "cpu", False
+
+        def factory(calls=calls, **kw):
+            calls.append(kw)
+            return ("loader", kw)
+
+        def get_scores(self, loader, dataset_name, skip, score_calls=score_calls):
+            score_calls.append((dataset_name, skip, loader[1]["validation_ids"]))
+            return _fake_rows(loader, dataset_name, skip)
+
+        monkeypatch.setattr(mod.BaseTrainer, "__init__", base_init, raising=False)
+        monkeypatch.setattr(mod, "get_training_data_loader", factory)
+        monkeypatch.setattr(mod.Reconstruct, "get_scores", get_scores)
+        args = _recon_args(tmp_path)
+        tr = mod.Reconstruct(args)
+        tr.reconstruct(args)
+        files = {p.name: p.read_bytes() for p in sorted((run_dir / "ood").iterdir())}
+        outs[side] = (calls, score_calls, files)
+
+    ref_calls, ref_scores, ref_files = outs["ref"]
+    our_calls, our_scores, our_files = outs["ours"]
+    assert len(ref_calls) == len(our_calls) == 5  # val, in, three out sets
+    for r, o in zip(ref_calls, our_calls):
+        assert {k: o[k] for k in r} == r                                  # every argument the reference passes, same value
+        assert set(o) - set(r) <= {"rank", "world_size", "device"}        # ours adds only the sharding / ingest knobs
+    assert ref_scores == our_scores
+    assert [s[0] for s in ref_scores] == ["val", "in", "out", "out", "out"]
+    assert sorted(ref_files) == ["results_fmnist_vflip.csv", "results_in.csv", "results_kmnist_hflip.csv",
+                                 "results_mnist.csv", "results_val.csv"]
+    assert ref_files == our_files
