@@ -29,6 +29,16 @@ def _module(name, **attrs):
     return m
 
 
+def _restore(saved, names):
+    """Undo what a test put into sys.modules under `names` - and nothing else (modules that real packages imported
+    lazily in the meantime must stay, or their classes exist twice)."""
+    for k in names:
+        if k in saved:
+            sys.modules[k] = saved[k]
+        else:
+            sys.modules.pop(k, None)
+
+
 def _load(name, path, package=None):
     spec = importlib.util.spec_from_file_location(name, path)
     mod = importlib.util.module_from_spec(spec)
@@ -72,10 +82,7 @@ def reference_modules(monkeypatch):
         rec_mod = _load("src.trainers.reconstruct", REF / "src" / "trainers" / "reconstruct.py", package="src.trainers")
         yield pl_mod, rec_mod
     finally:
-        for k in list(sys.modules):
-            if k not in saved:
-                del sys.modules[k]
-        sys.modules.update(saved)
+        _restore(saved, list(stubs) + ["src.losses", "src.losses.perceptual_loss", "src.trainers.reconstruct"])
 
 
 class _Passthrough:
@@ -229,10 +236,7 @@ def test_reference_base_trainer_construction_equals_ours(monkeypatch, over):
         ref_base = _load("ref_base_trainer", REF / "src" / "trainers" / "base.py")
         ref = ref_base.BaseTrainer(_args(**over))
     finally:
-        for k in list(sys.modules):
-            if k not in saved:
-                del sys.modules[k]
-        sys.modules.update(saved)
+        _restore(saved, list(stubs) + ["src.networks", "src.networks.passthrough_vqvae", "ref_base_trainer"])
 
     import ddpm_ood_b200.trainers.base as ours_base
 
@@ -322,3 +326,28 @@ def test_reference_reconstruct_orchestration_equals_ours(reference_modules, monk
     assert sorted(ref_files) == ["results_fmnist_vflip.csv", "results_in.csv", "results_kmnist_hflip.csv",
                                  "results_mnist.csv", "results_val.csv"]
     assert ref_files == our_files
+
+
+def test_reference_get_data_dicts_equals_ours(tmp_path, capsys):
+    """`get_data_dicts` of the reference (src/data/get_train_and_val_dataloader.py:8-34; its monai imports stubbed, they
+    are not touched without a process group) against ours: the one-row CSV of paths, `first_n`, the printed count."""
+    saved = dict(sys.modules)
+    monai = _module("monai", transforms=_module("monai.transforms"))
+    data = _module("monai.data", CacheDataset=None, Dataset=None, ThreadDataLoader=None, partition_dataset=None)
+    sys.modules.update({"monai": monai, "monai.transforms": monai.transforms, "monai.data": data})
+    try:
+        ref = _load("ref_loader", REF / "src" / "data" / "get_train_and_val_dataloader.py")
+    finally:
+        _restore(saved, ["monai", "monai.transforms", "monai.data", "ref_loader"])
+    from ddpm_ood_b200 import data as ours
+
+    paths = [f"/data/set/img_{i:03d}.npy" for i in range(11)] + ["/data/set/with space.nii.gz"]
+    ids = tmp_path / "ids.csv"
+    ids.write_text(",".join(paths) + "\n")
+    for first_n in (False, 5, 12, 40):
+        want = ref.get_data_dicts(str(ids), shuffle=False, first_n=first_n)
+        out_ref = capsys.readouterr().out
+        got = ours.get_data_dicts(str(ids), first_n=first_n)
+        out_ours = capsys.readouterr().out
+        assert got == want
+        assert out_ours == out_ref  # "Found N subjects."
