@@ -351,3 +351,27 @@ def test_reference_get_data_dicts_equals_ours(tmp_path, capsys):
         out_ours = capsys.readouterr().out
         assert got == want
         assert out_ours == out_ref  # "Found N subjects."
+
+
+def test_oracle_alexnet_trunk_equals_torchvision():
+    """lpips' `alexnet` feature extractor IS torchvision's `alexnet().features`, tapped after ReLU 1..5 (slices [0:2],
+    [2:5], [5:8], [8:10], [10:12]) [3P-RECALL for the tap points]; the trunk itself is pinned here against the installed
+    torchvision: same parameter shapes under the same indices, identical feature maps from shared weights."""
+    tv = pytest.importorskip("torchvision")
+    from oracle.lpips import AlexSlices
+
+    net = tv.models.alexnet(weights=None).features.eval()
+    ours = AlexSlices().eval()
+    tv_params = {k: v for k, v in net.state_dict().items()}
+    sd = {}
+    for name, p in ours.state_dict().items():  # "slice2.3.weight" -> features "3.weight"
+        key = name.split(".", 1)[1]
+        assert tv_params[key].shape == p.shape, name
+        sd[name] = tv_params[key]
+    assert len(sd) == len(tv_params) == 10
+    ours.load_state_dict(sd)
+    x = torch.randn((2, 3, 64, 64), generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        got = ours(x)
+        for k, end in enumerate((2, 5, 8, 10, 12)):
+            assert torch.equal(got[k], net[:end](x)), k
