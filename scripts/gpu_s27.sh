@@ -1,5 +1,6 @@
 #!/bin/bash
 # K-split accumulators for the narrow small-batch tiles: parity, batch-8 / batch-32 bench, in-kernel timeline.
+# (historical record: the K-split accumulator code this measured was removed afterwards - profiles/r02_halo_small_batch_s26.md)
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_conv_gemm_gpu.py -q -x > gpurun_out/s27_conv.log 2>&1; echo "conv rc=$?"; tail -3 gpurun_out/s27_conv.log
 for f in 0 1 2; do

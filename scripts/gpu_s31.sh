@@ -1,5 +1,6 @@
 #!/bin/bash
 # K-split accumulators on the narrow tiles, now that the issue stream is short: parity, A/B against the no-split variant.
+# (historical record: the K-split accumulator code this measured was removed afterwards - profiles/r02_halo_small_batch_s26.md)
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_conv_gemm_gpu.py -q -x > gpurun_out/s31_conv.log 2>&1; echo "conv rc=$?"; tail -3 gpurun_out/s31_conv.log
 V=ddpm_ood_b200/csrc/experiments/variants/lib_nosplit.so

@@ -1,5 +1,6 @@
 #!/bin/bash
 # A/B on one box: nine-tap loop of the wide tilings unrolled with constant row offsets (variant) vs the generic loop.
+# (historical record: the unrolled nine-tap variant this measured was not adopted - profiles/r02_halo_small_batch_s26.md)
 mkdir -p gpurun_out
 V=ddpm_ood_b200/csrc/experiments/variants/lib_unroll9.so
 DDPM_LIB_VARIANT=$V timeout 600 python -m pytest tests/test_conv_gemm_gpu.py -q -x -k "halo" > gpurun_out/s34_conv.log 2>&1; echo "conv(variant) rc=$?"; tail -2 gpurun_out/s34_conv.log
